@@ -1,0 +1,265 @@
+/*
+ * b200flow.h — C ABI of libb200flow.so: the B200 (sm_100a) hot path of the
+ * flow-classification pipeline that biagiom/spark-network-traffic-classifier
+ * drives through pyspark.ml.
+ *
+ * The reference has no FFI of its own: its operator API is the pyspark.ml
+ * Estimator/Transformer contract exercised at
+ *   code/network_traffic_classifier_kdd99.py:34-37,45-46,64,79,82,86-91
+ *   code/network_traffic_classifier_cicids17.py:41-46,68,83,86,90-95
+ * Each entry point below names the MLlib operator whose
+ * arithmetic it replaces.  The Python shim in
+ * spark-network-traffic-classifier_b200/pyspark binds these through ctypes
+ * (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer owned by the caller unless the
+ *    parameter name ends in _host; the library allocates no persistent memory;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *    nothing synchronises the host;
+ *  - return value: 0 = ok, negative = error (b200flow_last_error() has text);
+ *  - rows are `int64_t`; everything else that indexes columns/bins/classes is int32;
+ *  - RNG: Philox4x32-10, keyed by (seed, purpose) and counted by GLOBAL row /
+ *    (tree,node) so results do not depend on how rows are sharded over GPUs
+ *    (spec in DESIGN.md §RNG).
+ */
+#ifndef B200FLOW_H
+#define B200FLOW_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FLOW_OK            0
+#define B200FLOW_ERR_ARG      -1
+#define B200FLOW_ERR_CUDA     -2
+#define B200FLOW_ERR_LIMIT    -3
+
+/* element types of dense matrices handed to / produced by the library */
+#define B200FLOW_F32 0
+#define B200FLOW_F64 1
+
+/* ---- encode plan: one descriptor per OUTPUT slot of the assembled vector ---- */
+#define B200FLOW_SRC_F32    0  /* numeric field stored as float   */
+#define B200FLOW_SRC_F64    1  /* numeric field stored as double  */
+#define B200FLOW_SRC_I32    2  /* numeric field stored as int32   */
+#define B200FLOW_SRC_INDEX  3  /* int32 dictionary code -> StringIndexer rank, emitted as a number */
+#define B200FLOW_SRC_ONEHOT 4  /* int32 dictionary code -> rank; emits (rank == hot) ? 1 : 0       */
+
+typedef struct b200flow_slot {
+    int32_t kind;      /* B200FLOW_SRC_*                                             */
+    int32_t src_off;   /* byte offset of the source field inside one raw record      */
+    int32_t lut_off;   /* INDEX/ONEHOT: first entry of this column's code->rank LUT  */
+    int32_t lut_len;   /* INDEX/ONEHOT: dictionary size; code outside [0,len) or rank<0 = invalid */
+    int32_t hot;       /* ONEHOT: the rank this slot lights up for                   */
+    int32_t reserved;
+    double  mean;      /* StandardScaler withMean: subtracted first (0.0 = off)      */
+    double  scale;     /* StandardScaler withStd: 1/sigma, or 0 when sigma==0 (1.0 = off) */
+} b200flow_slot;       /* 40 bytes */
+
+const char* b200flow_last_error(void);
+int  b200flow_version(void);
+
+/* ------------------------------------------------------------------ encode ---
+ * R1  StringIndexer.fit  (kdd99.py:34-37, cicids17.py:45): per-code counts of one
+ * int32 dictionary-code field of the raw records.  counts[K] (int64) is ADDED to
+ * (caller zeroes; multi-GPU: allreduce the K counts).  Codes outside [0,K) are ignored. */
+int b200flow_category_counts(const void* records, int64_t n_rows, int32_t row_bytes,
+                             int32_t src_off, int32_t K, int64_t* counts, void* stream);
+
+/* R2+R3+R3b+R3c  StringIndexerModel.transform + OneHotEncoder + StandardScaler +
+ * VectorAssembler.transform fused (kdd99.py:37,46; cicids17.py:42,46): raw AoS
+ * records -> dense row-major [n_rows, n_out] matrix (out_dtype F32/F64), computed
+ * in fp64: out = (value - mean) * scale.
+ *   plan        device array of n_out b200flow_slot
+ *   lut         device int32 LUT pool (rank per code, -1 = unseen), may be NULL
+ *   label_*     optional label column: int32 code field -> rank (int32) in label_out
+ *               (label_off < 0: no label); an unseen label marks the row invalid
+ *   valid_out   optional uint8[n_rows]: 0 when the row has an unseen code, or
+ *               (check_nan != 0) a NaN numeric field  (handleInvalid="skip"/"error")
+ * Full tiles move global->shared->global with TMA bulk copies; records and the
+ * output must be 16-byte aligned. */
+int b200flow_encode(const void* records, int64_t n_rows, int32_t row_bytes,
+                    const b200flow_slot* plan, int32_t n_out,
+                    const int32_t* lut, int32_t lut_total,
+                    int32_t label_off, int32_t label_lut_off, int32_t label_lut_len,
+                    int32_t check_nan,
+                    void* out, int32_t out_dtype, int32_t* label_out, uint8_t* valid_out,
+                    void* stream);
+
+/* R3c  StandardScaler.fit: per-column shifted power sums of a dense [n, D] matrix
+ * (leading dimension ld elements): sum[d] += Σ(x-shift[d]), sumsq[d] += Σ(x-shift[d])².
+ * shift may be NULL (=0).  Two calls (shift = 0, then shift = mean) give the
+ * corrected two-pass variance; multi-GPU: allreduce the 2·D doubles between them. */
+int b200flow_column_moments(const void* x, int32_t dtype, int64_t n_rows, int32_t D, int64_t ld,
+                            const double* shift, double* sum, double* sumsq, void* stream);
+
+/* --------------------------------------------------------------- tree prep ---
+ * R4  RandomForest.findSplits, sampling half: Bernoulli(keep_threshold / 2^32) row
+ * sample keyed by (seed, global row); gathers the sampled rows of the dense feature
+ * matrix into a COLUMN-major fp64 buffer sample[F][cap]; *n_sampled is advanced
+ * atomically (caller zeroes; rows beyond cap are counted but not stored). */
+int b200flow_sample_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, int64_t ld,
+                         uint64_t seed, uint64_t keep_threshold, int64_t row_offset,
+                         double* sample, int64_t cap, int32_t* n_sampled, void* stream);
+
+/* R4  findSplitsForContinuousFeature: for every continuous feature (arity[f]==0)
+ * sort its n_s samples (in place, sample[f*cap .. +n_s)), run-length the distinct
+ * values and walk MLlib's stride rule -> thresholds[f*(max_bins-1) ..], n_thr[f].
+ * Categorical features (arity>0) get n_thr = 0.  scratch: F * pow2ceil(n_s) doubles. */
+int b200flow_find_splits(double* sample, int64_t cap, int32_t n_s, int32_t F,
+                         const int32_t* arity, int32_t max_bins,
+                         double* thresholds, int32_t* n_thr, void* stream);
+
+/* R5  TreePoint.convertToTreeRDD/findBin: dense features (+ int32 labels, may be NULL)
+ * -> binned TreePoint records tp[n][tp_stride] (uint8): bytes [0,F) = bin per feature
+ * (continuous: lower_bound over thresholds; categorical: (int)x), byte F = label.
+ * bad_rows (int32, caller zeroes) counts rows with a categorical value outside
+ * [0,arity) or non-integral (MLlib raises). */
+int b200flow_bin_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, int64_t ld,
+                      const double* thresholds, const int32_t* n_thr, const int32_t* arity,
+                      int32_t max_bins, const int32_t* labels,
+                      uint8_t* tp, int32_t tp_stride, int32_t* bad_rows, void* stream);
+
+/* R6  BaggedPoint.convertToBaggedRDD, pass 1: per (tree, block of 1024 rows) number of
+ * rows with Poisson weight > 0.  poisson_cdf: 32 uint32 thresholds, weight = #{k: r >= cdf[k]};
+ * NULL = no bagging (weight 1 for every row, numTrees==1).  blk_cnt[T][n_blocks] int32. */
+int b200flow_bag_count(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows,
+                       const uint32_t* poisson_cdf, int32_t* blk_cnt, void* stream);
+
+/* R6 pass 2: given blk_off = exclusive scan of blk_cnt (int64, tree-major), write the
+ * bagged entries (row index, weight) of every tree in row order. */
+int b200flow_bag_fill(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows,
+                      const uint32_t* poisson_cdf, const int64_t* blk_off,
+                      int32_t* ent_row, uint8_t* ent_w, void* stream);
+
+/* exclusive prefix sum utilities used by the trainer (single launch, any n) */
+int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* out,
+                                       int64_t* total, void* stream);
+
+/* ------------------------------------------------------------ tree growing ---
+ * One LEVEL of every tree is processed at once.  An active node is a "slot":
+ *   slot_tree[s], slot_nid[s] (MLlib node id: root 1, children 2i/2i+1),
+ *   slot_node[s]  index of the node in the forest node pool,
+ *   seg_begin/seg_end[s]  its bagged entries inside ent_row/ent_w.                */
+
+/* per-node feature subsets (RandomForest.selectNodesToSplit): m of F features by a
+ * partial Fisher-Yates keyed by (seed, tree, nid), sorted ascending -> subset[s*m..].
+ * m == F gives the identity. */
+int b200flow_feature_subsets(uint64_t seed, int32_t n_slots, const int32_t* slot_tree,
+                             const uint32_t* slot_nid, int32_t F, int32_t m,
+                             uint16_t* subset, void* stream);
+
+/* R7  findBestSplits/binSeqOp — HOT LOOP A.  hist[s][j][bin][class] += w for every entry
+ * of slot s and every j < m (feature subset[s*m+j]).  hist (uint32) must be zeroed by
+ * the caller; layout stride = m * n_bins * C.  chunk_off = exclusive scan over slots of
+ * ceil(len/chunk_rows) (int64[n_slots+1]); the grid is one CTA per chunk. */
+int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
+                        const int32_t* ent_row, const uint8_t* ent_w,
+                        int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
+                        const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
+                        const uint16_t* subset, int32_t m, int32_t n_bins, int32_t C,
+                        uint32_t* hist, void* stream);
+
+/* split record written by score_level, one per slot */
+typedef struct b200flow_split {
+    int32_t  feat;        /* feature index, -1 = no valid split (leaf)                   */
+    int32_t  kind;        /* 0 continuous (left iff bin <= bin_thr), 1 categorical (mask) */
+    int32_t  bin_thr;     /* continuous: split index s (threshold = thresholds[f][s])     */
+    int32_t  flags;       /* bit0 node is leaf, bit1 left child leaf, bit2 right child leaf */
+    double   gain;
+    double   impurity;    /* of this node                                                 */
+    uint64_t mask[4];     /* categorical: bit c set = category c goes left                */
+} b200flow_split;         /* 64 bytes */
+
+/* R8  binsToBestSplit / calculateImpurityStats / Gini — HOT LOOP B.  Reads the (all-reduced)
+ * histograms, writes split[s], the node's own class counts and both children's class counts
+ * (uint32 [n_slots][C] each).  feat_bins[f] = number of bins of feature f; feat_kind[f]:
+ * 0 continuous, 1 ordered categorical, 2 unordered categorical (bins = categories).
+ * level/max_depth/min_instances/min_info_gain as in MLlib's Strategy. */
+int b200flow_score_level(const uint32_t* hist, int32_t n_slots, const uint16_t* subset,
+                         int32_t m, int32_t n_bins, int32_t C,
+                         const int32_t* feat_bins, const int32_t* feat_kind,
+                         int32_t level, int32_t max_depth, int32_t min_instances,
+                         double min_info_gain,
+                         b200flow_split* split, uint32_t* node_counts,
+                         uint32_t* left_counts, uint32_t* right_counts, void* stream);
+
+/* forest node pool (SoA, all trees in one pool; roots are nodes 0..T-1) */
+typedef struct b200flow_node {
+    int32_t feat;      /* -1 = leaf                                      */
+    int32_t kind_bin;  /* kind<<16 | bin_thr                             */
+    int32_t left;      /* pool index of left child; right = left + 1     */
+    uint32_t nid;      /* MLlib node id                                  */
+} b200flow_node;       /* 16 bytes */
+
+/* grows the pool by one level: for each slot writes its node record (+ mask, counts), creates
+ * two children per split (counts from left/right_counts), and emits the next level's slots for
+ * the non-leaf children (next_* arrays, capacity 2*n_slots; next_parent = parent slot*2+side).
+ * counters[0] = node pool size (in/out), counters[1] = number of next slots (out). */
+int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, const uint32_t* slot_nid,
+                        const int32_t* slot_node, const b200flow_split* split,
+                        const uint32_t* node_counts, const uint32_t* left_counts,
+                        const uint32_t* right_counts, int32_t C,
+                        b200flow_node* nodes, uint64_t* node_mask, uint32_t* pool_counts,
+                        int32_t* node_tree, int64_t pool_capacity,
+                        int32_t* next_tree, uint32_t* next_nid, int32_t* next_node,
+                        int32_t* next_parent, int64_t* counters, void* stream);
+
+/* routes every entry of every split slot to its child: left entries grow up from seg_begin,
+ * right entries grow down from seg_end inside the same range of the destination buffers;
+ * cursors[s*2+{0,1}] (int32, caller zeroes) end as (#left, #right).  Entries of children
+ * that are leaves are dropped. */
+int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
+                             const int32_t* ent_row, const uint8_t* ent_w,
+                             int32_t* ent_row_out, uint8_t* ent_w_out,
+                             int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
+                             const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
+                             const b200flow_split* split, int32_t* cursors, void* stream);
+
+/* segment table of the next level from the parents' ranges and the partition cursors */
+int b200flow_next_segments(int32_t n_next, const int32_t* next_parent,
+                           const int64_t* seg_begin, const int64_t* seg_end,
+                           const int32_t* cursors, int64_t* next_begin, int64_t* next_end,
+                           void* stream);
+
+/* leaf payloads: prob[node][k] = counts[k] / Σcounts (fp64 true division), 0 if Σ == 0 */
+int b200flow_finalize_forest(int64_t n_nodes, const uint32_t* pool_counts, int32_t C,
+                             double* leaf_prob, void* stream);
+
+/* ----------------------------------------------------------------- predict ---
+ * R9  RandomForestClassificationModel.transform — HOT LOOP C.  Walks all T trees for every
+ * binned row; raw[n][C] = Σ_t leaf_prob (tree order, fp64), prob = raw/Σraw, pred = first argmax.
+ * dt_mode != 0 (DecisionTreeClassifier): raw = leaf class counts.  raw/prob may be NULL. */
+int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_rows,
+                     const b200flow_node* nodes, const uint64_t* node_mask,
+                     const double* leaf_prob, const uint32_t* pool_counts,
+                     int32_t T, int32_t C, int32_t dt_mode,
+                     double* raw, double* prob, double* pred, void* stream);
+
+/* R10 MulticlassMetrics: confusion matrix cm[label*C + pred] += 1 (int64, caller zeroes).
+ * pred / label are fp64 columns (as in the prediction DataFrame). */
+int b200flow_confusion(const double* pred, const double* label, int64_t n_rows, int32_t C,
+                       int64_t* cm, void* stream);
+
+/* -------------------------------------------------- either side of the path ---
+ * DataFrame.randomSplit (kdd99.py:52, cicids17.py:56): split id per row from a uniform keyed
+ * by (seed, global row): first k with u < cum_bounds[k] (n_splits <= 8).  out uint8[n]. */
+int b200flow_random_split(uint64_t seed, int64_t row_offset, int64_t n_rows,
+                          const double* cum_bounds_host, int32_t n_splits, uint8_t* split_id,
+                          void* stream);
+
+/* stable row compaction (where / handleInvalid="skip" / one randomSplit part):
+ * keeps rows with flag[i] == want; out_rows gets the kept rows' row_bytes-sized records in
+ * order.  Two calls: counts per block + scan happen inside (scratch: int64[n_blocks+1],
+ * n_blocks = ceil(n/1024)); *n_kept (device int64) receives the count. */
+int b200flow_compact_rows(const void* rows, int64_t n_rows, int32_t row_bytes,
+                          const uint8_t* flag, int32_t want, void* out_rows,
+                          int64_t* scratch, int64_t* n_kept, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FLOW_H */
