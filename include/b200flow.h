@@ -198,7 +198,9 @@ typedef struct b200flow_node {
 /* grows the pool by one level: for each slot writes its node record (+ mask, counts), creates
  * two children per split (counts from left/right_counts), and emits the next level's slots for
  * the non-leaf children (next_* arrays, capacity 2*n_slots; next_parent = parent slot*2+side).
- * counters[0] = node pool size (in/out), counters[1] = number of next slots (out). */
+ * counters: int64[4] {node pool size (in/out), number of next slots (out), overflow flag (out: 1 =
+ * pool_capacity too small, nothing written), pool size before the call} followed by
+ * 2*ceil(n_slots/256) int32 of scratch. */
 int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, const uint32_t* slot_nid,
                         const int32_t* slot_node, const b200flow_split* split,
                         const uint32_t* node_counts, const uint32_t* left_counts,
@@ -253,8 +255,8 @@ int b200flow_random_split(uint64_t seed, int64_t row_offset, int64_t n_rows,
 
 /* stable row compaction (where / handleInvalid="skip" / one randomSplit part):
  * keeps rows with flag[i] == want; out_rows gets the kept rows' row_bytes-sized records in
- * order.  Two calls: counts per block + scan happen inside (scratch: int64[n_blocks+1],
- * n_blocks = ceil(n/1024)); *n_kept (device int64) receives the count. */
+ * order.  Counting per block and the scan happen inside; scratch: (n_blocks+1) int64 followed by
+ * n_blocks int32, n_blocks = ceil(n/1024); *n_kept (device int64) receives the count. */
 int b200flow_compact_rows(const void* rows, int64_t n_rows, int32_t row_bytes,
                           const uint8_t* flag, int32_t want, void* out_rows,
                           int64_t* scratch, int64_t* n_kept, void* stream);

@@ -1,0 +1,409 @@
+"""RandomForest / DecisionTree trainer and batch predictor on libb200flow.so.
+
+Host logic only (the level loop MLlib runs on the Spark driver: RandomForest.run);
+every per-row / per-node computation is a kernel in csrc/forest.cu, csrc/treeprep.cu, csrc/predict.cu.
+Reference call sites: kdd99.py:61,64,79,82; cicids17.py:65,68,83,86.
+
+Rows may be sharded over ranks (one process per GPU): each rank holds a contiguous block of rows
+starting at global index `row_offset`; the only data-path collective is one all-reduce (sum, int32)
+of the per-node histograms per tree level (R7r).  Integer sums + counter-based RNG make the model
+bit-identical for any number of ranks.
+"""
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NODE_DTYPE, SPLIT_DTYPE, B200FlowError, call, ptr
+
+CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_level (<= 2048)
+HIST_BUDGET_BYTES = 4 << 30        # node-group cap for the histogram buffer (MLlib: maxMemoryInMB)
+
+
+@dataclass
+class ForestParams:
+    """MLlib Param defaults."""
+    num_trees: int = 20
+    max_depth: int = 5
+    max_bins: int = 32
+    min_instances_per_node: int = 1
+    min_info_gain: float = 0.0
+    feature_subset_strategy: str = "auto"
+    subsampling_rate: float = 1.0
+    impurity: str = "gini"
+    seed: int = 0
+    bootstrap: bool = True         # False for DecisionTreeClassifier (numTrees == 1)
+
+
+def tp_stride(F):
+    return (F + 1 + 15) // 16 * 16
+
+
+def poisson_cdf_table(rate=1.0):
+    """32 uint32 thresholds floor(CDF(k)*2^32), saturating."""
+    out = np.empty(32, np.uint32)
+    term = math.exp(-rate); cdf = 0.0
+    for k in range(32):
+        cdf += term
+        out[k] = min(int(math.floor(cdf * 4294967296.0)), 0xFFFFFFFF)
+        term = term * rate / (k + 1)
+    return out
+
+
+def build_metadata(n_rows, F, num_classes, arity, max_bins, num_trees, strategy="auto"):
+    """DecisionTreeMetadata.buildMetadata (A.1): (maxPossibleBins, feat_kind[F], numFeaturesPerNode)."""
+    arity = np.asarray(arity, np.int32)
+    mpb = int(min(max_bins, n_rows))
+    if mpb > 256:
+        raise B200FlowError("maxBins > 256 is not supported (bins are stored as uint8)")
+    if arity.size and int(arity.max()) > mpb:
+        raise ValueError("DecisionTree requires maxBins (= %d) to be at least as large as the number of values in each "
+                         "categorical feature, but a categorical feature has %d values. Consider removing this and other "
+                         "categorical features with a large number of values, or add more training examples."
+                         % (mpb, int(arity.max())))
+    kind = np.zeros(F, np.int32)
+    U = int(math.floor(math.log(mpb // 2 + 1) / math.log(2.0) + 1)) if num_classes > 2 else 0
+    for f in range(F):
+        if arity[f] > 1:
+            kind[f] = 2 if (num_classes > 2 and arity[f] <= U) else 1
+        elif arity[f] == 1:
+            kind[f] = 1
+    s = str(strategy)
+    if s == "auto":
+        s = "all" if num_trees == 1 else "sqrt"
+    if s == "all": m = F
+    elif s == "sqrt": m = int(math.ceil(math.sqrt(F)))
+    elif s == "log2": m = max(1, int(math.ceil(math.log(F) / math.log(2))))
+    elif s == "onethird": m = int(math.ceil(F / 3.0))
+    else:
+        try:
+            v = float(s)
+        except ValueError:
+            raise ValueError("Supported featureSubsetStrategy values: auto, all, onethird, sqrt, log2, (0.0-1.0], [1-n]; got %r" % strategy)
+        m = int(v) if ("." not in s and v >= 1) else int(math.ceil(v * F))
+    return mpb, kind, max(1, min(m, F))
+
+
+def _i32(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(dev)
+
+
+class ForestModel:
+    """Device-resident forest: one node pool for all trees (roots = nodes 0..T-1)."""
+
+    def __init__(self, T, C, F, arity, max_bins, thresholds, n_thr, nodes, node_mask, pool_counts, node_tree,
+                 leaf_prob, node_gain, n_nodes, dt_mode):
+        self.T, self.C, self.F, self.max_bins, self.dt_mode = T, C, F, max_bins, dt_mode
+        self.arity = np.asarray(arity, np.int32)
+        self.thresholds, self.n_thr = thresholds, n_thr          # device [F, max_bins-1] f64, [F] i32
+        self.nodes, self.node_mask, self.pool_counts = nodes, node_mask, pool_counts
+        self.node_tree, self.leaf_prob, self.node_gain, self.n_nodes = node_tree, leaf_prob, node_gain, n_nodes
+        self._arity_dev = _i32(self.arity, thresholds.device)
+
+    def bin(self, x, labels=None):
+        """TreePoint.findBin (R5) with this model's thresholds: dense [n, F] -> uint8 [n, stride]."""
+        n, F = x.shape
+        if F != self.F:
+            raise ValueError("expected %d features, got %d" % (self.F, F))
+        stride = tp_stride(F)
+        tp = torch.empty((n, stride), dtype=torch.uint8, device=x.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=x.device)
+        call("b200flow_bin_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), ptr(self.thresholds), ptr(self.n_thr),
+             ptr(self._arity_dev), self.max_bins, ptr(labels), ptr(tp), stride, ptr(bad))
+        return tp, bad
+
+    def predict_binned(self, tp, want_raw=True, want_prob=True):
+        n = tp.shape[0]
+        dev = tp.device
+        raw = torch.empty((n, self.C), dtype=torch.float64, device=dev) if want_raw else None
+        prob = torch.empty((n, self.C), dtype=torch.float64, device=dev) if want_prob else None
+        pred = torch.empty(n, dtype=torch.float64, device=dev)
+        call("b200flow_predict", ptr(tp), tp.shape[1], n, ptr(self.nodes), ptr(self.node_mask), ptr(self.leaf_prob),
+             ptr(self.pool_counts), self.T, self.C, 1 if self.dt_mode else 0, ptr(raw), ptr(prob), ptr(pred))
+        return raw, prob, pred
+
+    def predict(self, x, want_raw=True, want_prob=True):
+        """RandomForestClassificationModel.transform (R9): rawPrediction, probability, prediction."""
+        tp, _ = self.bin(x)
+        return self.predict_binned(tp, want_raw, want_prob)
+
+    def export(self):
+        """Canonical host copy, nodes ordered by (tree, MLlib node id) — what parity tests compare."""
+        n = self.n_nodes
+        nodes = self.nodes[:n].cpu().numpy().view(NODE_DTYPE).reshape(-1)
+        tree = self.node_tree[:n].cpu().numpy()
+        counts = self.pool_counts[:n].cpu().numpy().view(np.uint32).astype(np.int64)
+        mask = (self.node_mask[:n].cpu().numpy().view(np.uint64) if self.node_mask is not None
+                else np.zeros((n, 4), np.uint64))
+        gain = self.node_gain[:n].cpu().numpy()
+        order = np.lexsort((nodes["nid"], tree))
+        is_leaf = (nodes["feat"] < 0).astype(np.int32)
+        kind = np.where(is_leaf == 1, 0, nodes["kind_bin"] >> 16).astype(np.int32)
+        bin_thr = np.where(is_leaf == 1, 0, nodes["kind_bin"] & 0xffff).astype(np.int32)
+        mask = np.where(is_leaf[:, None] == 1, 0, mask).astype(np.uint64)
+        return dict(tree=tree[order], nid=nodes["nid"][order], feat=nodes["feat"][order], kind=kind[order],
+                    bin_thr=bin_thr[order], is_leaf=is_leaf[order], gain=gain[order], mask=mask[order],
+                    counts=counts[order])
+
+    def feature_importances(self):
+        """TreeEnsembleModel.featureImportances: per tree Σ gain·count over internal nodes, normalised per tree,
+        averaged over trees and normalised (host-side, from the canonical export)."""
+        ex = self.export()
+        imp = np.zeros(self.F)
+        for t in range(self.T):
+            sel = (ex["tree"] == t) & (ex["is_leaf"] == 0)
+            v = np.zeros(self.F)
+            np.add.at(v, ex["feat"][sel], ex["gain"][sel] * ex["counts"][sel].sum(1))
+            if v.sum() > 0:
+                imp += v / v.sum()
+        return imp / imp.sum() if imp.sum() > 0 else imp
+
+
+def _gather_sample(sample, n_s, cap, F, group):
+    """all-gather the per-rank findSplits samples (column-major [F, cap]) into one buffer."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    counts = [torch.zeros(1, dtype=torch.int64, device=sample.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n_s], dtype=torch.int64, device=sample.device), group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    mine = sample.view(F, cap)[:, :mx].contiguous()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    tot = sum(counts)
+    new_cap = 1
+    while new_cap < max(tot, 2):
+        new_cap <<= 1
+    out = torch.empty((F, new_cap), dtype=torch.float64, device=sample.device)
+    pos = 0
+    for p, c in zip(parts, counts):
+        out[:, pos:pos + c] = p[:, :c]; pos += c
+    return out.view(-1), tot, new_cap
+
+
+def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
+    """RandomForest.run (R4-R8) on a dense CUDA feature matrix x [n, F] (f32/f64) and int32 labels [n].
+
+    arity[f] = 0 for a continuous feature, else the number of categories (from the StringIndexer's
+    nominal metadata).  With `group`, x/labels are this rank's row shard starting at
+    global row `row_offset`.  Returns a ForestModel."""
+    import torch.distributed as dist
+    _lib.require_cuda()
+    p = params
+    if p.impurity != "gini":
+        raise B200FlowError("impurity=%r: only 'gini' is implemented on the B200 path" % p.impurity)
+    if not (0 <= p.max_depth <= 30):
+        raise ValueError("maxDepth must be in [0, 30], got %d" % p.max_depth)
+    dev = x.device
+    n, F = x.shape
+    C = int(num_classes)
+    T = int(p.num_trees)
+    seed = int(p.seed) & 0xFFFFFFFFFFFFFFFF
+    n_global = n
+    if group is not None:
+        t = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, group=group)
+        n_global = int(t.item())
+    mpb, kind, m = build_metadata(n_global, F, C, arity, p.max_bins, T, p.feature_subset_strategy)
+    arity = np.asarray(arity, np.int32)
+    arity_dev = _i32(arity, dev)
+    labels = labels.to(torch.int32).contiguous()
+
+    # ---- R4 findSplits: Bernoulli row sample keyed by global row, sort + stride walk on device
+    has_cont = bool((arity == 0).any())
+    frac = min(1.0, max(mpb * mpb, 10000) / float(n_global)) if has_cont else 1.0
+    keep = int(frac * 4294967296.0)
+    expect = n if frac >= 1.0 else int(n * frac + 6.0 * math.sqrt(max(n * frac, 1.0)) + 64)
+    cap = 1
+    while cap < max(min(expect, n), 2):
+        cap <<= 1
+    sample = torch.empty(F * cap, dtype=torch.float64, device=dev)
+    n_s_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    thresholds = torch.zeros((F, mpb - 1), dtype=torch.float64, device=dev)
+    n_thr = torch.zeros(F, dtype=torch.int32, device=dev)
+    if has_cont:
+        call("b200flow_sample_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), seed, keep, int(row_offset),
+             ptr(sample), cap, ptr(n_s_dev))
+        n_s = int(n_s_dev.item())
+        if n_s > cap:
+            raise B200FlowError("findSplits sample overflow (%d > %d)" % (n_s, cap))
+        if group is not None:
+            sample, n_s, cap = _gather_sample(sample, n_s, cap, F, group)
+        call("b200flow_find_splits", ptr(sample), cap, n_s, F, ptr(arity_dev), mpb, ptr(thresholds), ptr(n_thr))
+    del sample
+
+    # ---- R5 binning
+    stride = tp_stride(F)
+    tp = torch.empty((n, stride), dtype=torch.uint8, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("b200flow_bin_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), ptr(thresholds), ptr(n_thr), ptr(arity_dev),
+         mpb, ptr(labels), ptr(tp), stride, ptr(bad))
+    feat_bins = torch.where(arity_dev > 0, arity_dev, n_thr + 1).to(torch.int32).contiguous()
+    head = torch.cat([bad, feat_bins.max().reshape(1).to(torch.int32)]).cpu()
+    if int(head[0]) != 0:
+        raise ValueError("categorical feature value outside [0, arity) or non-integral in %d cells" % int(head[0]))
+    n_bins = int(head[1])
+    feat_kind = _i32(kind, dev)
+
+    # ---- R6 bagging: count, scan, fill -> entries of every tree in row order
+    bagging = p.bootstrap and T > 1
+    cdf = torch.from_numpy(poisson_cdf_table(p.subsampling_rate).view(np.int32).copy()).to(dev) if bagging else None
+    nb = (n + 1023) // 1024
+    blk_cnt = torch.zeros(max(T * nb, 1), dtype=torch.int32, device=dev)
+    blk_off = torch.zeros(T * nb + 1, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    if n > 0:
+        call("b200flow_bag_count", seed, T, int(row_offset), n, ptr(cdf), ptr(blk_cnt))
+    call("b200flow_exclusive_scan_i32_to_i64", ptr(blk_cnt), T * nb, ptr(blk_off), ptr(total))
+    E = int(total.item())
+    ent_row = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    ent_w = torch.empty(max(E, 1), dtype=torch.uint8, device=dev)
+    ent_row2 = torch.empty_like(ent_row); ent_w2 = torch.empty_like(ent_w)
+    if n > 0:
+        call("b200flow_bag_fill", seed, T, int(row_offset), n, ptr(cdf), ptr(blk_off), ptr(ent_row), ptr(ent_w))
+
+    # ---- node pool
+    cap_nodes = max(4096, 4 * T)
+    nodes = torch.zeros((cap_nodes, 16), dtype=torch.uint8, device=dev)
+    use_mask = bool((kind > 0).any())
+    node_mask = torch.zeros((cap_nodes, 4), dtype=torch.int64, device=dev) if use_mask else None
+    pool_counts = torch.zeros((cap_nodes, C), dtype=torch.int32, device=dev)
+    node_tree = torch.zeros(cap_nodes, dtype=torch.int32, device=dev)
+    node_gain = torch.zeros(cap_nodes, dtype=torch.float64, device=dev)
+    root = np.zeros(T, NODE_DTYPE); root["feat"] = -1; root["left"] = -1; root["nid"] = 1
+    nodes[:T] = torch.from_numpy(root.view(np.uint8).reshape(T, 16).copy()).to(dev)
+    node_tree[:T] = torch.arange(T, dtype=torch.int32, device=dev)
+    pool_size = T
+
+    def grow_pool(need):
+        nonlocal nodes, node_mask, pool_counts, node_tree, node_gain, cap_nodes
+        if need <= cap_nodes:
+            return
+        new_cap = cap_nodes
+        while new_cap < need:
+            new_cap *= 2
+        def ext(t, shape_tail):
+            nt = torch.zeros((new_cap,) + shape_tail, dtype=t.dtype, device=dev)
+            nt[:cap_nodes] = t
+            return nt
+        nodes = ext(nodes, (16,)); pool_counts = ext(pool_counts, (C,)); node_tree = ext(node_tree, ())
+        node_gain = ext(node_gain, ())
+        if node_mask is not None:
+            node_mask = ext(node_mask, (4,))
+        cap_nodes = new_cap
+
+    # ---- level 0 slots: one per tree
+    slot_tree = torch.arange(T, dtype=torch.int32, device=dev)
+    slot_nid = torch.ones(T, dtype=torch.int32, device=dev)
+    slot_node = torch.arange(T, dtype=torch.int32, device=dev)
+    idx = torch.arange(T, dtype=torch.int64, device=dev) * nb
+    seg_begin = blk_off[idx].contiguous()
+    seg_end = blk_off[idx + nb].contiguous()
+    n_slots = T
+    level = 0
+    per_slot_hist = m * n_bins * C * 4
+    group_slots = max(1, HIST_BUDGET_BYTES // per_slot_hist)
+    stats = dict(levels=0, slots=0, entries=E, hist_launches=0)
+
+    while n_slots > 0:
+        grow_pool(pool_size + 2 * n_slots)
+        subset = torch.empty((n_slots, m), dtype=torch.int16, device=dev)
+        call("b200flow_feature_subsets", seed, n_slots, ptr(slot_tree), ptr(slot_nid), F, m, ptr(subset))
+        lens = seg_end - seg_begin
+        nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()
+        chunk_off = torch.empty(n_slots + 1, dtype=torch.int64, device=dev)
+        call("b200flow_exclusive_scan_i32_to_i64", ptr(nch), n_slots, ptr(chunk_off), ptr(total))
+        n_chunks = int(total.item())
+        split = torch.empty((n_slots, 64), dtype=torch.uint8, device=dev)
+        node_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
+        left_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
+        right_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
+        g_rows = min(group_slots, n_slots)
+        hist = torch.empty(g_rows * m * n_bins * C, dtype=torch.int32, device=dev)
+        for g0 in range(0, n_slots, group_slots):
+            g1 = min(n_slots, g0 + group_slots)
+            gs = g1 - g0
+            h = hist[:gs * m * n_bins * C]
+            h.zero_()
+            if g0 == 0 and g1 == n_slots:
+                coff, gch = chunk_off, n_chunks
+            else:
+                coff = (chunk_off[g0:g1 + 1] - chunk_off[g0]).contiguous()
+                gch = int((chunk_off[g1] - chunk_off[g0]).item())
+            # R7 HOT LOOP A
+            call("b200flow_hist_level", ptr(tp), stride, F, ptr(ent_row), ptr(ent_w), gs, ptr(seg_begin[g0:g1]),
+                 ptr(seg_end[g0:g1]), ptr(coff), gch, CHUNK_ROWS, ptr(subset[g0:g1]), m, n_bins, C, ptr(h))
+            stats["hist_launches"] += 1
+            if group is not None:                       # R7r: the one data-path collective
+                dist.all_reduce(h, group=group)
+            # R8 HOT LOOP B
+            call("b200flow_score_level", ptr(h), gs, ptr(subset[g0:g1]), m, n_bins, C, ptr(feat_bins), ptr(feat_kind),
+                 level, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(split[g0:g1]),
+                 ptr(node_counts[g0:g1]), ptr(left_counts[g0:g1]), ptr(right_counts[g0:g1]))
+        del hist
+        # grow the pool by this level's children and emit the next level's slots
+        nblk = (n_slots + 255) // 256
+        counters = torch.zeros(4 + nblk + 1, dtype=torch.int64, device=dev)
+        counters[0] = pool_size
+        next_tree = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
+        next_nid = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
+        next_node = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
+        next_parent = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
+        call("b200flow_grow_level", n_slots, ptr(slot_tree), ptr(slot_nid), ptr(slot_node), ptr(split), ptr(node_counts),
+             ptr(left_counts), ptr(right_counts), C, ptr(nodes), ptr(node_mask), ptr(pool_counts), ptr(node_tree),
+             cap_nodes, ptr(next_tree), ptr(next_nid), ptr(next_node), ptr(next_parent), ptr(counters))
+        node_gain[slot_node.long()] = split.view(torch.float64)[:, 2]
+        cnt = counters[:3].cpu()
+        if int(cnt[2]) != 0:
+            raise B200FlowError("node pool overflow (capacity %d)" % cap_nodes)
+        pool_size, n_next = int(cnt[0]), int(cnt[1])
+        stats["levels"] += 1; stats["slots"] += n_slots
+        if n_next == 0:
+            break
+        # route every entry to its child segment
+        cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
+        call("b200flow_partition_level", ptr(tp), stride, ptr(ent_row), ptr(ent_w), ptr(ent_row2), ptr(ent_w2), n_slots,
+             ptr(seg_begin), ptr(seg_end), ptr(chunk_off), n_chunks, CHUNK_ROWS, ptr(split), ptr(cursors))
+        next_begin = torch.empty(n_next, dtype=torch.int64, device=dev)
+        next_end = torch.empty(n_next, dtype=torch.int64, device=dev)
+        call("b200flow_next_segments", n_next, ptr(next_parent), ptr(seg_begin), ptr(seg_end), ptr(cursors),
+             ptr(next_begin), ptr(next_end))
+        ent_row, ent_row2 = ent_row2, ent_row
+        ent_w, ent_w2 = ent_w2, ent_w
+        slot_tree, slot_nid, slot_node = next_tree[:n_next], next_nid[:n_next], next_node[:n_next]
+        seg_begin, seg_end = next_begin, next_end
+        n_slots = n_next
+        level += 1
+
+    leaf_prob = torch.empty((pool_size, C), dtype=torch.float64, device=dev)
+    call("b200flow_finalize_forest", pool_size, ptr(pool_counts), C, ptr(leaf_prob))
+    model = ForestModel(T, C, F, arity, mpb, thresholds, n_thr, nodes, node_mask, pool_counts, node_tree, leaf_prob,
+                        node_gain, pool_size, dt_mode=(T == 1 and not p.bootstrap))
+    model.train_stats = stats
+    model.feat_kind, model.feat_bins, model.n_bins, model.m = kind, feat_bins, n_bins, m
+    return model
+
+
+def confusion_matrix(pred, label, C):
+    """MulticlassMetrics counting (R10): int64 [C, C], cm[label, pred]."""
+    cm = torch.zeros((C, C), dtype=torch.int64, device=pred.device)
+    call("b200flow_confusion", ptr(pred.contiguous()), ptr(label.contiguous()), pred.shape[0], C, ptr(cm))
+    return cm
+
+
+def metrics_from_confusion(cm):
+    """MulticlassMetrics (A.8) + macro-F1 from the C x C counts (host, C^2 numbers)."""
+    cm = np.asarray(cm, np.float64)
+    N = cm.sum()
+    sup = cm.sum(1); predl = cm.sum(0); tp = np.diag(cm)
+    labs = sup > 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = np.where(predl > 0, tp / predl, 0.0)
+        r = np.where(sup > 0, tp / sup, 0.0)
+        f1 = np.where(p + r > 0, 2 * p * r / (p + r), 0.0)
+    w = sup / N if N else sup
+    return dict(accuracy=float(tp[labs].sum() / N) if N else 0.0,
+                weightedPrecision=float((p * w)[labs].sum()), weightedRecall=float((r * w)[labs].sum()),
+                f1=float((f1 * w)[labs].sum()), macroF1=float(f1[labs].mean()) if labs.any() else 0.0)

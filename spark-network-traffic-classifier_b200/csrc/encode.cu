@@ -1,0 +1,291 @@
+// encode.cu — the fused row-parallel encode path.
+//
+// Replaces, for the reference call sites kdd99.py:34-37,45-46 and cicids17.py:41-46, MLlib's
+// StringIndexer.fit (category counts), StringIndexerModel.transform (code -> rank lookup),
+// OneHotEncoder (expand), StandardScaler (fit moments + scale) and VectorAssembler (concat)
+// with ONE pass over the raw AoS flow records.
+//
+// encode kernel, data movement (HBM-bound; algorithmic bytes/row = row_bytes + n_out*sizeof(out) + 4):
+//   HBM --cp.async.bulk (TMA, UBLKCP) + mbarrier--> smem record tile [R x row_bytes], NS-deep ring
+//   threads: one fixed OUTPUT slot per thread, rows strided -> smem out tile [R x n_out] (bank-conflict free)
+//   smem out tile --cp.async.bulk store (bulk_group)--> HBM, double buffered
+// Arithmetic is fp64 ((v - mean) * scale, no FMA contraction) and rounded once to the output type.
+#include "common.cuh"
+
+namespace b200flow {
+
+// ------------------------------------------------------------------ R1 category counts
+__global__ void __launch_bounds__(256) category_counts_kernel(const uint8_t* __restrict__ rec, int64_t n, int row_bytes,
+                                                              int src_off, int K, unsigned long long* counts,
+                                                              int use_smem) {
+    extern __shared__ uint32_t sh_cnt[];
+    if (use_smem) {
+        for (int i = threadIdx.x; i < K; i += blockDim.x) sh_cnt[i] = 0;
+        __syncthreads();
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int code = __ldg((const int*)(rec + i * row_bytes + src_off));
+        if (code >= 0 && code < K) {
+            if (use_smem) atomicAdd(&sh_cnt[code], 1u);
+            else atomicAdd(&counts[code], 1ull);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < K; i += blockDim.x)
+            if (sh_cnt[i]) atomicAdd(&counts[i], (unsigned long long)sh_cnt[i]);
+    }
+}
+
+// ------------------------------------------------------------------ fused encode
+struct EncodeArgs {
+    const uint8_t* records; int64_t n_rows; int row_bytes;
+    const b200flow_slot* plan; int n_out;
+    const int32_t* lut; int lut_total; int lut_in_smem;
+    int label_off, label_lut_off, label_lut_len, check_nan;
+    void* out; int32_t* label_out; uint8_t* valid_out;
+    int R;            // rows per tile (multiple of 4)
+    int in_stride;    // bytes per input stage (128-aligned)
+    int out_stride;   // bytes per output stage (128-aligned)
+};
+
+constexpr int kEncStages = 4;     // TMA load ring depth
+constexpr int kEncThreads = 256;
+
+__device__ __forceinline__ double enc_read_field(const uint8_t* rowp, int kind, int off) {
+    if (kind == B200FLOW_SRC_F32) return (double)(*(const float*)(rowp + off));
+    if (kind == B200FLOW_SRC_F64) {
+        const uint32_t* p = (const uint32_t*)(rowp + off);   // 4-byte aligned reads: fields need not be 8-aligned
+        return __hiloint2double((int)p[1], (int)p[0]);
+    }
+    return (double)(*(const int32_t*)(rowp + off));          // I32
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // layout: [in ring][out x2][mbar x4][badtag 2*R][plan][lut]
+    uint8_t* in_base = smem;
+    uint8_t* out_base = in_base + (size_t)kEncStages * a.in_stride;
+    uint64_t* mbar = (uint64_t*)(out_base + 2 * (size_t)a.out_stride);
+    int32_t* badtag = (int32_t*)(mbar + kEncStages);
+    b200flow_slot* plan_sh = (b200flow_slot*)(badtag + 2 * a.R + ((2 * a.R) & 1));   // keep 8-byte alignment
+    int32_t* lut_sh = (int32_t*)(plan_sh + a.n_out);
+
+    const int tid = threadIdx.x, bd = blockDim.x;
+    const int R = a.R, n_out = a.n_out, row_bytes = a.row_bytes;
+    const int64_t n_tiles = (a.n_rows + R - 1) / R;
+    const uint32_t tile_in_bytes = (uint32_t)R * row_bytes;
+    const uint32_t tile_out_bytes = (uint32_t)R * n_out * sizeof(OUT);
+
+    if (tid == 0) {
+        for (int s = 0; s < kEncStages; ++s) mbar_init(&mbar[s], 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < n_out * (int)(sizeof(b200flow_slot) / 4); i += bd) ((uint32_t*)plan_sh)[i] = ((const uint32_t*)a.plan)[i];
+    if (a.lut_in_smem) for (int i = tid; i < a.lut_total; i += bd) lut_sh[i] = a.lut[i];
+    for (int i = tid; i < 2 * R; i += bd) badtag[i] = 0;
+    __syncthreads();
+    const int32_t* lut = a.lut_in_smem ? lut_sh : a.lut;
+
+    auto issue_load = [&](int64_t tile, int s) {
+        int64_t rows = a.n_rows - tile * R;
+        if (rows >= R) {
+            mbar_arrive_expect_tx(&mbar[s], tile_in_bytes);
+            bulk_g2s(in_base + (size_t)s * a.in_stride, a.records + tile * (int64_t)tile_in_bytes, tile_in_bytes, &mbar[s]);
+        } else {
+            mbar_arrive(&mbar[s]);      // ragged last tile: loaded cooperatively below
+        }
+    };
+    if (tid == 0)
+        for (int s = 0; s < kEncStages; ++s) {
+            int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+            if (t < n_tiles) issue_load(t, s);
+        }
+
+    // thread -> output slot mapping: one fixed slot per thread when n_out <= blockDim
+    const bool fixed = n_out <= bd;
+    const int rp = fixed ? bd / n_out : 1;
+    const int d0 = fixed ? tid % n_out : tid;
+    const int r0 = fixed ? tid / n_out : 0;
+    const int dstep = fixed ? n_out : bd;
+    const bool active = fixed ? (tid < rp * n_out) : true;
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kEncStages, o = it & 1;
+        const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
+        const int64_t row_base = tile * R;
+        const int rows = (int)min((int64_t)R, a.n_rows - row_base);
+        const bool full = rows == R;
+        uint8_t* in_t = in_base + (size_t)s * a.in_stride;
+        OUT* out_t = (OUT*)(out_base + (size_t)o * a.out_stride);
+        int32_t* bad = badtag + o * R;
+        const int tag = it + 1;
+
+        mbar_wait(&mbar[s], ph);
+        if (!full) {
+            const uint32_t* src = (const uint32_t*)(a.records + row_base * row_bytes);
+            for (int i = tid; i < rows * row_bytes / 4; i += bd) ((uint32_t*)in_t)[i] = __ldg(src + i);
+            __syncthreads();
+        }
+
+        if (active) {
+            for (int d = d0; d < n_out; d += dstep) {
+                const b200flow_slot sl = plan_sh[d];
+                for (int r = r0; r < rows; r += rp) {
+                    const uint8_t* rowp = in_t + r * row_bytes;
+                    double v;
+                    if (sl.kind <= B200FLOW_SRC_I32) {
+                        v = enc_read_field(rowp, sl.kind, sl.src_off);
+                        if (a.check_nan && v != v) bad[r] = tag;
+                    } else {
+                        int code = *(const int32_t*)(rowp + sl.src_off);
+                        int rank = (code >= 0 && code < sl.lut_len) ? lut[sl.lut_off + code] : -1;
+                        if (rank < 0) bad[r] = tag;
+                        v = (sl.kind == B200FLOW_SRC_INDEX) ? (double)rank : (rank == sl.hot ? 1.0 : 0.0);
+                    }
+                    out_t[r * n_out + d] = (OUT)((v - sl.mean) * sl.scale);
+                }
+            }
+        }
+        if (a.label_off >= 0 && tid < rows) {      // label column: one thread per row, straight to HBM
+            int code = *(const int32_t*)(in_t + tid * row_bytes + a.label_off);
+            int rank = (code >= 0 && code < a.label_lut_len) ? lut[a.label_lut_off + code] : -1;
+            if (rank < 0) bad[tid] = tag;
+            if (a.label_out) a.label_out[row_base + tid] = rank;
+        }
+        if (a.label_off >= 0 && bd < rows) {       // R > blockDim: remaining rows
+            for (int r = tid + bd; r < rows; r += bd) {
+                int code = *(const int32_t*)(in_t + r * row_bytes + a.label_off);
+                int rank = (code >= 0 && code < a.label_lut_len) ? lut[a.label_lut_off + code] : -1;
+                if (rank < 0) bad[r] = tag;
+                if (a.label_out) a.label_out[row_base + r] = rank;
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();                            // A: tile computed, input stage s consumed
+        if (tid == 0) {
+            if (full) { bulk_s2g((OUT*)a.out + row_base * n_out, out_t, tile_out_bytes); bulk_commit(); }
+            int64_t next = tile + (int64_t)kEncStages * gridDim.x;
+            if (next < n_tiles) issue_load(next, s);
+            bulk_wait_read<1>();                    // the store issued one tile ago has drained its buffer
+        }
+        if (!full) {
+            OUT* dst = (OUT*)a.out + row_base * n_out;
+            for (int i = tid; i < rows * n_out; i += bd) dst[i] = out_t[i];
+        }
+        if (a.valid_out) for (int r = tid; r < rows; r += bd) a.valid_out[row_base + r] = (bad[r] != tag) ? 1 : 0;
+        __syncthreads();                            // B: out buffer (o^1) and badtag reusable
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
+// ------------------------------------------------------------------ R3c column moments
+template <typename T>
+__global__ void __launch_bounds__(256) column_moments_kernel(const T* __restrict__ x, int64_t n, int D, int64_t ld,
+                                                             const double* __restrict__ shift, double* sum, double* sumsq) {
+    extern __shared__ double sh_m[];     // [2][blockDim]
+    const int tid = threadIdx.x, bd = blockDim.x;
+    const int64_t rows_per_block = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t rb = (int64_t)blockIdx.x * rows_per_block, re = min(n, rb + rows_per_block);
+    for (int dbase = 0; dbase < D; dbase += bd) {
+        const int dn = min(bd, D - dbase);
+        const int rp = bd / dn;
+        double s = 0.0, q = 0.0;
+        if (tid < rp * dn) {
+            const int d = dbase + tid % dn;
+            const double sft = shift ? shift[d] : 0.0;
+            for (int64_t r = rb + tid / dn; r < re; r += rp) {
+                double v = (double)x[r * ld + d] - sft;
+                s += v; q += v * v;
+            }
+        }
+        sh_m[tid] = s; sh_m[bd + tid] = q;
+        __syncthreads();
+        if (tid < dn) {
+            for (int k = 1; k < rp; ++k) { s += sh_m[tid + k * dn]; q += sh_m[bd + tid + k * dn]; }
+            atomicAdd(&sum[dbase + tid], s);
+            atomicAdd(&sumsq[dbase + tid], q);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace b200flow
+
+using namespace b200flow;
+
+extern "C" int b200flow_category_counts(const void* records, int64_t n_rows, int32_t row_bytes, int32_t src_off,
+                                        int32_t K, int64_t* counts, void* stream) {
+    B2F_REQUIRE(records && counts && K > 0 && row_bytes >= 4 && src_off >= 0 && src_off + 4 <= row_bytes && (src_off & 3) == 0 &&
+                    (row_bytes & 3) == 0, "category_counts: bad arguments");
+    if (n_rows <= 0) return B200FLOW_OK;
+    int use_smem = K <= 8192;
+    int grid = grid_for(n_rows, 256 * 8, kNumSMs * 8);
+    category_counts_kernel<<<grid, 256, use_smem ? K * 4 : 0, (cudaStream_t)stream>>>(
+        (const uint8_t*)records, n_rows, row_bytes, src_off, K, (unsigned long long*)counts, use_smem);
+    return check_launch("category_counts");
+}
+
+extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_bytes, const b200flow_slot* plan,
+                               int32_t n_out, const int32_t* lut, int32_t lut_total, int32_t label_off,
+                               int32_t label_lut_off, int32_t label_lut_len, int32_t check_nan, void* out,
+                               int32_t out_dtype, int32_t* label_out, uint8_t* valid_out, void* stream) {
+    B2F_REQUIRE(records && plan && out, "encode: null pointer");
+    B2F_REQUIRE(n_out > 0 && n_out <= 4096 && row_bytes >= 4 && (row_bytes & 3) == 0, "encode: bad n_out/row_bytes");
+    B2F_REQUIRE(out_dtype == B200FLOW_F32 || out_dtype == B200FLOW_F64, "encode: bad out_dtype");
+    B2F_REQUIRE(((uintptr_t)records & 15) == 0 && ((uintptr_t)out & 15) == 0, "encode: records/out must be 16-byte aligned");
+    B2F_REQUIRE(label_off < 0 || (label_off + 4 <= row_bytes && (label_off & 3) == 0 && lut), "encode: bad label_off");
+    if (n_rows <= 0) return B200FLOW_OK;
+    const int osz = out_dtype == B200FLOW_F32 ? 4 : 8;
+    EncodeArgs a;
+    a.records = (const uint8_t*)records; a.n_rows = n_rows; a.row_bytes = row_bytes; a.plan = plan; a.n_out = n_out;
+    a.lut = lut; a.lut_total = lut ? lut_total : 0; a.lut_in_smem = (lut && lut_total > 0 && lut_total <= 4096) ? 1 : 0;
+    a.label_off = label_off; a.label_lut_off = label_lut_off; a.label_lut_len = label_lut_len; a.check_nan = check_nan;
+    a.out = out; a.label_out = label_out; a.valid_out = valid_out;
+    // tile rows: keep one CTA near 52 KB of smem so four CTAs share an SM (>= 64 KB of loads in flight per SM)
+    const int fixed_bytes = kEncStages * 8 + n_out * (int)sizeof(b200flow_slot) + (a.lut_in_smem ? a.lut_total * 4 : 0) + 1024;
+    const int per_row = row_bytes * kEncStages + n_out * osz * 2 + 8;
+    int budget = 52 * 1024 - fixed_bytes;
+    int R = budget > 0 ? budget / per_row : 0;
+    if (R < 4) R = 4;                    // very wide rows: fewer CTAs per SM
+    if (R > 512) R = 512;
+    R &= ~3;
+    if ((int64_t)R > ((n_rows + 3) & ~(int64_t)3)) R = (int)((n_rows + 3) & ~(int64_t)3);
+    a.R = R;
+    a.in_stride = (R * row_bytes + 127) & ~127;
+    a.out_stride = (R * n_out * osz + 127) & ~127;
+    size_t smem = (size_t)kEncStages * a.in_stride + 2 * (size_t)a.out_stride + kEncStages * 8 + (2 * R + 2) * 4 +
+                  (size_t)n_out * sizeof(b200flow_slot) + (a.lut_in_smem ? (size_t)a.lut_total * 4 : 0) + 16;
+    B2F_REQUIRE(smem <= 227 * 1024, "encode: record too wide for shared memory (row_bytes=%d n_out=%d)", row_bytes, n_out);
+    const int64_t n_tiles = (n_rows + R - 1) / R;
+    int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    int grid = (int)(n_tiles < (int64_t)kNumSMs * ctas_per_sm ? n_tiles : (int64_t)kNumSMs * ctas_per_sm);
+    cudaError_t e;
+    if (out_dtype == B200FLOW_F32) {
+        e = cudaFuncSetAttribute(encode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) encode_kernel<float><<<grid, kEncThreads, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(encode_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) encode_kernel<double><<<grid, kEncThreads, smem, (cudaStream_t)stream>>>(a);
+    }
+    if (e != cudaSuccess) { set_error("encode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
+    return check_launch("encode");
+}
+
+extern "C" int b200flow_column_moments(const void* x, int32_t dtype, int64_t n_rows, int32_t D, int64_t ld,
+                                       const double* shift, double* sum, double* sumsq, void* stream) {
+    B2F_REQUIRE(x && sum && sumsq && D > 0 && ld >= D, "column_moments: bad arguments");
+    B2F_REQUIRE(dtype == B200FLOW_F32 || dtype == B200FLOW_F64, "column_moments: bad dtype");
+    if (n_rows <= 0) return B200FLOW_OK;
+    int grid = grid_for(n_rows, 256, kNumSMs * 4);
+    size_t smem = 2 * 256 * sizeof(double);
+    if (dtype == B200FLOW_F32)
+        column_moments_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)x, n_rows, D, ld, shift, sum, sumsq);
+    else
+        column_moments_kernel<double><<<grid, 256, smem, (cudaStream_t)stream>>>((const double*)x, n_rows, D, ld, shift, sum, sumsq);
+    return check_launch("column_moments");
+}

@@ -1,0 +1,527 @@
+// forest.cu — the RandomForest level loop: per-node per-feature
+// integer histograms (HOT LOOP A), Gini split scoring (HOT LOOP B), pool growth and row routing.
+// Reference call sites: classifiers[c].fit(train_set) kdd99.py:79 / cicids17.py:83; upstream
+// algorithm: ml/tree/impl/RandomForest.scala findBestSplits/binsToBestSplit (restated in A.5).
+//
+// Data layout in HBM
+//   tp        [n_rows][stride] uint8   TreePoint: bin per feature, label at byte F (row = 3..5 x 16 B)
+//   ent_row/w [E] int32/uint8          bagged entries of all trees; a node owns a contiguous segment
+//   hist      [slots][m][n_bins][C] uint32   exact integer counts (weights are integer Poisson draws)
+// The row -> node relation is kept by PARTITIONING the entry array level by level (no per-row tree
+// walk as in MLlib); histograms are accumulated in shared memory per (node, chunk) and flushed
+// with sparse global REDs, so the multi-GPU all-reduce sees one dense uint32 buffer per level.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace b200flow {
+
+// ------------------------------------------------------------------ feature subsets
+constexpr int kMaxSubset = 128;
+
+__global__ void __launch_bounds__(128) feature_subsets_kernel(uint64_t seed, int n_slots, const int32_t* __restrict__ slot_tree,
+                                                              const uint32_t* __restrict__ slot_nid, int F, int m,
+                                                              uint16_t* subset) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    uint16_t* out = subset + (int64_t)s * m;
+    if (m >= F) { for (int i = 0; i < F; ++i) out[i] = (uint16_t)i; return; }
+    // virtual partial Fisher-Yates: only touched positions are materialised (pos[], val[])
+    uint16_t pos[kMaxSubset], val[kMaxSubset], pick[kMaxSubset];
+    int nt = 0;
+    const int tree = slot_tree[s]; const uint32_t nid = slot_nid[s];
+    uint4 r = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < m; ++i) {
+        if ((i & 3) == 0) r = philox_keyed(seed, PURPOSE_FEAT, (uint32_t)tree, nid, (uint32_t)(i >> 2), 0u);
+        uint32_t w = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+        int j = i + (int)(w % (uint32_t)(F - i));
+        int vi = i, vj = j, ki = -1, kj = -1;
+        for (int k = 0; k < nt; ++k) { if (pos[k] == i) { vi = val[k]; ki = k; } if (pos[k] == j) { vj = val[k]; kj = k; } }
+        pick[i] = (uint16_t)vj;                       // perm[i] <- old perm[j]
+        if (j != i) {                                  // perm[j] <- old perm[i]
+            if (kj >= 0) val[kj] = (uint16_t)vi; else { pos[nt] = (uint16_t)j; val[nt] = (uint16_t)vi; ++nt; }
+        }
+        (void)ki;
+    }
+    for (int i = 1; i < m; ++i) {                      // insertion sort ascending
+        uint16_t x = pick[i]; int k = i - 1;
+        while (k >= 0 && pick[k] > x) { pick[k + 1] = pick[k]; --k; }
+        pick[k + 1] = x;
+    }
+    for (int i = 0; i < m; ++i) out[i] = pick[i];
+}
+
+// chunk id -> (slot, chunk-in-slot) by binary search over the exclusive scan chunk_off[n_slots+1]
+__device__ __forceinline__ int find_slot(const int64_t* __restrict__ chunk_off, int n_slots, int64_t c) {
+    int lo = 0, hi = n_slots;                          // last s with chunk_off[s] <= c
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(chunk_off + mid) <= c) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// ------------------------------------------------------------------ R7 histogram build (HOT LOOP A)
+__global__ void __launch_bounds__(256) hist_level_kernel(const uint8_t* __restrict__ tp, int stride, int F,
+                                                         const int32_t* __restrict__ ent_row, const uint8_t* __restrict__ ent_w,
+                                                         int n_slots, const int64_t* __restrict__ seg_begin,
+                                                         const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off,
+                                                         int chunk_rows, const uint16_t* __restrict__ subset, int m, int n_bins,
+                                                         int C, uint32_t* hist) {
+    extern __shared__ uint32_t sh_hist[];              // [m][n_bins][C]
+    __shared__ int sh_feat[256];
+    const int64_t c = blockIdx.x;
+    const int s = find_slot(chunk_off, n_slots, c);
+    const int64_t b = seg_begin[s] + (c - chunk_off[s]) * chunk_rows;
+    const int64_t e = min(seg_end[s], b + chunk_rows);
+    const int hsz = m * n_bins * C;
+    for (int i = threadIdx.x; i < hsz; i += blockDim.x) sh_hist[i] = 0;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) sh_feat[j] = subset[(int64_t)s * m + j];
+    __syncthreads();
+    const int nbC = n_bins * C;
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const int row = ent_row[i];
+        const uint32_t w = ent_w[i];
+        const uint8_t* rec = tp + (int64_t)row * stride;
+        const int lab = rec[F];
+        for (int j = 0; j < m; ++j) {
+            const int bin = rec[sh_feat[j]];
+            atomicAdd(&sh_hist[j * nbC + bin * C + lab], w);
+        }
+    }
+    __syncthreads();
+    uint32_t* gh = hist + (int64_t)s * hsz;
+    for (int i = threadIdx.x; i < hsz; i += blockDim.x) {
+        uint32_t v = sh_hist[i];
+        if (v) atomicAdd(gh + i, v);
+    }
+}
+
+// ------------------------------------------------------------------ R8 split scoring (HOT LOOP B)
+__device__ __forceinline__ double gini_u32(const uint32_t* c, int C, double tot) {
+    if (tot == 0.0) return 0.0;
+    double imp = 1.0;
+    for (int k = 0; k < C; ++k) { double f = (double)c[k] / tot; imp -= f * f; }
+    return imp;
+}
+
+// gain of one candidate split; L = left class counts (smem), tot = node class counts (smem). A.5
+__device__ __forceinline__ double split_gain(const uint32_t* L, const uint32_t* tot, int C, double parent_imp,
+                                             int min_inst, double min_gain) {
+    double lc = 0.0, rc = 0.0;
+    for (int k = 0; k < C; ++k) { lc += (double)L[k]; rc += (double)(tot[k] - L[k]); }
+    if (lc < (double)min_inst || rc < (double)min_inst) return -DBL_MAX;
+    const double t = lc + rc;
+    double gl = 1.0, gr = 1.0;
+    if (lc == 0.0) gl = 0.0; else for (int k = 0; k < C; ++k) { double f = (double)L[k] / lc; gl -= f * f; }
+    if (rc == 0.0) gr = 0.0; else for (int k = 0; k < C; ++k) { double f = (double)(tot[k] - L[k]) / rc; gr -= f * f; }
+    const double lw = lc / t, rw = rc / t;
+    const double gain = parent_imp - lw * gl - rw * gr;
+    if (gain < min_gain) return -DBL_MAX;
+    return gain;
+}
+
+constexpr int kScoreWarps = 8;
+
+// one CTA per slot, one warp per feature of the node's subset (looping when m > warps)
+__global__ void __launch_bounds__(32 * kScoreWarps) score_level_kernel(
+    const uint32_t* __restrict__ hist, int n_slots, const uint16_t* __restrict__ subset, int m, int n_bins, int C,
+    const int32_t* __restrict__ feat_bins, const int32_t* __restrict__ feat_kind, int level, int max_depth, int min_inst,
+    double min_gain, b200flow_split* split, uint32_t* node_counts, uint32_t* left_counts, uint32_t* right_counts) {
+    extern __shared__ __align__(8) uint8_t sm_raw[];
+    const int s = blockIdx.x;
+    const int w = warp_id(), lane = lane_id(), nw = blockDim.x >> 5;
+    const int nbC = n_bins * C;
+    // per-warp scratch: cum[nbC] u32, tmp[nbC] u32, cen[n_bins] f64, order[n_bins] i32, bestL[C] u32
+    const size_t per_warp = ((size_t)2 * nbC * 4 + (size_t)n_bins * 8 + (size_t)n_bins * 4 + (size_t)C * 4 + 7) & ~(size_t)7;
+    uint32_t* tot = (uint32_t*)sm_raw;                                         // [C] node class counts
+    uint8_t* wbase = sm_raw + (((size_t)C * 4 + 7) & ~(size_t)7) + per_warp * w;
+    double* cen = (double*)wbase;
+    uint32_t* cum = (uint32_t*)(cen + n_bins);
+    uint32_t* tmp = cum + nbC;
+    int* order = (int*)(tmp + nbC);
+    uint32_t* bestL = (uint32_t*)(order + n_bins);
+    __shared__ double sh_gain[kScoreWarps];
+    __shared__ int sh_j[kScoreWarps], sh_s[kScoreWarps];
+    __shared__ unsigned long long sh_mask[kScoreWarps][4];
+
+    const uint32_t* h0 = hist + (int64_t)s * m * nbC;
+    // node class counts = Σ over the bins of the first subset feature
+    {
+        const int f0 = subset[(int64_t)s * m];
+        const int nb0 = feat_bins[f0];
+        for (int k = threadIdx.x; k < C; k += blockDim.x) {
+            uint32_t a = 0;
+            for (int b = 0; b < nb0; ++b) a += h0[b * C + k];
+            tot[k] = a;
+        }
+    }
+    __syncthreads();
+    double ptot = 0.0;
+    for (int k = 0; k < C; ++k) ptot += (double)tot[k];
+    const double parent_imp = gini_u32(tot, C, ptot);
+
+    double wbest = -DBL_MAX; int wj = -1, ws = -1;
+    unsigned long long wmask[4] = {0, 0, 0, 0};
+    for (int j = w; j < m; j += nw) {
+        const int f = subset[(int64_t)s * m + j];
+        const int nb = feat_bins[f], kind = feat_kind[f];
+        const uint32_t* h = h0 + (int64_t)j * nbC;
+        double lbest = -DBL_MAX; int ls = -1;            // this lane's best split for feature j
+        __syncwarp();
+        if (kind == 0) {
+            for (int i = lane; i < nb * C; i += 32) cum[i] = h[i];
+            __syncwarp();
+            for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int b = 0; b < nb; ++b) { a += cum[b * C + k]; cum[b * C + k] = a; } }
+            __syncwarp();
+            for (int sp = lane; sp < nb - 1; sp += 32) {
+                double g = split_gain(cum + sp * C, tot, C, parent_imp, min_inst, min_gain);
+                if (g > lbest) { lbest = g; ls = sp; }
+            }
+        } else if (kind == 1) {
+            for (int i = lane; i < nb * C; i += 32) tmp[i] = h[i];
+            __syncwarp();
+            for (int c = lane; c < nb; c += 32) {        // centroid per category
+                double cnt = 0.0;
+                for (int k = 0; k < C; ++k) cnt += (double)tmp[c * C + k];
+                double ce;
+                if (cnt == 0.0) ce = DBL_MAX;
+                else if (C > 2) ce = gini_u32(tmp + c * C, C, cnt);
+                else ce = (double)tmp[c * C + 1];
+                cen[c] = ce;
+            }
+            __syncwarp();
+            for (int c = lane; c < nb; c += 32) {        // stable rank by centroid
+                const double ce = cen[c]; int rk = 0;
+                for (int c2 = 0; c2 < nb; ++c2) { double o = cen[c2]; rk += (o < ce || (o == ce && c2 < c)) ? 1 : 0; }
+                order[rk] = c;
+            }
+            __syncwarp();
+            for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int i = 0; i < nb; ++i) { a += tmp[order[i] * C + k]; cum[i * C + k] = a; } }
+            __syncwarp();
+            for (int sp = lane; sp < nb - 1; sp += 32) {
+                double g = split_gain(cum + sp * C, tot, C, parent_imp, min_inst, min_gain);
+                if (g > lbest) { lbest = g; ls = sp; }
+            }
+        } else {
+            for (int i = lane; i < nb * C; i += 32) tmp[i] = h[i];
+            __syncwarp();
+            const int ns = (1 << (nb - 1)) - 1;           // nb <= 6 -> ns <= 31: one split per lane
+            if (lane < ns) {
+                const unsigned bits = (unsigned)(lane + 1);
+                uint32_t* L = cum + lane * C;
+                for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += tmp[c * C + k]; L[k] = a; }
+                double g = split_gain(L, tot, C, parent_imp, min_inst, min_gain);
+                if (g > lbest) { lbest = g; ls = lane; }
+            }
+        }
+        // first max over splits: larger gain wins, ties -> smaller split index
+        double g = lbest; int sp = ls;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double og = __shfl_xor_sync(0xffffffffu, g, o); int os = __shfl_xor_sync(0xffffffffu, sp, o);
+            if (os >= 0 && (sp < 0 || og > g || (og == g && os < sp))) { g = og; sp = os; }
+        }
+        if (sp >= 0 && g > wbest) {                        // first max over this warp's features (ascending j)
+            wbest = g; wj = j; ws = sp;
+            __syncwarp();
+            for (int k = lane; k < C; k += 32) bestL[k] = cum[sp * C + k];
+            wmask[0] = wmask[1] = wmask[2] = wmask[3] = 0;
+            if (kind == 1) { for (int i = 0; i <= sp; ++i) { int c = order[i]; wmask[c >> 6] |= 1ull << (c & 63); } }
+            else if (kind == 2) wmask[0] = (unsigned long long)(sp + 1);
+            __syncwarp();
+        }
+    }
+    if (lane == 0) { sh_gain[w] = wbest; sh_j[w] = wj; sh_s[w] = ws; for (int q = 0; q < 4; ++q) sh_mask[w][q] = wmask[q]; }
+    __syncthreads();
+    // first max over features: larger gain, ties -> smaller j
+    int bw = -1; double bg = -DBL_MAX; int bj = -1;
+    for (int q = 0; q < nw; ++q)
+        if (sh_j[q] >= 0 && (bw < 0 || sh_gain[q] > bg || (sh_gain[q] == bg && sh_j[q] < bj))) { bw = q; bg = sh_gain[q]; bj = sh_j[q]; }
+    if (w != (bw < 0 ? 0 : bw)) return;
+    // the winning warp (or warp 0 when there is no valid split) writes the records
+    const bool has = bw >= 0;
+    for (int k = lane; k < C; k += 32) {
+        node_counts[(int64_t)s * C + k] = tot[k];
+        uint32_t l = has ? bestL[k] : 0u;
+        left_counts[(int64_t)s * C + k] = l;
+        right_counts[(int64_t)s * C + k] = has ? tot[k] - l : 0u;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        b200flow_split o;
+        o.gain = has ? bg : -DBL_MAX; o.impurity = parent_imp;
+        const bool leaf = !(has && bg > 0.0) || level >= max_depth;
+        int flags = leaf ? 1 : 0;
+        o.feat = -1; o.kind = 0; o.bin_thr = 0;
+        o.mask[0] = o.mask[1] = o.mask[2] = o.mask[3] = 0;
+        if (!leaf) {
+            const int f = subset[(int64_t)s * m + bj];
+            o.feat = f; o.kind = feat_kind[f] == 0 ? 0 : 1; o.bin_thr = sh_s[bw];
+            for (int q = 0; q < 4; ++q) o.mask[q] = sh_mask[bw][q];
+            double lc = 0.0, rc = 0.0, gl = 1.0, gr = 1.0;
+            for (int k = 0; k < C; ++k) { lc += (double)bestL[k]; rc += (double)(tot[k] - bestL[k]); }
+            if (lc == 0.0) gl = 0.0; else for (int k = 0; k < C; ++k) { double fq = (double)bestL[k] / lc; gl -= fq * fq; }
+            if (rc == 0.0) gr = 0.0; else for (int k = 0; k < C; ++k) { double fq = (double)(tot[k] - bestL[k]) / rc; gr -= fq * fq; }
+            if (level + 1 == max_depth || gl == 0.0) flags |= 2;
+            if (level + 1 == max_depth || gr == 0.0) flags |= 4;
+        }
+        o.flags = flags;
+        split[s] = o;
+    }
+}
+
+// ------------------------------------------------------------------ pool growth (3 kernels: count, scan, write)
+constexpr int kGrowBlock = 256;
+
+__device__ __forceinline__ void grow_flags(const b200flow_split* __restrict__ split, int s, int n_slots, int* is_split, int* n_next) {
+    int fl = s < n_slots ? split[s].flags : 1;
+    *is_split = (fl & 1) ? 0 : 1;
+    *n_next = (fl & 1) ? 0 : ((fl & 2) ? 0 : 1) + ((fl & 4) ? 0 : 1);
+}
+
+__global__ void __launch_bounds__(kGrowBlock) grow_count_kernel(int n_slots, const b200flow_split* __restrict__ split, int32_t* blk) {
+    __shared__ int sh[2];
+    if (threadIdx.x < 2) sh[threadIdx.x] = 0;
+    __syncthreads();
+    int is, nn; grow_flags(split, blockIdx.x * kGrowBlock + threadIdx.x, n_slots, &is, &nn);
+    is = warp_sum(is); nn = warp_sum(nn);
+    if (lane_id() == 0) { if (is) atomicAdd(&sh[0], is); if (nn) atomicAdd(&sh[1], nn); }
+    __syncthreads();
+    if (threadIdx.x < 2) blk[2 * blockIdx.x + threadIdx.x] = sh[threadIdx.x];
+}
+
+// single CTA: exclusive scan of the interleaved (split, next) block counts, in place; updates counters
+__global__ void __launch_bounds__(1024) grow_scan_kernel(int n_blocks, int32_t* blk, int64_t* counters, int64_t pool_capacity) {
+    __shared__ int sh[33];
+    __shared__ int carry[2];
+    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += 1024) {
+        int i = base + threadIdx.x;
+        int a = i < n_blocks ? blk[2 * i] : 0, b = i < n_blocks ? blk[2 * i + 1] : 0;
+        int ta, tb;
+        int ea = block_exclusive_scan(a, sh, &ta);
+        __syncthreads();
+        int eb = block_exclusive_scan(b, sh, &tb);
+        if (i < n_blocks) { blk[2 * i] = carry[0] + ea; blk[2 * i + 1] = carry[1] + eb; }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry[0] += ta; carry[1] += tb; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int64_t pool = counters[0];
+        counters[3] = pool;                               // pool size before this level (base for grow_write)
+        int64_t grown = pool + 2 * (int64_t)carry[0];
+        counters[2] = grown > pool_capacity ? 1 : 0;      // overflow flag: nothing is written then
+        counters[0] = grown > pool_capacity ? pool : grown;
+        counters[1] = grown > pool_capacity ? 0 : carry[1];
+    }
+}
+
+__global__ void __launch_bounds__(kGrowBlock) grow_write_kernel(
+    int n_slots, const int32_t* __restrict__ slot_tree, const uint32_t* __restrict__ slot_nid,
+    const int32_t* __restrict__ slot_node, const b200flow_split* __restrict__ split,
+    const uint32_t* __restrict__ node_counts, const uint32_t* __restrict__ left_counts,
+    const uint32_t* __restrict__ right_counts, int C, b200flow_node* nodes, uint64_t* node_mask, uint32_t* pool_counts,
+    int32_t* node_tree, const int32_t* __restrict__ blk, const int64_t* __restrict__ counters, int32_t* next_tree,
+    uint32_t* next_nid, int32_t* next_node, int32_t* next_parent) {
+    __shared__ int sh[33];
+    if (counters[2]) return;
+    const int s = blockIdx.x * kGrowBlock + threadIdx.x;
+    int is, nn; grow_flags(split, s, n_slots, &is, &nn);
+    int t0, t1;
+    int e0 = block_exclusive_scan(is, sh, &t0);
+    __syncthreads();
+    int e1 = block_exclusive_scan(nn, sh, &t1);
+    if (s >= n_slots) return;
+    const b200flow_split sp = split[s];
+    const int node = slot_node[s];
+    const uint32_t nid = slot_nid[s];
+    const int tree = slot_tree[s];
+    b200flow_node nd;
+    nd.nid = nid; nd.feat = -1; nd.kind_bin = 0; nd.left = -1;
+    for (int k = 0; k < C; ++k) pool_counts[(int64_t)node * C + k] = node_counts[(int64_t)s * C + k];
+    if (is) {
+        const int64_t child = counters[3] + 2 * ((int64_t)blk[2 * blockIdx.x] + e0);
+        nd.feat = sp.feat; nd.kind_bin = (sp.kind << 16) | (sp.bin_thr & 0xffff); nd.left = (int32_t)child;
+        if (node_mask) for (int q = 0; q < 4; ++q) node_mask[(int64_t)node * 4 + q] = sp.mask[q];
+        b200flow_node ch; ch.feat = -1; ch.kind_bin = 0; ch.left = -1;
+        ch.nid = nid * 2u;     nodes[child] = ch;
+        ch.nid = nid * 2u + 1; nodes[child + 1] = ch;
+        node_tree[child] = tree; node_tree[child + 1] = tree;
+        for (int k = 0; k < C; ++k) {
+            pool_counts[child * C + k] = left_counts[(int64_t)s * C + k];
+            pool_counts[(child + 1) * C + k] = right_counts[(int64_t)s * C + k];
+        }
+        int64_t ns = (int64_t)blk[2 * blockIdx.x + 1] + e1;
+        if (!(sp.flags & 2)) { next_tree[ns] = tree; next_nid[ns] = nid * 2u; next_node[ns] = (int32_t)child; next_parent[ns] = s * 2; ++ns; }
+        if (!(sp.flags & 4)) { next_tree[ns] = tree; next_nid[ns] = nid * 2u + 1; next_node[ns] = (int32_t)child + 1; next_parent[ns] = s * 2 + 1; }
+    }
+    nodes[node] = nd;
+}
+
+// ------------------------------------------------------------------ row routing
+constexpr int kPartPerThread = 8;      // chunk_rows <= 256 * 8
+
+__global__ void __launch_bounds__(256) partition_level_kernel(
+    const uint8_t* __restrict__ tp, int stride, const int32_t* __restrict__ ent_row, const uint8_t* __restrict__ ent_w,
+    int32_t* ent_row_out, uint8_t* ent_w_out, int n_slots, const int64_t* __restrict__ seg_begin,
+    const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off, int chunk_rows,
+    const b200flow_split* __restrict__ split, int32_t* cursors) {
+    const int64_t c = blockIdx.x;
+    const int s = find_slot(chunk_off, n_slots, c);
+    const b200flow_split sp = split[s];
+    if (sp.flags & 1) return;                          // leaf: its entries are dropped
+    const bool keepL = !(sp.flags & 2), keepR = !(sp.flags & 4);
+    if (!keepL && !keepR) return;
+    const int64_t sb = seg_begin[s], se = seg_end[s];
+    const int64_t b = sb + (c - chunk_off[s]) * chunk_rows;
+    const int64_t e = min(se, b + chunk_rows);
+    const int lane = lane_id();
+    int rows[kPartPerThread]; uint32_t wts = 0, wts2 = 0; uint32_t dec = 0;   // dec: 2 bits per entry (1 = left kept, 2 = right kept)
+    int nL = 0, nR = 0;
+#pragma unroll
+    for (int k = 0; k < kPartPerThread; ++k) {
+        const int64_t i = b + threadIdx.x + (int64_t)k * blockDim.x;
+        int d = 0; rows[k] = 0;
+        if (i < e) {
+            const int row = ent_row[i];
+            const uint32_t w = ent_w[i];
+            rows[k] = row;
+            if (k < 4) wts |= w << (8 * k); else wts2 |= w << (8 * (k - 4));
+            const int bin = tp[(int64_t)row * stride + sp.feat];
+            const bool left = sp.kind == 0 ? (bin <= sp.bin_thr) : ((sp.mask[bin >> 6] >> (bin & 63)) & 1ull);
+            d = left ? (keepL ? 1 : 0) : (keepR ? 2 : 0);
+        }
+        dec |= (uint32_t)d << (2 * k);
+        nL += __popc(__ballot_sync(0xffffffffu, d == 1));
+        nR += __popc(__ballot_sync(0xffffffffu, d == 2));
+    }
+    int baseL = 0, baseR = 0;                           // one cursor reservation per warp and side
+    if (lane == 0) { if (nL) baseL = atomicAdd(&cursors[2 * s], nL); if (nR) baseR = atomicAdd(&cursors[2 * s + 1], nR); }
+    baseL = __shfl_sync(0xffffffffu, baseL, 0); baseR = __shfl_sync(0xffffffffu, baseR, 0);
+#pragma unroll
+    for (int k = 0; k < kPartPerThread; ++k) {
+        const int d = (dec >> (2 * k)) & 3;
+        const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t w = k < 4 ? (wts >> (8 * k)) & 0xffu : (wts2 >> (8 * (k - 4))) & 0xffu;
+        if (d == 1) { int64_t p = sb + baseL + __popc(mL & lt); ent_row_out[p] = rows[k]; ent_w_out[p] = (uint8_t)w; }
+        else if (d == 2) { int64_t p = se - 1 - (baseR + __popc(mR & lt)); ent_row_out[p] = rows[k]; ent_w_out[p] = (uint8_t)w; }
+        baseL += __popc(mL); baseR += __popc(mR);
+    }
+}
+
+__global__ void next_segments_kernel(int n_next, const int32_t* __restrict__ next_parent, const int64_t* __restrict__ seg_begin,
+                                     const int64_t* __restrict__ seg_end, const int32_t* __restrict__ cursors,
+                                     int64_t* next_begin, int64_t* next_end) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_next) return;
+    const int p = next_parent[i], ps = p >> 1;
+    if ((p & 1) == 0) { next_begin[i] = seg_begin[ps]; next_end[i] = seg_begin[ps] + cursors[2 * ps]; }
+    else { next_begin[i] = seg_end[ps] - cursors[2 * ps + 1]; next_end[i] = seg_end[ps]; }
+}
+
+__global__ void finalize_forest_kernel(int64_t n_nodes, const uint32_t* __restrict__ pool_counts, int C, double* leaf_prob) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    double tot = 0.0;
+    for (int k = 0; k < C; ++k) tot += (double)pool_counts[i * C + k];
+    for (int k = 0; k < C; ++k) leaf_prob[i * C + k] = tot != 0.0 ? (double)pool_counts[i * C + k] / tot : 0.0;
+}
+
+}  // namespace b200flow
+
+using namespace b200flow;
+
+extern "C" int b200flow_feature_subsets(uint64_t seed, int32_t n_slots, const int32_t* slot_tree, const uint32_t* slot_nid,
+                                        int32_t F, int32_t m, uint16_t* subset, void* stream) {
+    B2F_REQUIRE(slot_tree && slot_nid && subset && F > 0 && F < 65536 && m > 0 && m <= F, "feature_subsets: bad arguments");
+    B2F_REQUIRE(m == F || m <= kMaxSubset, "feature_subsets: subset size %d > %d not supported", m, kMaxSubset);
+    if (n_slots <= 0) return B200FLOW_OK;
+    feature_subsets_kernel<<<(n_slots + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, n_slots, slot_tree, slot_nid, F, m, subset);
+    return check_launch("feature_subsets");
+}
+
+extern "C" int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const int32_t* ent_row, const uint8_t* ent_w,
+                                   int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end, const int64_t* chunk_off,
+                                   int64_t n_chunks, int32_t chunk_rows, const uint16_t* subset, int32_t m, int32_t n_bins,
+                                   int32_t C, uint32_t* hist, void* stream) {
+    B2F_REQUIRE(tp && ent_row && ent_w && seg_begin && seg_end && chunk_off && subset && hist, "hist_level: null pointer");
+    B2F_REQUIRE(m > 0 && m <= 256 && n_bins > 0 && n_bins <= 256 && C > 0 && C <= 256 && chunk_rows > 0, "hist_level: bad shape");
+    size_t smem = (size_t)m * n_bins * C * 4;
+    B2F_REQUIRE(smem <= 200 * 1024, "hist_level: per-node histogram (%zu B) exceeds shared memory", smem);
+    if (n_slots <= 0 || n_chunks <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(n_chunks < ((int64_t)1 << 31), "hist_level: too many chunks");
+    cudaError_t e = cudaFuncSetAttribute(hist_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
+    hist_level_kernel<<<(unsigned)n_chunks, 256, smem, (cudaStream_t)stream>>>(tp, tp_stride, F, ent_row, ent_w, n_slots, seg_begin,
+                                                                             seg_end, chunk_off, chunk_rows, subset, m, n_bins, C, hist);
+    return check_launch("hist_level");
+}
+
+extern "C" int b200flow_score_level(const uint32_t* hist, int32_t n_slots, const uint16_t* subset, int32_t m, int32_t n_bins,
+                                    int32_t C, const int32_t* feat_bins, const int32_t* feat_kind, int32_t level, int32_t max_depth,
+                                    int32_t min_instances, double min_info_gain, b200flow_split* split, uint32_t* node_counts,
+                                    uint32_t* left_counts, uint32_t* right_counts, void* stream) {
+    B2F_REQUIRE(hist && subset && feat_bins && feat_kind && split && node_counts && left_counts && right_counts, "score_level: null pointer");
+    B2F_REQUIRE(m > 0 && n_bins > 0 && n_bins <= 256 && C > 0 && C <= 256, "score_level: bad shape");
+    if (n_slots <= 0) return B200FLOW_OK;
+    int nw = m < kScoreWarps ? m : kScoreWarps;
+    size_t per_warp = ((size_t)2 * n_bins * C * 4 + (size_t)n_bins * 8 + (size_t)n_bins * 4 + (size_t)C * 4 + 7) & ~(size_t)7;
+    while (nw > 1 && per_warp * nw + C * 4 + 64 > 100 * 1024) --nw;
+    size_t smem = (((size_t)C * 4 + 7) & ~(size_t)7) + per_warp * nw;
+    B2F_REQUIRE(smem <= 200 * 1024, "score_level: scratch exceeds shared memory");
+    cudaError_t e = cudaFuncSetAttribute(score_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("score_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
+    score_level_kernel<<<n_slots, 32 * nw, smem, (cudaStream_t)stream>>>(hist, n_slots, subset, m, n_bins, C, feat_bins, feat_kind, level,
+                                                                        max_depth, min_instances, min_info_gain, split, node_counts,
+                                                                        left_counts, right_counts);
+    return check_launch("score_level");
+}
+
+extern "C" int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, const uint32_t* slot_nid, const int32_t* slot_node,
+                                   const b200flow_split* split, const uint32_t* node_counts, const uint32_t* left_counts,
+                                   const uint32_t* right_counts, int32_t C, b200flow_node* nodes, uint64_t* node_mask,
+                                   uint32_t* pool_counts, int32_t* node_tree, int64_t pool_capacity, int32_t* next_tree,
+                                   uint32_t* next_nid, int32_t* next_node, int32_t* next_parent, int64_t* counters, void* stream) {
+    B2F_REQUIRE(slot_tree && slot_nid && slot_node && split && node_counts && left_counts && right_counts && nodes && pool_counts &&
+                    node_tree && next_tree && next_nid && next_node && next_parent && counters, "grow_level: null pointer");
+    if (n_slots <= 0) return B200FLOW_OK;
+    // counters: int64[4] {pool size, n_next, overflow flag, pool size before the level} followed by the
+    // int32 scratch for the per-block counts (2 * ceil(n_slots/256) ints), all caller-owned.
+    const int nb = (n_slots + kGrowBlock - 1) / kGrowBlock;
+    int32_t* blk = (int32_t*)(counters + 4);
+    grow_count_kernel<<<nb, kGrowBlock, 0, (cudaStream_t)stream>>>(n_slots, split, blk);
+    grow_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nb, blk, counters, pool_capacity);
+    grow_write_kernel<<<nb, kGrowBlock, 0, (cudaStream_t)stream>>>(n_slots, slot_tree, slot_nid, slot_node, split, node_counts, left_counts,
+                                                                  right_counts, C, nodes, node_mask, pool_counts, node_tree, blk, counters,
+                                                                  next_tree, next_nid, next_node, next_parent);
+    return check_launch("grow_level");
+}
+
+extern "C" int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride, const int32_t* ent_row, const uint8_t* ent_w,
+                                        int32_t* ent_row_out, uint8_t* ent_w_out, int32_t n_slots, const int64_t* seg_begin,
+                                        const int64_t* seg_end, const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
+                                        const b200flow_split* split, int32_t* cursors, void* stream) {
+    B2F_REQUIRE(tp && ent_row && ent_w && ent_row_out && ent_w_out && seg_begin && seg_end && chunk_off && split && cursors,
+                "partition_level: null pointer");
+    B2F_REQUIRE(chunk_rows > 0 && chunk_rows <= 256 * kPartPerThread, "partition_level: chunk_rows must be <= %d", 256 * kPartPerThread);
+    if (n_slots <= 0 || n_chunks <= 0) return B200FLOW_OK;
+    partition_level_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(tp, tp_stride, ent_row, ent_w, ent_row_out, ent_w_out, n_slots,
+                                                                               seg_begin, seg_end, chunk_off, chunk_rows, split, cursors);
+    return check_launch("partition_level");
+}
+
+extern "C" int b200flow_next_segments(int32_t n_next, const int32_t* next_parent, const int64_t* seg_begin, const int64_t* seg_end,
+                                      const int32_t* cursors, int64_t* next_begin, int64_t* next_end, void* stream) {
+    B2F_REQUIRE(next_parent && seg_begin && seg_end && cursors && next_begin && next_end, "next_segments: null pointer");
+    if (n_next <= 0) return B200FLOW_OK;
+    next_segments_kernel<<<(n_next + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_next, next_parent, seg_begin, seg_end, cursors, next_begin, next_end);
+    return check_launch("next_segments");
+}
+
+extern "C" int b200flow_finalize_forest(int64_t n_nodes, const uint32_t* pool_counts, int32_t C, double* leaf_prob, void* stream) {
+    B2F_REQUIRE(pool_counts && leaf_prob && C > 0, "finalize_forest: bad arguments");
+    if (n_nodes <= 0) return B200FLOW_OK;
+    finalize_forest_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_nodes, pool_counts, C, leaf_prob);
+    return check_launch("finalize_forest");
+}

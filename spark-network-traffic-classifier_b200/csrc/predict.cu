@@ -1,0 +1,195 @@
+// predict.cu — batch prediction (HOT LOOP C), the confusion-matrix kernel of
+// MulticlassMetrics (R10) and the two relational steps either side of the path (§8f rank 1):
+// randomSplit and stable row compaction.
+// Reference call sites: model.transform(test_set) kdd99.py:82 / cicids17.py:86; evaluator.evaluate
+// kdd99.py:86-91; randomSplit kdd99.py:52; where / handleInvalid="skip" cicids17.py:30-35,41.
+#include "common.cuh"
+
+namespace b200flow {
+
+// ------------------------------------------------------------------ R9 predict
+// One thread per row; the row's bins live in registers-free transposed smem (word k of thread t at
+// [k*blockDim + t]); votes accumulate in fp64 in tree order in smem ([class*blockDim + t]).
+__global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict__ tp, int stride, int64_t n,
+                                                      const b200flow_node* __restrict__ nodes,
+                                                      const unsigned long long* __restrict__ node_mask,
+                                                      const double* __restrict__ leaf_prob,
+                                                      const uint32_t* __restrict__ pool_counts, int T, int C, int dt_mode,
+                                                      double* raw, double* prob, double* pred) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int bd = blockDim.x, tid = threadIdx.x;
+    const int words = stride / 4;
+    uint32_t* binw = (uint32_t*)sm;                               // [words][bd]
+    double* votes = (double*)(sm + (size_t)words * bd * 4);       // [C][bd]
+    for (int64_t base = (int64_t)blockIdx.x * bd; base < n; base += (int64_t)gridDim.x * bd) {
+        const int64_t i = base + tid;
+        const bool live = i < n;
+        if (live) {
+            const uint4* src = (const uint4*)(tp + i * stride);
+            for (int q = 0; q < words / 4; ++q) {
+                uint4 v = ld_stream_u4(src + q);
+                binw[(4 * q + 0) * bd + tid] = v.x; binw[(4 * q + 1) * bd + tid] = v.y;
+                binw[(4 * q + 2) * bd + tid] = v.z; binw[(4 * q + 3) * bd + tid] = v.w;
+            }
+            for (int k = 0; k < C; ++k) votes[k * bd + tid] = 0.0;
+            for (int t = 0; t < T; ++t) {
+                int idx = t;
+                b200flow_node nd = nodes[idx];
+                while (nd.feat >= 0) {
+                    const int f = nd.feat;
+                    const int bin = (binw[(f >> 2) * bd + tid] >> ((f & 3) * 8)) & 0xff;
+                    bool left;
+                    if ((nd.kind_bin >> 16) == 0) left = bin <= (nd.kind_bin & 0xffff);
+                    else left = (node_mask[(int64_t)idx * 4 + (bin >> 6)] >> (bin & 63)) & 1ull;
+                    idx = nd.left + (left ? 0 : 1);
+                    nd = nodes[idx];
+                }
+                if (dt_mode) { for (int k = 0; k < C; ++k) votes[k * bd + tid] += (double)pool_counts[(int64_t)idx * C + k]; }
+                else { for (int k = 0; k < C; ++k) votes[k * bd + tid] += leaf_prob[(int64_t)idx * C + k]; }
+            }
+            double s = 0.0; int arg = 0; double best = votes[tid];
+            for (int k = 0; k < C; ++k) { double v = votes[k * bd + tid]; s += v; if (v > best) { best = v; arg = k; } }
+            for (int k = 0; k < C; ++k) {
+                double v = votes[k * bd + tid];
+                if (raw) raw[i * C + k] = v;
+                if (prob) prob[i * C + k] = s != 0.0 ? v / s : 0.0;
+            }
+            pred[i] = (double)arg;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ R10 confusion matrix
+__global__ void __launch_bounds__(256) confusion_kernel(const double* __restrict__ pred, const double* __restrict__ label,
+                                                        int64_t n, int C, unsigned long long* cm, int use_smem) {
+    extern __shared__ uint32_t sh_cm[];
+    if (use_smem) { for (int i = threadIdx.x; i < C * C; i += blockDim.x) sh_cm[i] = 0; __syncthreads(); }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)label[i], p = (int)pred[i];
+        if (l >= 0 && l < C && p >= 0 && p < C) {
+            if (use_smem) atomicAdd(&sh_cm[l * C + p], 1u); else atomicAdd(&cm[l * C + p], 1ull);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x) if (sh_cm[i]) atomicAdd(&cm[i], (unsigned long long)sh_cm[i]);
+    }
+}
+
+// ------------------------------------------------------------------ randomSplit
+struct SplitBounds { double cum[8]; int n; };
+
+__global__ void __launch_bounds__(256) random_split_kernel(uint64_t seed, int64_t row_offset, int64_t n, SplitBounds bnd,
+                                                           uint8_t* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = (uint64_t)(row_offset + i);
+        const uint4 r = philox_keyed(seed, PURPOSE_RSPLIT, (uint32_t)g, (uint32_t)(g >> 32), 0u, 0u);
+        const double u = (double)r.x * 2.3283064365386963e-10;     // 2^-32
+        int k = 0;
+        while (k < bnd.n - 1 && !(u < bnd.cum[k])) ++k;
+        out[i] = (uint8_t)k;
+    }
+}
+
+// ------------------------------------------------------------------ stable row compaction
+constexpr int kCompactRows = 1024;
+
+__global__ void __launch_bounds__(256) compact_count_kernel(const uint8_t* __restrict__ flag, int64_t n, int want, int32_t* blk_cnt) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int c = 0;
+    const int64_t rb = (int64_t)blockIdx.x * kCompactRows + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (rb + k < n && (flag[rb + k] != 0) == (want != 0)) ++c;
+    c = warp_sum(c);
+    if (lane_id() == 0 && c) atomicAdd(&cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(256) compact_scatter_kernel(const uint8_t* __restrict__ rows, int64_t n, int row_bytes,
+                                                              const uint8_t* __restrict__ flag, int want,
+                                                              const int64_t* __restrict__ blk_off, uint8_t* out) {
+    __shared__ int sh[33];
+    __shared__ int src_of[kCompactRows];                 // kept rows of this block, in order
+    const int64_t rb0 = (int64_t)blockIdx.x * kCompactRows;
+    const int64_t rb = rb0 + threadIdx.x * 4;
+    int keep[4], c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { keep[k] = (rb + k < n && (flag[rb + k] != 0) == (want != 0)) ? 1 : 0; c += keep[k]; }
+    int tot;
+    int pos = block_exclusive_scan(c, sh, &tot);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (keep[k]) src_of[pos++] = threadIdx.x * 4 + k;
+    __syncthreads();
+    const int words = row_bytes / 4;
+    const uint32_t* src = (const uint32_t*)(rows + rb0 * row_bytes);
+    uint32_t* dst = (uint32_t*)(out + blk_off[blockIdx.x] * row_bytes);
+    for (int64_t i = threadIdx.x; i < (int64_t)tot * words; i += blockDim.x) {
+        int r = (int)(i / words), wd = (int)(i - (int64_t)r * words);
+        dst[i] = src[(int64_t)src_of[r] * words + wd];
+    }
+}
+
+}  // namespace b200flow
+
+using namespace b200flow;
+
+extern "C" int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_rows, const b200flow_node* nodes,
+                                const uint64_t* node_mask, const double* leaf_prob, const uint32_t* pool_counts, int32_t T,
+                                int32_t C, int32_t dt_mode, double* raw, double* prob, double* pred, void* stream) {
+    B2F_REQUIRE(tp && nodes && pred && T > 0 && C > 0 && (tp_stride & 15) == 0, "predict: bad arguments");
+    B2F_REQUIRE(dt_mode ? pool_counts != nullptr : leaf_prob != nullptr, "predict: missing leaf payload");
+    B2F_REQUIRE(((uintptr_t)tp & 15) == 0, "predict: tp must be 16-byte aligned");
+    if (n_rows <= 0) return B200FLOW_OK;
+    int bd = 128;
+    size_t per_thread = (size_t)tp_stride + (size_t)C * 8;
+    while (bd > 32 && per_thread * bd > 96 * 1024) bd >>= 1;
+    size_t smem = per_thread * bd;
+    B2F_REQUIRE(smem <= 200 * 1024, "predict: too many classes/features for shared memory");
+    cudaError_t e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("predict: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
+    int grid = grid_for(n_rows, bd, kNumSMs * 16);
+    predict_kernel<<<grid, bd, smem, (cudaStream_t)stream>>>(tp, tp_stride, n_rows, nodes, (const unsigned long long*)node_mask, leaf_prob,
+                                                             pool_counts, T, C, dt_mode, raw, prob, pred);
+    return check_launch("predict");
+}
+
+extern "C" int b200flow_confusion(const double* pred, const double* label, int64_t n_rows, int32_t C, int64_t* cm, void* stream) {
+    B2F_REQUIRE(pred && label && cm && C > 0 && C <= 1024, "confusion: bad arguments");
+    if (n_rows <= 0) return B200FLOW_OK;
+    int use_smem = (size_t)C * C * 4 <= 64 * 1024;
+    size_t smem = use_smem ? (size_t)C * C * 4 : 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(confusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int grid = grid_for(n_rows, 256 * 8, kNumSMs * 4);
+    confusion_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pred, label, n_rows, C, (unsigned long long*)cm, use_smem);
+    return check_launch("confusion");
+}
+
+extern "C" int b200flow_random_split(uint64_t seed, int64_t row_offset, int64_t n_rows, const double* cum_bounds_host,
+                                     int32_t n_splits, uint8_t* split_id, void* stream) {
+    B2F_REQUIRE(cum_bounds_host && split_id && n_splits >= 1 && n_splits <= 8, "random_split: bad arguments");
+    if (n_rows <= 0) return B200FLOW_OK;
+    SplitBounds b; b.n = n_splits;
+    for (int i = 0; i < 8; ++i) b.cum[i] = i < n_splits ? cum_bounds_host[i] : 2.0;
+    int grid = grid_for(n_rows, 256 * 4, kNumSMs * 8);
+    random_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n_rows, b, split_id);
+    return check_launch("random_split");
+}
+
+extern "C" int b200flow_compact_rows(const void* rows, int64_t n_rows, int32_t row_bytes, const uint8_t* flag, int32_t want,
+                                     void* out_rows, int64_t* scratch, int64_t* n_kept, void* stream) {
+    B2F_REQUIRE(rows && flag && out_rows && scratch && n_kept && row_bytes > 0 && (row_bytes & 3) == 0, "compact_rows: bad arguments");
+    B2F_REQUIRE(((uintptr_t)rows & 3) == 0 && ((uintptr_t)out_rows & 3) == 0, "compact_rows: buffers must be 4-byte aligned");
+    if (n_rows <= 0) { cudaMemsetAsync(n_kept, 0, 8, (cudaStream_t)stream); return check_launch("compact_rows"); }
+    const int64_t nb = (n_rows + kCompactRows - 1) / kCompactRows;
+    // scratch: int64 off[nb+1] first (8-aligned), then int32 cnt[nb]
+    int64_t* off = scratch;
+    int32_t* cnt = (int32_t*)(scratch + nb + 1);
+    compact_count_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(flag, n_rows, want, cnt);
+    int rc = b200flow_exclusive_scan_i32_to_i64(cnt, nb, off, n_kept, stream);
+    if (rc) return rc;
+    compact_scatter_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)rows, n_rows, row_bytes, flag, want, off, (uint8_t*)out_rows);
+    return check_launch("compact_rows");
+}

@@ -1,0 +1,286 @@
+// treeprep.cu — what RandomForest.run does before the level loop:
+//   findSplits sample + findSplitsForContinuousFeature, TreePoint binning, Poisson bagging.
+// Reference call sites: classifiers[c].fit(train_set) kdd99.py:79 / cicids17.py:83.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200flow {
+
+// ------------------------------------------------------------------ exclusive scan (single CTA)
+__global__ void __launch_bounds__(1024) scan_i32_i64_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* out,
+                                                            int64_t* total) {
+    __shared__ int sh[33];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 4096) {
+        int64_t i0 = base + (int64_t)threadIdx.x * 4;
+        int v[4]; int s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+        int tot;
+        int ex = block_exclusive_scan(s, sh, &tot);
+        long long c = carry + ex;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = c; c += v[k]; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[n] = carry; if (total) *total = carry; }
+}
+
+// ------------------------------------------------------------------ R4 sample rows
+template <typename T>
+__global__ void __launch_bounds__(256) sample_rows_kernel(const T* __restrict__ x, int64_t n, int F, int64_t ld,
+                                                          uint64_t seed, uint64_t keep_thr, int64_t row_offset,
+                                                          double* sample, int64_t cap, int32_t* n_sampled) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t g = (uint64_t)(row_offset + i);
+        uint4 r = philox_keyed(seed, PURPOSE_SAMPLE, (uint32_t)g, (uint32_t)(g >> 32), 0u, 0u);
+        if ((uint64_t)r.x < keep_thr) {
+            int slot = atomicAdd(n_sampled, 1);
+            if (slot < cap)
+                for (int f = 0; f < F; ++f) sample[(int64_t)f * cap + slot] = (double)x[i * ld + f];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ R4 findSplitsForContinuousFeature
+// One CTA per feature: bitonic sort of the (padded to pow2 with +inf) sample column in global/L2,
+// then one thread walks the distinct values with MLlib's stride rule.
+__global__ void __launch_bounds__(1024) find_splits_kernel(double* sample, int64_t cap, int n_s, int n_pad,
+                                                           const int32_t* __restrict__ arity, int max_bins,
+                                                           double* thresholds, int32_t* n_thr) {
+    const int f = blockIdx.x;
+    __shared__ int sh_distinct;
+    if (arity[f] > 0 || n_s <= 0) { if (threadIdx.x == 0) n_thr[f] = 0; return; }
+    double* v = sample + (int64_t)f * cap;
+    for (int i = n_s + threadIdx.x; i < n_pad; i += blockDim.x) v[i] = INFINITY;
+    if (threadIdx.x == 0) sh_distinct = 0;
+    __syncthreads();
+    for (int k = 2; k <= n_pad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+                int p = i ^ j;
+                if (p > i) {
+                    double a = v[i], b = v[p];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { v[i] = b; v[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    int local = 0;
+    for (int i = 1 + threadIdx.x; i < n_s; i += blockDim.x) local += (v[i] != v[i - 1]) ? 1 : 0;
+    local = warp_sum(local);
+    if (lane_id() == 0 && local) atomicAdd(&sh_distinct, local);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int possible = sh_distinct;            // #distinct - 1
+    const int num_splits = max_bins - 1;
+    double* thr = thresholds + (int64_t)f * num_splits;
+    int nt = 0;
+    if (possible == 0) {
+    } else if (possible <= num_splits) {
+        for (int i = 1; i < n_s; ++i)
+            if (v[i] != v[i - 1]) thr[nt++] = (v[i - 1] + v[i]) / 2.0;
+    } else {
+        const double stride = (double)n_s / (double)(num_splits + 1);
+        double target = stride;
+        // run-length walk: cur = cumulative count up to and including the current distinct value
+        int i = 1;
+        while (i < n_s && v[i] == v[0]) ++i;
+        double cur = (double)i;                   // count of the first distinct value
+        while (i < n_s) {
+            int j = i + 1;
+            while (j < n_s && v[j] == v[i]) ++j;
+            const double prev = cur;
+            cur += (double)(j - i);
+            if (fabs(prev - target) < fabs(cur - target)) {
+                if (nt < num_splits) thr[nt++] = (v[i - 1] + v[i]) / 2.0;
+                target += stride;
+            }
+            i = j;
+        }
+    }
+    n_thr[f] = nt;
+}
+
+// ------------------------------------------------------------------ R5 TreePoint binning
+// thread -> (row, feature) with a fixed feature per thread; bins staged in smem, written as 16-byte words.
+template <typename T>
+__global__ void __launch_bounds__(256) bin_rows_kernel(const T* __restrict__ x, int64_t n, int F, int64_t ld,
+                                                       const double* __restrict__ thresholds,
+                                                       const int32_t* __restrict__ n_thr, const int32_t* __restrict__ arity,
+                                                       int max_bins, const int32_t* __restrict__ labels, uint8_t* tp,
+                                                       int stride, int32_t* bad_rows, int R, int thr_in_smem) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    uint8_t* tile = sm;                                   // [R][stride]
+    double* thr_sh = (double*)(sm + (((size_t)R * stride + 15) & ~(size_t)15));
+    const int tid = threadIdx.x, bd = blockDim.x, ns = max_bins - 1;
+    if (thr_in_smem) for (int i = tid; i < F * ns; i += bd) thr_sh[i] = thresholds[i];
+    const double* thr_all = thr_in_smem ? thr_sh : thresholds;
+    const int64_t n_tiles = (n + R - 1) / R;
+    const bool fixed = F <= bd;
+    const int rp = fixed ? bd / F : 1;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t rb = t * R;
+        const int rows = (int)min((int64_t)R, n - rb);
+        __syncthreads();                                  // previous tile written out (and thr_sh ready)
+        for (int i = tid; i < rows * stride / 4; i += bd) ((uint32_t*)tile)[i] = 0;   // pad bytes
+        __syncthreads();
+        if (!fixed || tid < rp * F) {
+            for (int f = fixed ? tid % F : tid; f < F; f += fixed ? F : bd) {
+                const int ar = arity[f];
+                const int nt = n_thr[f];
+                const double* thr = thr_all + (int64_t)f * ns;
+                for (int r = fixed ? tid / F : 0; r < rows; r += rp) {
+                    const double v = (double)x[(rb + r) * ld + f];
+                    int b;
+                    if (ar > 0) {
+                        b = (int)v;
+                        if (!((double)b == v) || b < 0 || b >= ar) { b = 0; atomicAdd(bad_rows, 1); }
+                    } else {
+                        int lo = 0, hi = nt;              // lower_bound: first b with v <= thr[b]
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (v <= thr[mid]) hi = mid; else lo = mid + 1; }
+                        b = lo;
+                    }
+                    tile[r * stride + f] = (uint8_t)b;
+                }
+            }
+        }
+        if (labels) for (int r = tid; r < rows; r += bd) tile[r * stride + F] = (uint8_t)labels[rb + r];
+        __syncthreads();
+        uint4* dst = (uint4*)(tp + rb * stride);
+        for (int i = tid; i < rows * stride / 16; i += bd) st_stream_u4(dst + i, ((const uint4*)tile)[i]);
+    }
+}
+
+// ------------------------------------------------------------------ R6 bagging
+constexpr int kBagBlockRows = 1024;
+
+__global__ void __launch_bounds__(256) bag_count_kernel(uint64_t seed, int64_t row_offset, int64_t n,
+                                                        const uint32_t* __restrict__ cdf, int32_t* blk_cnt, int64_t n_blocks) {
+    __shared__ uint32_t cdf_sh[32];
+    __shared__ int cnt_sh;
+    const int t = blockIdx.y;
+    if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
+    if (threadIdx.x == 0) cnt_sh = 0;
+    __syncthreads();
+    const int64_t rb = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int64_t i = rb + k;
+        if (i < n) c += (cdf ? bag_weight(seed, t, (uint64_t)(row_offset + i), cdf_sh) : 1u) > 0 ? 1 : 0;
+    }
+    c = warp_sum(c);
+    if (lane_id() == 0 && c) atomicAdd(&cnt_sh, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blk_cnt[(int64_t)t * n_blocks + blockIdx.x] = cnt_sh;
+}
+
+__global__ void __launch_bounds__(256) bag_fill_kernel(uint64_t seed, int64_t row_offset, int64_t n,
+                                                       const uint32_t* __restrict__ cdf, const int64_t* __restrict__ blk_off,
+                                                       int64_t n_blocks, int32_t* ent_row, uint8_t* ent_w) {
+    __shared__ uint32_t cdf_sh[32];
+    __shared__ int sh[33];
+    const int t = blockIdx.y;
+    if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
+    __syncthreads();
+    const int64_t rb = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
+    uint32_t w[4]; int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int64_t i = rb + k;
+        w[k] = (i < n) ? (cdf ? bag_weight(seed, t, (uint64_t)(row_offset + i), cdf_sh) : 1u) : 0u;
+        c += w[k] > 0 ? 1 : 0;
+    }
+    int tot;
+    int ex = block_exclusive_scan(c, sh, &tot);
+    int64_t pos = blk_off[(int64_t)t * n_blocks + blockIdx.x] + ex;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (w[k] > 0) { ent_row[pos] = (int32_t)(rb + k); ent_w[pos] = (uint8_t)min(w[k], 255u); ++pos; }
+}
+
+}  // namespace b200flow
+
+using namespace b200flow;
+
+extern "C" int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* out, int64_t* total, void* stream) {
+    B2F_REQUIRE(in && out && n >= 0, "scan: bad arguments");
+    scan_i32_i64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(in, n, out, total);
+    return check_launch("exclusive_scan");
+}
+
+extern "C" int b200flow_sample_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, int64_t ld, uint64_t seed,
+                                    uint64_t keep_threshold, int64_t row_offset, double* sample, int64_t cap,
+                                    int32_t* n_sampled, void* stream) {
+    B2F_REQUIRE(x && sample && n_sampled && F > 0 && ld >= F && cap > 0, "sample_rows: bad arguments");
+    if (n_rows <= 0) return B200FLOW_OK;
+    int grid = grid_for(n_rows, 256 * 4, kNumSMs * 8);
+    if (dtype == B200FLOW_F32)
+        sample_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, n_rows, F, ld, seed, keep_threshold, row_offset, sample, cap, n_sampled);
+    else if (dtype == B200FLOW_F64)
+        sample_rows_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, n_rows, F, ld, seed, keep_threshold, row_offset, sample, cap, n_sampled);
+    else { set_error("sample_rows: bad dtype"); return B200FLOW_ERR_ARG; }
+    return check_launch("sample_rows");
+}
+
+extern "C" int b200flow_find_splits(double* sample, int64_t cap, int32_t n_s, int32_t F, const int32_t* arity,
+                                    int32_t max_bins, double* thresholds, int32_t* n_thr, void* stream) {
+    B2F_REQUIRE(sample && arity && thresholds && n_thr && F > 0 && max_bins >= 2 && max_bins <= 256, "find_splits: bad arguments");
+    B2F_REQUIRE(n_s >= 0 && n_s <= cap, "find_splits: n_s exceeds cap");
+    int n_pad = 1; while (n_pad < n_s) n_pad <<= 1;
+    B2F_REQUIRE(n_pad <= cap, "find_splits: cap must be >= pow2ceil(n_s)");
+    find_splits_kernel<<<F, 1024, 0, (cudaStream_t)stream>>>(sample, cap, n_s, n_pad, arity, max_bins, thresholds, n_thr);
+    return check_launch("find_splits");
+}
+
+extern "C" int b200flow_bin_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, int64_t ld,
+                                 const double* thresholds, const int32_t* n_thr, const int32_t* arity, int32_t max_bins,
+                                 const int32_t* labels, uint8_t* tp, int32_t tp_stride, int32_t* bad_rows, void* stream) {
+    B2F_REQUIRE(x && thresholds && n_thr && arity && tp && bad_rows, "bin_rows: null pointer");
+    B2F_REQUIRE(F > 0 && F < 65536 && ld >= F && tp_stride >= F + 1 && (tp_stride & 15) == 0 && max_bins >= 2 && max_bins <= 256,
+                "bin_rows: bad shape (F=%d stride=%d max_bins=%d)", F, tp_stride, max_bins);
+    B2F_REQUIRE(((uintptr_t)tp & 15) == 0, "bin_rows: tp must be 16-byte aligned");
+    if (n_rows <= 0) return B200FLOW_OK;
+    size_t thr_bytes = (size_t)F * (max_bins - 1) * 8;
+    int thr_in_smem = thr_bytes <= 96 * 1024;
+    int R = 4096 / tp_stride; if (R < 8) R = 8; if (R > 128) R = 128;
+    size_t smem = (((size_t)R * tp_stride + 15) & ~(size_t)15) + (thr_in_smem ? thr_bytes : 0);
+    int64_t n_tiles = (n_rows + R - 1) / R;
+    int per_sm = (int)((200 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
+    int grid = (int)(n_tiles < (int64_t)kNumSMs * per_sm ? n_tiles : (int64_t)kNumSMs * per_sm);
+    cudaError_t e;
+    if (dtype == B200FLOW_F32) {
+        e = cudaFuncSetAttribute(bin_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) bin_rows_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)x, n_rows, F, ld, thresholds, n_thr, arity, max_bins, labels, tp, tp_stride, bad_rows, R, thr_in_smem);
+    } else if (dtype == B200FLOW_F64) {
+        e = cudaFuncSetAttribute(bin_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) bin_rows_kernel<double><<<grid, 256, smem, (cudaStream_t)stream>>>((const double*)x, n_rows, F, ld, thresholds, n_thr, arity, max_bins, labels, tp, tp_stride, bad_rows, R, thr_in_smem);
+    } else { set_error("bin_rows: bad dtype"); return B200FLOW_ERR_ARG; }
+    if (e != cudaSuccess) { set_error("bin_rows: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
+    return check_launch("bin_rows");
+}
+
+extern "C" int b200flow_bag_count(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows, const uint32_t* poisson_cdf,
+                                  int32_t* blk_cnt, void* stream) {
+    B2F_REQUIRE(blk_cnt && T > 0 && T <= 65535 && n_rows >= 0, "bag_count: bad arguments");
+    if (n_rows == 0) return B200FLOW_OK;
+    int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
+    bag_count_kernel<<<dim3((unsigned)nb, (unsigned)T), 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n_rows, poisson_cdf, blk_cnt, nb);
+    return check_launch("bag_count");
+}
+
+extern "C" int b200flow_bag_fill(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows, const uint32_t* poisson_cdf,
+                                 const int64_t* blk_off, int32_t* ent_row, uint8_t* ent_w, void* stream) {
+    B2F_REQUIRE(blk_off && ent_row && ent_w && T > 0 && T <= 65535 && n_rows >= 0 && n_rows < ((int64_t)1 << 31), "bag_fill: bad arguments");
+    if (n_rows == 0) return B200FLOW_OK;
+    int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
+    bag_fill_kernel<<<dim3((unsigned)nb, (unsigned)T), 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n_rows, poisson_cdf, blk_off, nb, ent_row, ent_w);
+    return check_launch("bag_fill");
+}
