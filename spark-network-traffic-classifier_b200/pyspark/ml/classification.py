@@ -1,0 +1,342 @@
+"""pyspark.ml.classification shim.
+
+RandomForestClassifier / DecisionTreeClassifier (kdd99.py:61,64; cicids17.py:65,68) are the hot path and run
+entirely on the b200flow CUDA kernels (histogram build, Gini split scoring, batch predict).
+LogisticRegression and NaiveBayes (kdd99.py:57,67; cicids17.py:61,71) are OUT of the kernel scope (SURVEY.md
+§8f rank 4): they are small torch implementations that exist only so the reference scripts run to completion.
+"""
+import zlib
+
+import numpy as np
+import torch
+
+from b200flow import forest as fr
+
+from . import Estimator, Model
+from ..sql import ColumnData
+from .feature import IllegalArgumentException, _materialize
+
+
+def _default_seed(obj):
+    # pyspark uses hash(type(self).__name__), which Python 3 randomises per process; a stable hash is used instead
+    return zlib.crc32(type(obj).__name__.encode())
+
+
+def _features_and_labels(df, est):
+    fcol, lcol = est.getOrDefault("featuresCol"), est.getOrDefault("labelCol")
+    for c in (fcol, lcol):
+        if c not in df._cols:
+            raise IllegalArgumentException("Field \"%s\" does not exist." % c)
+    fc = df._cols[fcol]
+    if fc.kind != "vector":
+        raise IllegalArgumentException("Column %s must be of type vector" % fcol)
+    x = fc.data
+    y = df._column_tensor(lcol)
+    lab_meta = df._cols[lcol].meta.get("ml_attr", {})
+    if lab_meta.get("type") == "nominal":
+        num_classes = len(lab_meta["vals"])
+    else:
+        if bool(((y < 0) | (y != torch.floor(y))).any().item()):
+            raise IllegalArgumentException("Classifier was given dataset with invalid label. Labels must be integers in [0, numClasses).")
+        num_classes = int(y.max().item()) + 1 if y.numel() else 0
+    return x, y, num_classes, fc.meta.get("attrs")
+
+
+def _arity_from_attrs(attrs, F):
+    if not attrs or len(attrs) != F:
+        return [0] * F
+    return [int(a.get("arity", 0)) if a.get("type") in ("nominal", "binary") else 0 for a in attrs]
+
+
+class _TreeParams:
+    _defaults = {"featuresCol": "features", "labelCol": "label", "predictionCol": "prediction",
+                 "probabilityCol": "probability", "rawPredictionCol": "rawPrediction", "maxDepth": 5, "maxBins": 32,
+                 "minInstancesPerNode": 1, "minInfoGain": 0.0, "maxMemoryInMB": 256, "cacheNodeIds": False,
+                 "checkpointInterval": 10, "impurity": "gini", "seed": None}
+
+
+class _TreeClassifierBase(Estimator, _TreeParams):
+    def _forest_params(self, num_trees, strategy, subsampling, bootstrap):
+        imp = str(self.getOrDefault("impurity")).lower()
+        if imp not in ("gini", "entropy"):
+            raise IllegalArgumentException("impurity must be gini or entropy, got %r" % imp)
+        seed = self.getOrDefault("seed")
+        return fr.ForestParams(num_trees=int(num_trees), max_depth=int(self.getOrDefault("maxDepth")),
+                               max_bins=int(self.getOrDefault("maxBins")),
+                               min_instances_per_node=int(self.getOrDefault("minInstancesPerNode")),
+                               min_info_gain=float(self.getOrDefault("minInfoGain")), feature_subset_strategy=str(strategy),
+                               subsampling_rate=float(subsampling), impurity=imp,
+                               seed=_default_seed(self) if seed is None else int(seed), bootstrap=bootstrap)
+
+    def _train(self, df, params):
+        x, y, C, attrs = _features_and_labels(df, self)
+        if C > 100:
+            raise IllegalArgumentException("Classifier inferred %d classes; maximum is 100" % C)
+        try:
+            forest = fr.fit_forest(x, y.to(torch.int32), C, _arity_from_attrs(attrs, x.shape[1]), params)
+        except ValueError as e:
+            raise IllegalArgumentException(str(e))
+        return forest
+
+
+class RandomForestClassifier(_TreeClassifierBase):
+    _defaults = {"numTrees": 20, "featureSubsetStrategy": "auto", "subsamplingRate": 1.0}
+
+    def __init__(self, featuresCol=None, labelCol=None, predictionCol=None, probabilityCol=None, rawPredictionCol=None,
+                 maxDepth=None, maxBins=None, minInstancesPerNode=None, minInfoGain=None, maxMemoryInMB=None,
+                 cacheNodeIds=None, checkpointInterval=None, impurity=None, numTrees=None, featureSubsetStrategy=None,
+                 seed=None, subsamplingRate=None):
+        kw = dict(locals()); kw.pop("self"); kw.pop("__class__", None)
+        super().__init__(**kw)
+
+    def _fit(self, df):
+        p = self._forest_params(self.getOrDefault("numTrees"), self.getOrDefault("featureSubsetStrategy"),
+                                self.getOrDefault("subsamplingRate"), bootstrap=True)
+        m = RandomForestClassificationModel(self._train(df, p))
+        m._paramMap = {k: v for k, v in self._paramMap.items() if k in m._all_defaults()}
+        return m
+
+
+class DecisionTreeClassifier(_TreeClassifierBase):
+    """MLlib trains it as RandomForest.run(numTrees=1, featureSubsetStrategy='all'), no bagging."""
+
+    def __init__(self, featuresCol=None, labelCol=None, predictionCol=None, probabilityCol=None, rawPredictionCol=None,
+                 maxDepth=None, maxBins=None, minInstancesPerNode=None, minInfoGain=None, maxMemoryInMB=None,
+                 cacheNodeIds=None, checkpointInterval=None, impurity=None, seed=None):
+        kw = dict(locals()); kw.pop("self"); kw.pop("__class__", None)
+        super().__init__(**kw)
+
+    def _fit(self, df):
+        p = self._forest_params(1, "all", 1.0, bootstrap=False)
+        m = DecisionTreeClassificationModel(self._train(df, p))
+        m._paramMap = {k: v for k, v in self._paramMap.items() if k in m._all_defaults()}
+        return m
+
+
+class _ForestModelBase(Model, _TreeParams):
+    def __init__(self, forest):
+        super().__init__()
+        self._forest = forest
+
+    @property
+    def numClasses(self):
+        return self._forest.C
+
+    @property
+    def numFeatures(self):
+        return self._forest.F
+
+    @property
+    def totalNumNodes(self):
+        return self._forest.n_nodes
+
+    @property
+    def featureImportances(self):
+        from .linalg import DenseVector
+        return DenseVector(self._forest.feature_importances())
+
+    def _transform(self, df):
+        fcol = self.getOrDefault("featuresCol")
+        if fcol not in df._cols or df._cols[fcol].kind != "vector":
+            raise IllegalArgumentException("Column %s must be of type vector" % fcol)
+        x = df._cols[fcol].data
+        raw, prob, pred = self._forest.predict(x)          # R9: bin + walk all trees on the GPU
+        cols = dict(df._cols)
+        for name, key, kind in ((self.getOrDefault("rawPredictionCol"), raw, "vector"),
+                                (self.getOrDefault("probabilityCol"), prob, "vector"),
+                                (self.getOrDefault("predictionCol"), pred, "numeric")):
+            if name:
+                if name in cols:
+                    raise IllegalArgumentException("Output column %s already exists." % name)
+                cols[name] = ColumnData(kind, key, "f64")
+        return df._with(cols=cols)
+
+    def _tree_strings(self):
+        ex = self._forest.export()
+        thr = self._forest.thresholds.cpu().numpy()
+        out = []
+        for t in range(self._forest.T):
+            sel = np.nonzero(ex["tree"] == t)[0]
+            idx = {int(ex["nid"][i]): i for i in sel}
+            lines = []
+
+            def rec(nid, depth):
+                i = idx[nid]
+                pad = " " * (depth + 1)
+                if ex["is_leaf"][i]:
+                    lines.append("%sPredict: %.1f" % (pad, float(np.argmax(ex["counts"][i]))))
+                    return
+                f = int(ex["feat"][i])
+                if ex["kind"][i] == 0:
+                    v = thr[f, int(ex["bin_thr"][i])]
+                    lines.append("%sIf (feature %d <= %s)" % (pad, f, repr(float(v)))); rec(nid * 2, depth + 1)
+                    lines.append("%sElse (feature %d > %s)" % (pad, f, repr(float(v)))); rec(nid * 2 + 1, depth + 1)
+                else:
+                    cats = [c for c in range(256) if (int(ex["mask"][i][c >> 6]) >> (c & 63)) & 1]
+                    s = "{%s}" % ",".join("%.1f" % c for c in cats)
+                    lines.append("%sIf (feature %d in %s)" % (pad, f, s)); rec(nid * 2, depth + 1)
+                    lines.append("%sElse (feature %d not in %s)" % (pad, f, s)); rec(nid * 2 + 1, depth + 1)
+            rec(1, 0)
+            out.append((len(sel), lines))
+        return out
+
+
+class RandomForestClassificationModel(_ForestModelBase):
+    _defaults = {"numTrees": 20, "featureSubsetStrategy": "auto", "subsamplingRate": 1.0}
+
+    @property
+    def getNumTrees(self):
+        return self._forest.T
+
+    @property
+    def treeWeights(self):
+        return [1.0] * self._forest.T
+
+    @property
+    def toDebugString(self):
+        parts = ["RandomForestClassificationModel with %d trees" % self._forest.T]
+        for t, (nn, lines) in enumerate(self._tree_strings()):
+            parts.append("  Tree %d (weight 1.0):" % t)
+            parts += ["  " + l for l in lines]
+        return "\n".join(parts) + "\n"
+
+    def __repr__(self):
+        return "RandomForestClassificationModel with %d trees" % self._forest.T
+
+
+class DecisionTreeClassificationModel(_ForestModelBase):
+    @property
+    def numNodes(self):
+        return self._forest.n_nodes
+
+    @property
+    def depth(self):
+        nid = self._forest.export()["nid"].astype(np.int64)
+        return int(np.floor(np.log2(nid.max()))) if len(nid) else 0
+
+    @property
+    def toDebugString(self):
+        nn, lines = self._tree_strings()[0]
+        return "DecisionTreeClassificationModel of depth %d with %d nodes\n%s\n" % (self.depth, nn, "\n".join(lines))
+
+    def __repr__(self):
+        return "DecisionTreeClassificationModel of depth %d with %d nodes" % (self.depth, self.numNodes)
+
+
+# ------------------------------------------------------------------------------- out-of-scope models (torch)
+class _ProbModel(Model):
+    _defaults = {"featuresCol": "features", "labelCol": "label", "predictionCol": "prediction",
+                 "probabilityCol": "probability", "rawPredictionCol": "rawPrediction"}
+
+    def _emit(self, df, raw):
+        prob = torch.softmax(raw, 1)
+        pred = torch.argmax(raw, 1).to(torch.float64)
+        cols = dict(df._cols)
+        cols[self.getOrDefault("rawPredictionCol")] = ColumnData("vector", raw, "f64")
+        cols[self.getOrDefault("probabilityCol")] = ColumnData("vector", prob, "f64")
+        cols[self.getOrDefault("predictionCol")] = ColumnData("numeric", pred, "f64")
+        return df._with(cols=cols)
+
+
+class LogisticRegression(Estimator):
+    """Multinomial elastic-net logistic regression on standardized features, proximal gradient (FISTA) — a
+    functional stand-in for MLlib's OWLQN (not a parity target; kdd99.py:57, cicids17.py:61)."""
+    _defaults = dict(_ProbModel._defaults, maxIter=100, regParam=0.0, elasticNetParam=0.0, tol=1e-6, fitIntercept=True,
+                     standardization=True, family="auto", threshold=0.5)
+
+    def __init__(self, featuresCol=None, labelCol=None, predictionCol=None, maxIter=None, regParam=None,
+                 elasticNetParam=None, tol=None, fitIntercept=None, threshold=None, probabilityCol=None,
+                 rawPredictionCol=None, standardization=None, family=None):
+        kw = dict(locals()); kw.pop("self"); kw.pop("__class__", None)
+        super().__init__(**kw)
+
+    def _fit(self, df):
+        x, y, C, _ = _features_and_labels(df, self)
+        x = x.to(torch.float64); n, D = x.shape
+        std = x.std(0, unbiased=True); inv = torch.where(std > 0, 1.0 / std, torch.zeros_like(std))
+        xs = x * inv
+        Y = torch.nn.functional.one_hot(y.long(), C).to(torch.float64)
+        lam, alpha = float(self.getOrDefault("regParam")), float(self.getOrDefault("elasticNetParam"))
+        l1, l2 = lam * alpha, lam * (1.0 - alpha)
+        W = torch.zeros((D, C), dtype=torch.float64, device=x.device)
+        pri = Y.mean(0).clamp_min(1e-12)
+        b = torch.log(pri) - torch.log(pri).mean()
+        L = 0.25 * float((xs * xs).sum(1).mean().item()) + l2 + 1e-12     # Lipschitz bound of the smooth part
+        Z, t = W.clone(), 1.0
+        for _ in range(int(self.getOrDefault("maxIter"))):
+            P = torch.softmax(xs @ Z + b, 1)
+            G = xs.t() @ (P - Y) / n + l2 * Z
+            if self.getOrDefault("fitIntercept"):
+                b = b - (P - Y).mean(0) / 0.25
+            Wn = Z - G / L
+            Wn = torch.sign(Wn) * torch.clamp(Wn.abs() - l1 / L, min=0.0)
+            tn = 0.5 * (1.0 + (1.0 + 4.0 * t * t) ** 0.5)
+            Z = Wn + ((t - 1.0) / tn) * (Wn - W)
+            W, t = Wn, tn
+        m = LogisticRegressionModel((W * inv[:, None]).contiguous(), b, C)
+        m._paramMap = {k: v for k, v in self._paramMap.items() if k in m._all_defaults()}
+        return m
+
+
+class LogisticRegressionModel(_ProbModel):
+    def __init__(self, W, b, C):
+        super().__init__()
+        self._W, self._b, self.numClasses = W, b, C
+
+    @property
+    def coefficientMatrix(self):
+        return self._W.t().cpu().numpy()
+
+    @property
+    def interceptVector(self):
+        return self._b.cpu().numpy()
+
+    def _transform(self, df):
+        x = df._cols[self.getOrDefault("featuresCol")].data.to(torch.float64)
+        return self._emit(df, x @ self._W + self._b)
+
+
+class NaiveBayes(Estimator):
+    """Multinomial naive Bayes with Laplace smoothing (kdd99.py:67, cicids17.py:71); rejects negative features
+    as MLlib does (the reason for the where-filters at cicids17.py:30-35)."""
+    _defaults = dict(_ProbModel._defaults, smoothing=1.0, modelType="multinomial")
+
+    def __init__(self, featuresCol=None, labelCol=None, predictionCol=None, probabilityCol=None, rawPredictionCol=None,
+                 smoothing=None, modelType=None):
+        kw = dict(locals()); kw.pop("self"); kw.pop("__class__", None)
+        super().__init__(**kw)
+
+    def _fit(self, df):
+        if self.getOrDefault("modelType") != "multinomial":
+            raise IllegalArgumentException("only modelType='multinomial' is implemented")
+        x, y, C, _ = _features_and_labels(df, self)
+        x = x.to(torch.float64)
+        if bool((x < 0).any().item()):
+            raise IllegalArgumentException("requirement failed: Naive Bayes requires nonnegative feature values but found a negative value.")
+        Y = torch.nn.functional.one_hot(y.long(), C).to(torch.float64)
+        lam = float(self.getOrDefault("smoothing"))
+        cls_n = Y.sum(0)
+        feat = Y.t() @ x                                             # [C, D] per-class feature sums
+        pi = torch.log(cls_n + lam) - torch.log(cls_n.sum() + C * lam)
+        theta = torch.log(feat + lam) - torch.log(feat.sum(1, keepdim=True) + x.shape[1] * lam)
+        m = NaiveBayesModel(pi, theta, C)
+        m._paramMap = {k: v for k, v in self._paramMap.items() if k in m._all_defaults()}
+        return m
+
+
+class NaiveBayesModel(_ProbModel):
+    def __init__(self, pi, theta, C):
+        super().__init__()
+        self._pi, self._theta, self.numClasses = pi, theta, C
+
+    @property
+    def pi(self):
+        return self._pi.cpu().numpy()
+
+    @property
+    def theta(self):
+        return self._theta.cpu().numpy()
+
+    def _transform(self, df):
+        x = df._cols[self.getOrDefault("featuresCol")].data.to(torch.float64)
+        return self._emit(df, x @ self._theta.t() + self._pi)

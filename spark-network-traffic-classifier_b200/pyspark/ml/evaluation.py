@@ -1,0 +1,33 @@
+"""pyspark.ml.evaluation.MulticlassClassificationEvaluator (kdd99.py:86-91; cicids17.py:90-95):
+confusion counts by the b200flow kernel (R10), metrics per MulticlassMetrics (A.8) + macro-F1."""
+import torch
+
+from b200flow import forest as fr
+
+from .param import Params
+
+
+class MulticlassClassificationEvaluator(Params):
+    _defaults = {"predictionCol": "prediction", "labelCol": "label", "metricName": "f1"}
+    _metrics = ("f1", "accuracy", "weightedPrecision", "weightedRecall", "macroF1")
+
+    def __init__(self, predictionCol=None, labelCol=None, metricName=None):
+        super().__init__(predictionCol=predictionCol, labelCol=labelCol, metricName=metricName)
+
+    def confusionMatrix(self, dataset):
+        pred = dataset._column_tensor(self.getOrDefault("predictionCol")).to(torch.float64).contiguous()
+        lab = dataset._column_tensor(self.getOrDefault("labelCol")).to(torch.float64).contiguous()
+        if pred.numel() == 0:
+            return torch.zeros((1, 1), dtype=torch.int64)
+        C = int(torch.maximum(pred.max(), lab.max()).item()) + 1
+        return fr.confusion_matrix(pred, lab, C).cpu()
+
+    def evaluate(self, dataset, params=None):
+        ev = self.copy(params) if params else self
+        name = ev.getOrDefault("metricName")
+        if name not in self._metrics:
+            raise ValueError("metricName must be one of %s, got %r" % (list(self._metrics), name))
+        return fr.metrics_from_confusion(ev.confusionMatrix(dataset).numpy())[name]
+
+    def isLargerBetter(self):
+        return True

@@ -1,0 +1,332 @@
+"""pyspark.ml.feature shim: StringIndexer, VectorAssembler (used by the reference scripts: kdd99.py:34-35,45-46;
+cicids17.py:41-46) and OneHotEncoder, StandardScaler (named by the north star) — all executed by the fused
+b200flow encode kernel.  Each output column remembers how it derives from the raw record fields
+(ColumnData.prov), so VectorAssembler / StandardScaler re-run ONE fused kernel over the raw AoS records
+instead of chaining per-stage passes (StringIndexer lookup + one-hot expand + scale + assemble).
+"""
+import copy
+
+import numpy as np
+import torch
+
+from b200flow import encode as enc
+from b200flow._lib import B200FlowError
+from b200flow.encode import EncodePlan, RecordSchema
+
+from . import Estimator, Model, Transformer
+from ..sql import ColumnData, DataFrame
+
+
+class SparkException(Exception):
+    pass
+
+
+class IllegalArgumentException(ValueError):
+    pass
+
+
+def _check_handle_invalid(v, allowed=("error", "skip", "keep")):
+    if v not in allowed:
+        raise IllegalArgumentException("handleInvalid must be one of %s, got %r" % (list(allowed), v))
+    return v
+
+
+def _dense_schema(D):
+    return RecordSchema([("v%d" % i, "f64") for i in range(D)])
+
+
+def _materialize(df, name):
+    """numeric/vector value of a column as a contiguous f64 [n, k] CUDA tensor."""
+    c = df._cols[name]
+    if c.kind == "field":
+        return df._field_values(name).to(torch.float64).reshape(-1, 1).contiguous()
+    d = c.data
+    return (d.reshape(d.shape[0], -1) if d.dim() == 1 else d).to(torch.float64).contiguous()
+
+
+# ----------------------------------------------------------------------------------- StringIndexer
+class StringIndexer(Estimator):
+    _defaults = {"inputCol": None, "outputCol": None, "handleInvalid": "error", "stringOrderType": "frequencyDesc"}
+
+    def __init__(self, inputCol=None, outputCol=None, handleInvalid=None, stringOrderType=None):
+        super().__init__(inputCol=inputCol, outputCol=outputCol, handleInvalid=handleInvalid, stringOrderType=stringOrderType)
+
+    def _fit(self, df):
+        col = self.getOrDefault("inputCol")
+        if col not in df._cols:
+            raise IllegalArgumentException("Field \"%s\" does not exist." % col)
+        c = df._cols[col]
+        order = self.getOrDefault("stringOrderType")
+        if c.kind == "field" and df._schema.type_of[col] == "code":
+            strings = df._dicts[col]
+            counts = enc.category_counts(df._rec, df._schema, col, max(len(strings), 1)).cpu().numpy()[:len(strings)]
+        else:                                              # numeric column: cast to string like Spark does
+            vals, cnt = torch.unique(_materialize(df, col)[:, 0], return_counts=True)
+            keep = ~torch.isnan(vals)
+            strings = [repr(float(v)) for v in vals[keep].cpu().numpy()]
+            counts = cnt[keep].cpu().numpy()
+        idx = [i for i in range(len(strings)) if counts[i] > 0]
+        if order == "frequencyDesc":                        # ties alphabetical (Spark >= 3.0; 2.4 unspecified)
+            idx.sort(key=lambda i: (-int(counts[i]), strings[i]))
+        elif order == "frequencyAsc":
+            idx.sort(key=lambda i: (int(counts[i]), strings[i]))
+        elif order == "alphabetDesc":
+            idx.sort(key=lambda i: strings[i], reverse=True)
+        elif order == "alphabetAsc":
+            idx.sort(key=lambda i: strings[i])
+        else:
+            raise IllegalArgumentException("unsupported stringOrderType %r" % order)
+        m = StringIndexerModel([strings[i] for i in idx])
+        m._paramMap = dict(self._paramMap)
+        return m
+
+
+class StringIndexerModel(Model):
+    _defaults = dict(StringIndexer._defaults)
+
+    def __init__(self, labels):
+        super().__init__()
+        self.labels = list(labels)
+
+    def _transform(self, df):
+        col, out = self.getOrDefault("inputCol"), self.getOrDefault("outputCol")
+        hi = _check_handle_invalid(self.getOrDefault("handleInvalid"))
+        if col not in df._cols:
+            raise IllegalArgumentException("Field \"%s\" does not exist." % col)
+        if out in df._cols:
+            raise IllegalArgumentException("Output column %s already exists." % out)
+        c = df._cols[col]
+        K = len(self.labels)
+        rank_of = {s: i for i, s in enumerate(self.labels)}
+        if c.kind == "field" and df._schema.type_of[col] == "code":
+            rec, schema, field = df._rec, df._schema, col
+            strings = df._dicts[col]
+            prov_ok = True
+        else:                                              # numeric input: dictionary-encode on the fly (host dictionary)
+            vals = _materialize(df, col)[:, 0]
+            uniq, inv = torch.unique(vals, return_inverse=True)
+            strings = [repr(float(v)) for v in uniq.cpu().numpy()]
+            schema, field = RecordSchema([("c", "code")]), "c"
+            rec = inv.to(torch.int32).contiguous().view(torch.uint8).reshape(-1, 4)
+            prov_ok = False
+        lut = np.array([rank_of.get(s, K if hi == "keep" else -1) for s in strings] or [0], np.int32)
+        plan = EncodePlan(schema).add_index(field, lut)
+        vals, _, valid = plan.run(rec, torch.float64)
+        labels = self.labels + (["__unknown"] if hi == "keep" else [])
+        newc = ColumnData("numeric", vals.view(-1), "f64", {"ml_attr": {"type": "nominal", "vals": labels}},
+                          ("index", field, lut, labels) if prov_ok else None)
+        cols = dict(df._cols); cols[out] = newc
+        res = df._with(cols=cols)
+        if hi != "keep":
+            n_bad = int((valid == 0).sum().item())
+            if n_bad:
+                if hi == "error":
+                    raise SparkException("Unseen label in column %s (%d rows). To handle unseen labels, set Param "
+                                         "handleInvalid to keep." % (col, n_bad))
+                res = res._compact(valid)
+        return res
+
+
+# ----------------------------------------------------------------------------------- VectorAssembler
+class VectorAssembler(Transformer):
+    _defaults = {"inputCols": None, "outputCol": None, "handleInvalid": "error"}
+
+    def __init__(self, inputCols=None, outputCol=None, handleInvalid=None):
+        super().__init__(inputCols=inputCols, outputCol=outputCol, handleInvalid=handleInvalid)
+
+    def _transform(self, df):
+        cols_in, out = list(self.getOrDefault("inputCols") or []), self.getOrDefault("outputCol")
+        hi = _check_handle_invalid(self.getOrDefault("handleInvalid"))
+        if out in df._cols:
+            raise IllegalArgumentException("Output column %s already exists." % out)
+        for c in cols_in:
+            if c not in df._cols:
+                raise IllegalArgumentException("Field \"%s\" does not exist." % c)
+        fused = df._rec is not None and all(df._cols[c].prov is not None for c in cols_in)
+        attrs = []
+        if fused:
+            plan = EncodePlan(df._schema)
+            for name in cols_in:
+                c = df._cols[name]
+                p = c.prov
+                if p[0] == "field":
+                    if df._schema.type_of[name] == "code":
+                        raise IllegalArgumentException("Data type string of column %s is not supported." % name)
+                    plan.add_numeric(name); attrs.append({"type": "numeric", "name": name})
+                elif p[0] == "index":
+                    plan.add_index(p[1], p[2]); attrs.append({"type": "nominal", "name": name, "arity": len(p[3])})
+                elif p[0] == "onehot":
+                    width = p[3] - 1 if p[4] else p[3]
+                    plan.add_onehot(p[1], p[2], p[3], drop_last=p[4])
+                    attrs += [{"type": "binary", "name": "%s_%d" % (name, k), "arity": 2} for k in range(width)]
+                elif p[0] == "plan":
+                    sub = p[1]
+                    for s in sub.slots:
+                        lo = s[2]
+                        if s[0] >= 3:                        # re-home the slot's LUT in this plan's pool
+                            lo, _ = plan._add_lut(sub.lut_array()[s[2]:s[2] + s[3]])
+                        plan.slots.append((s[0], s[1], lo, s[3], s[4], s[5], s[6]))
+                    attrs += list(c.meta.get("attrs", [{"type": "numeric"}] * sub.n_out))
+                else:
+                    raise B200FlowError("unknown provenance %r" % (p,))
+            plan.check_nan = 1
+            feats, _, valid = plan.run(df._rec, torch.float64)
+            prov = ("plan", plan)
+        else:                                               # columns without raw provenance: concatenate, then one pass
+            parts = [_materialize(df, c) for c in cols_in]
+            for name, part in zip(cols_in, parts):
+                meta = df._cols[name].meta
+                if "attrs" in meta:
+                    attrs += list(meta["attrs"])
+                elif meta.get("ml_attr", {}).get("type") == "nominal":
+                    attrs.append({"type": "nominal", "name": name, "arity": len(meta["ml_attr"]["vals"])})
+                else:
+                    attrs += [{"type": "numeric", "name": name}] * part.shape[1]
+            dense = torch.cat(parts, 1).contiguous()
+            plan = EncodePlan(_dense_schema(dense.shape[1]))
+            for i in range(dense.shape[1]):
+                plan.add_numeric("v%d" % i)
+            plan.check_nan = 1
+            feats, _, valid = plan.run(dense.view(torch.uint8).reshape(dense.shape[0], -1), torch.float64)
+            prov = None
+        newc = ColumnData("vector", feats, "f64", {"attrs": attrs}, prov)
+        cols = dict(df._cols); cols[out] = newc
+        res = df._with(cols=cols)
+        if hi != "keep":
+            n_bad = int((valid == 0).sum().item()) if df._n else 0
+            if n_bad:
+                if hi == "error":
+                    raise SparkException("Encountered NaN/null while assembling a row with handleInvalid = \"error\". Consider "
+                                         "removing NaNs from dataset or using handleInvalid = \"keep\" or \"skip\".")
+                res = res._compact(valid)
+        return res
+
+
+# ----------------------------------------------------------------------------------- OneHotEncoder
+class OneHotEncoder(Estimator):
+    """Spark >= 3.0 OneHotEncoder / 2.3-2.4 OneHotEncoderEstimator (inputCols/outputCols, or single inputCol/outputCol)."""
+    _defaults = {"inputCols": None, "outputCols": None, "inputCol": None, "outputCol": None, "dropLast": True,
+                 "handleInvalid": "error"}
+
+    def __init__(self, inputCols=None, outputCols=None, inputCol=None, outputCol=None, dropLast=None, handleInvalid=None):
+        super().__init__(inputCols=inputCols, outputCols=outputCols, inputCol=inputCol, outputCol=outputCol,
+                         dropLast=dropLast, handleInvalid=handleInvalid)
+
+    def _io(self):
+        if self.getOrDefault("inputCols"):
+            return list(self.getOrDefault("inputCols")), list(self.getOrDefault("outputCols"))
+        return [self.getOrDefault("inputCol")], [self.getOrDefault("outputCol")]
+
+    def _fit(self, df):
+        ins, outs = self._io()
+        if len(ins) != len(outs):
+            raise IllegalArgumentException("The number of input and output columns must match")
+        sizes = []
+        for name in ins:
+            c = df._cols[name]
+            vals = c.meta.get("ml_attr", {}).get("vals")
+            if vals is not None:
+                sizes.append(len(vals))
+            else:
+                v = _materialize(df, name)[:, 0]
+                if bool(((v < 0) | (v != torch.floor(v))).any().item()):
+                    raise SparkException("Values to encode must be non-negative integers")
+                sizes.append(int(v.max().item()) + 1 if v.numel() else 0)
+        m = OneHotEncoderModel(sizes)
+        m._paramMap = dict(self._paramMap)
+        return m
+
+
+OneHotEncoderEstimator = OneHotEncoder
+
+
+class OneHotEncoderModel(Model):
+    _defaults = dict(OneHotEncoder._defaults)
+
+    def __init__(self, categorySizes):
+        super().__init__()
+        self.categorySizes = list(categorySizes)
+
+    def _transform(self, df):
+        ins, outs = OneHotEncoder._io(self)
+        drop = bool(self.getOrDefault("dropLast"))
+        hi = _check_handle_invalid(self.getOrDefault("handleInvalid"), ("error", "keep"))
+        cols = dict(df._cols)
+        for name, out, K in zip(ins, outs, self.categorySizes):
+            if out in cols:
+                raise IllegalArgumentException("Output column %s already exists." % out)
+            c = df._cols[name]
+            ncat = K + 1 if hi == "keep" else K           # 'keep': one extra category for invalid values
+            if c.prov is not None and c.prov[0] == "index" and df._rec is not None:
+                field, lut = c.prov[1], c.prov[2].copy()
+                lut[lut >= K] = K if hi == "keep" else -1
+                rec, schema, prov_ok = df._rec, df._schema, True
+            else:
+                v = _materialize(df, name)[:, 0]
+                rec = v.to(torch.int32).contiguous().view(torch.uint8).reshape(-1, 4)
+                schema, field, prov_ok = RecordSchema([("c", "code")]), "c", False
+                lut = np.arange(K, dtype=np.int32)
+            plan = EncodePlan(schema).add_onehot(field, lut, ncat, drop_last=drop)
+            if plan.n_out == 0:
+                raise IllegalArgumentException("column %s has a single category; nothing to encode with dropLast" % name)
+            vec, _, valid = plan.run(rec, torch.float64)
+            if hi == "error" and df._n and int((valid == 0).sum().item()):
+                raise SparkException("Unseen value in column %s. To handle unseen values, set Param handleInvalid to keep." % name)
+            width = plan.n_out
+            cols[out] = ColumnData("vector", vec, "f64", {"attrs": [{"type": "binary", "name": "%s_%d" % (out, k), "arity": 2}
+                                                                      for k in range(width)]},
+                                   ("onehot", field, lut, ncat, drop) if prov_ok else None)
+        return df._with(cols=cols)
+
+
+# ----------------------------------------------------------------------------------- StandardScaler
+class StandardScaler(Estimator):
+    _defaults = {"inputCol": None, "outputCol": None, "withMean": False, "withStd": True}
+
+    def __init__(self, withMean=None, withStd=None, inputCol=None, outputCol=None):
+        super().__init__(withMean=withMean, withStd=withStd, inputCol=inputCol, outputCol=outputCol)
+
+    def _fit(self, df):
+        x = _materialize(df, self.getOrDefault("inputCol"))
+        mean, std = enc.column_moments(x)                  # R3c: corrected two-pass, unbiased (n-1)
+        m = StandardScalerModel(mean.cpu().numpy(), std.cpu().numpy())
+        m._paramMap = dict(self._paramMap)
+        return m
+
+
+class StandardScalerModel(Model):
+    _defaults = dict(StandardScaler._defaults)
+
+    def __init__(self, mean, std):
+        super().__init__()
+        self.mean, self.std = np.asarray(mean, np.float64), np.asarray(std, np.float64)
+
+    def _transform(self, df):
+        name, out = self.getOrDefault("inputCol"), self.getOrDefault("outputCol")
+        if out in df._cols:
+            raise IllegalArgumentException("Output column %s already exists." % out)
+        c = df._cols[name]
+        D = len(self.mean)
+        mean = self.mean if self.getOrDefault("withMean") else np.zeros(D)
+        scale = (np.where(self.std != 0, 1.0 / np.where(self.std != 0, self.std, 1.0), 0.0)
+                 if self.getOrDefault("withStd") else np.ones(D))
+        plan = None
+        if c.prov is not None and c.prov[0] == "plan" and df._rec is not None:
+            src = c.prov[1]
+            if src.n_out == D and all(s[5] == 0.0 and s[6] == 1.0 for s in src.slots):
+                plan = copy.copy(src); plan.slots = list(src.slots); plan.luts = list(src.luts); plan._dev = None
+                plan.label = None
+                plan.set_scaling(mean, scale)              # fused: index + one-hot + scale + assemble from raw records
+                vec, _, _ = plan.run(df._rec, torch.float64, want_valid=False)
+        if plan is None:
+            x = _materialize(df, name)
+            if x.shape[1] != D:
+                raise IllegalArgumentException("vector size %d does not match the fitted size %d" % (x.shape[1], D))
+            plan = EncodePlan(_dense_schema(D))
+            for i in range(D):
+                plan.add_numeric("v%d" % i, mean[i], scale[i])
+            vec, _, _ = plan.run(x.view(torch.uint8).reshape(x.shape[0], -1), torch.float64, want_valid=False)
+            plan = None
+        cols = dict(df._cols)
+        cols[out] = ColumnData("vector", vec, "f64", {"attrs": [{"type": "numeric"}] * D}, ("plan", plan) if plan else None)
+        return df._with(cols=cols)

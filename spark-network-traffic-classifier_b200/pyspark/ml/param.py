@@ -20,7 +20,7 @@ class Params:
     def _all_defaults(cls):
         d = {}
         for klass in reversed(cls.__mro__):
-            d.update(getattr(klass, "_defaults", {}))
+            d.update(klass.__dict__.get("_defaults", {}))
         return d
 
     def getOrDefault(self, name):

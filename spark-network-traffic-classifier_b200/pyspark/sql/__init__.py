@@ -322,7 +322,7 @@ class DataFrame:
             else:
                 d = c.data.contiguous()
                 rb = d.element_size() * (d.shape[1] if d.dim() == 2 else 1)
-                cols[name] = ColumnData(c.kind, run(d, rb) if n > 0 else d, c.dtype, c.meta, None)
+                cols[name] = ColumnData(c.kind, run(d, rb) if n > 0 else d, c.dtype, c.meta, c.prov if rec is not None else None)
         k = int(kept.item()) if (outs) else int(flag.sum().item())
         rec = rec[:k] if rec is not None else None
         for name, c in cols.items():
