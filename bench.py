@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — flow-records/sec of fit+transform on the KDD99-full-shaped workload (BASELINE.json configs[1]:
+4,898,431 rows x 41 features, 5 classes, RandomForest 100 trees depth 16, maxBins 70, 75/25 split).
+
+One "step" = one pass of the hot path over the whole record batch:
+  StringIndexer.fit x4 -> fused encode (index + assemble) -> randomSplit 75/25 -> RandomForest.fit(train)
+  -> model.transform(test) -> confusion/macro-F1.
+`value`  : records/s with the raw AoS records already resident in HBM (b200flow functional API).
+`e2e`    : the same pass through the pyspark.ml-shaped shim (the call a user of the reference makes), starting from
+           PINNED HOST records (H2D inside the timed region) and ending with predictions + metric back on the host.
+`roofline`: dominant kernel (by CUDA-event time inside the timed steps) against the measured HBM copy peak.
+`--impl reference`: the CPU arm — the MLlib-semantics oracle (oracle/, "port": Spark itself cannot run here, no JVM)
+           on all host threads over a bounded row sample of the same workload.
+Launch: python bench.py --gpus N --steps K --warmup W   (N>1 under torchrun; rows are sharded, weak scaling).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "spark-network-traffic-classifier_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+KDD_FULL_ROWS = 4898431
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=KDD_FULL_ROWS, help="rows per GPU")
+    ap.add_argument("--trees", type=int, default=100)
+    ap.add_argument("--depth", type=int, default=16)
+    ap.add_argument("--classes", type=int, default=5)
+    ap.add_argument("--max-bins", type=int, default=70)
+    ap.add_argument("--cpu-rows", type=int, default=250000, help="row sample for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {"workload": "KDD99-full-shaped synthetic flows: %d rows/GPU x 41 features (168-B AoS records), %d-class, "
+                        "RandomForest numTrees=%d maxDepth=%d maxBins=%d, randomSplit 75/25, fit+transform"
+                        % (a.rows, a.classes, a.trees, a.depth, a.max_bins),
+            "rows_per_gpu": a.rows, "global_rows": a.rows * world, "features": 41, "classes": a.classes,
+            "num_trees": a.trees, "max_depth": a.depth, "max_bins": a.max_bins,
+            "parallelism": "rows sharded over %d GPU(s), per-level histogram all-reduce" % world,
+            "l2_policy": "inputs (%.0f MB records per GPU) larger than the 126 MB L2" % (a.rows * 168 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_pass(rec_np, dicts, a):
+    """the oracle's (MLlib-semantics CPU restatement) version of one step on a host record batch."""
+    import oracle
+    from b200flow import synth
+    from b200flow.encode import EncodePlan
+    schema = synth.kdd_schema()
+    luts, ordered = {}, {}
+    for c in synth.KDD_CATEGORICAL + ["label"]:
+        cnt = oracle.category_counts(rec_np, schema.row_bytes, schema.offsets[c], len(dicts[c]))
+        ordered[c], luts[c] = oracle.string_index_order(cnt, dicts[c])
+    plan = EncodePlan(schema)                                   # plan container only (host bookkeeping, no kernels)
+    for c in synth.KDD_COLUMNS:
+        if c not in synth.KDD_CATEGORICAL and c != "label":
+            plan.add_numeric(c)
+    for c in synth.KDD_CATEGORICAL:
+        plan.add_index(c, luts[c])
+    plan.set_label("label", luts["label"])
+    x, y, _ = oracle.encode(rec_np, schema.row_bytes, plan.slot_array(), plan.lut_array(), *plan.label)
+    sid = oracle.random_split(2019, len(y), [0.75, 1.0])
+    tr = sid == 0
+    arity = [0] * 38 + [len(ordered[c]) for c in synth.KDD_CATEGORICAL]
+    C = len(ordered["label"])
+    fo, meta = oracle.fit_forest(x[tr], y[tr], C, arity, num_trees=a.trees, max_bins=a.max_bins, max_depth=a.depth, seed=2019)
+    tp, _ = oracle.bin_rows(x[~tr], meta["thresholds"], meta["n_thr"], meta["arity"], meta["max_bins"])
+    _, _, pred = fo.predict(tp)
+    cm = oracle.confusion(pred, y[~tr].astype(np.float64), C)
+    return oracle.metrics(cm)["macroF1"]
+
+
+def run_reference(a):
+    """--impl reference: rank 0 only; times the CPU arm on a bounded sample with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from b200flow import synth
+    rec, dicts = synth.make_kdd(a.cpu_rows, a.classes, seed=2019, device="cpu")
+    rec_np = rec.numpy()
+    for _ in range(min(a.warmup, 1)):
+        cpu_pass(rec_np[:20000], dicts, a)
+    t = []
+    f1 = 0.0
+    for _ in range(a.steps):
+        t0 = time.perf_counter(); f1 = cpu_pass(rec_np, dicts, a); t.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(t) / len(t)
+    v = a.cpu_rows / (ms / 1e3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {"impl": "reference", "metric": "flow-records/sec fit+transform", "value": v, "unit": "records/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
+            "macro_f1": f1,
+            "cpu_baseline": {"value": v, "unit": "records/s", "cores": oracle.num_threads(), "kind": "port",
+                             "sample": "%d-row sample of the workload (same generator/seed), full 100-tree depth-16 forest; "
+                                       "oracle = C++/OpenMP restatement of MLlib (Spark needs a JVM: absent)" % a.cpu_rows},
+            "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:                                  # NVML missing: report that instead of dying
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def step_resident(rec, dicts, a, grp):
+    """one pass with the records resident in HBM, functional API.  Returns (macroF1, n_test_local)."""
+    from b200flow import dist as bdist, encode as enc, forest as fr, rows, synth
+    schema = synth.kdd_schema()
+    dev = rec.device
+    n = rec.shape[0]
+    luts, ordered = {}, {}
+    for c in synth.KDD_CATEGORICAL + ["label"]:                                     # R1 StringIndexer.fit
+        cnt = bdist.all_reduce_sum_(enc.category_counts(rec, schema, c, len(dicts[c])), grp).cpu().numpy()
+        ordered[c], luts[c] = enc.string_index_order(cnt, dicts[c])
+    plan = enc.EncodePlan(schema)
+    for c in synth.KDD_COLUMNS:
+        if c not in synth.KDD_CATEGORICAL and c != "label":
+            plan.add_numeric(c)
+    for c in synth.KDD_CATEGORICAL:
+        plan.add_index(c, luts[c])
+    plan.set_label("label", luts["label"])
+    x, y, _ = plan.run(rec, torch.float32, want_valid=False)                        # R2+R3 fused encode
+    off, _ = bdist.global_offset(n, dev, grp)
+    sid = rows.random_split_ids(n, [0.75, 0.25], 2019, off, dev)
+    (xtr, ytr), ntr = rows.compact_many([x, y], sid == 0)
+    (xte, yte), nte = rows.compact_many([x, y], sid == 1)
+    del x, y
+    arity = [0] * 38 + [len(ordered[c]) for c in synth.KDD_CATEGORICAL]
+    C = len(ordered["label"])
+    p = fr.ForestParams(num_trees=a.trees, max_depth=a.depth, max_bins=a.max_bins, seed=2019)
+    toff, _ = bdist.global_offset(ntr, dev, grp)
+    model = fr.fit_forest(xtr, ytr, C, arity, p, row_offset=toff, group=grp)       # R4-R8
+    raw, prob, pred = model.predict(xte)                                            # R9
+    cm = bdist.all_reduce_sum_(fr.confusion_matrix(pred, yte.to(torch.float64), C), grp)   # R10
+    f1 = fr.metrics_from_confusion(cm.cpu().numpy())["macroF1"]
+    return f1, nte, model.train_stats, model.n_nodes
+
+
+def step_e2e(host_rec, dicts, a):
+    """the same pass through the pyspark.ml-shaped shim, from pinned host records to host predictions."""
+    from b200flow import synth
+    from pyspark.ml import Pipeline
+    from pyspark.ml.classification import RandomForestClassifier
+    from pyspark.ml.evaluation import MulticlassClassificationEvaluator
+    from pyspark.ml.feature import StringIndexer, VectorAssembler
+    from pyspark.sql import DataFrame
+    dataset = DataFrame.fromRecords(host_rec, synth.kdd_schema(), dicts)            # H2D of the raw records
+    cats = synth.KDD_CATEGORICAL
+    indexers = [StringIndexer(inputCol=c, outputCol=c + "_num") for c in cats]
+    indexers.append(StringIndexer(inputCol="label", outputCol="label_num"))
+    dataset = Pipeline(stages=indexers).fit(dataset).transform(dataset)
+    numerical = [c for c in dataset.columns if c not in cats + ["label", "label_num"]]
+    dataset = VectorAssembler(inputCols=numerical, outputCol="features").transform(dataset)
+    dataset = dataset.select(["features", "label_num"])
+    train, test = dataset.randomSplit([0.75, 0.25], seed=2019)
+    rf = RandomForestClassifier(labelCol="label_num", featuresCol="features", numTrees=a.trees, maxBins=a.max_bins,
+                                maxDepth=a.depth, seed=2019)
+    pred = rf.fit(train).transform(test)
+    ev = MulticlassClassificationEvaluator(labelCol="label_num", predictionCol="prediction", metricName="macroF1")
+    f1 = ev.evaluate(pred)
+    host_pred = pred._cols["prediction"].data.cpu()                                 # D2H of the step's result
+    return f1, host_pred
+
+
+def timed(fn, steps, warmup, grp):
+    import torch.distributed as dist
+    out = None
+    for _ in range(warmup):
+        out = fn()
+    if grp is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if grp is not None:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if grp is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / steps, out
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch.distributed as dist
+    from b200flow import _lib, forest as fr, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    _lib.require_cuda()
+    grp = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        grp = dist.group.WORLD
+    dev = torch.device("cuda", local)
+    rec, dicts = synth.make_kdd(a.rows, a.classes, seed=2019, device=dev, row_offset=rank * a.rows)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- value: records resident in HBM --------------------------------------------------------------
+    for _ in range(a.warmup):
+        step_resident(rec, dicts, a, grp)
+    fr.PROFILE = {}
+    if sampler:
+        sampler.start()
+    k0 = _lib.launches
+    ms_step, (f1, nte, stats, n_nodes) = timed(lambda: step_resident(rec, dicts, a, grp), a.steps, 0, grp)
+    launches = (_lib.launches - k0) // a.steps
+    prof = fr.profile_totals()
+    hist_entries = float(sum(float(t.item()) for t in fr.PROFILE.get("_hist_entries", [])))
+    fr.PROFILE = None
+    global_rows = a.rows * world
+    value = global_rows / (ms_step / 1e3)
+
+    # ---- e2e: host records -> shim -> host predictions -----------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        host_rec = rec.cpu().pin_memory()
+        ms_e2e, (f1_e2e, host_pred) = timed(lambda: step_e2e(host_rec, dicts, a), a.steps, min(a.warmup, 1), grp)
+        e2e = {"value": global_rows / (ms_e2e / 1e3), "unit": "records/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(host_rec.numel()), "d2h_bytes_per_step": int(host_pred.numel() * 8 + 8),
+               "macro_f1": f1_e2e, "api": "pyspark.ml shim: Pipeline(StringIndexer x4) -> VectorAssembler -> randomSplit -> "
+                                          "RandomForestClassifier.fit -> transform -> MulticlassClassificationEvaluator"}
+        del host_rec
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA events on the launching stream, inside the timed steps) -----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    kern = {k: {"launches_per_step": v[0] // a.steps, "ms_per_step": v[1] / a.steps, "share_of_step": v[1] / a.steps / ms_step}
+            for k, v in prof.items() if not k.startswith("_")}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    ntr_rows = a.rows - nte                                                         # local train rows
+    F = 41
+    ent_per_step = hist_entries / a.steps
+    alg = {  # algorithmic bytes per step of each kernel
+        "encode": a.rows * (168 + 41 * 4 + 4),
+        "bin_rows": (ntr_rows + nte) * (41 * 4 + 48),
+        "hist_level": ent_per_step * (4 + 1) + min(ent_per_step, float(ntr_rows) * kern.get("hist_level", {}).get("launches_per_step", 1)) * (F + 1),
+        "partition_level": ent_per_step * (4 + 1 + 1 + 5),
+        "predict": nte * (48 + 8 + 2 * 8 * a.classes),
+    }
+    for k in kern:
+        if k in alg and kern[k]["ms_per_step"] > 0:
+            kern[k]["achieved_gbs"] = alg[k] / (kern[k]["ms_per_step"] * 1e-3) / 1e9
+            kern[k]["frac_of_hbm_peak"] = kern[k]["achieved_gbs"] / peak
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    d = kern[dom]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": d.get("achieved_gbs"), "peak": peak, "unit": "GB/s",
+                "frac": d.get("frac_of_hbm_peak"), "traffic": traffic, "peak_source": peak_src,
+                "launches_per_step": d["launches_per_step"], "avg_launch_ms": d["ms_per_step"] / max(d["launches_per_step"], 1),
+                "share_of_step": d["share_of_step"],
+                "note": "achieved = algorithmic bytes / CUDA-event kernel time inside the timed steps; the histogram kernel is "
+                        "shared-memory-atomic bound, not HBM bound (DESIGN.md)"}
+
+    # ---- CPU baseline (oracle, bounded sample) ---------------------------------------------------------
+    cpu = None
+    if not a.no_cpu_baseline:
+        import oracle
+        rec_c, dicts_c = synth.make_kdd(a.cpu_rows, a.classes, seed=2019, device="cpu")
+        t0 = time.perf_counter(); f1_cpu = cpu_pass(rec_c.numpy(), dicts_c, a); dt = time.perf_counter() - t0
+        cpu = {"value": a.cpu_rows / dt, "unit": "records/s", "cores": oracle.num_threads(), "kind": "port",
+               "sample": "%d-row sample of the same workload (same generator), full %d-tree depth-%d forest, %.1f s; oracle = "
+                         "C++/OpenMP restatement of MLlib (Spark itself needs a JVM: absent)" % (a.cpu_rows, a.trees, a.depth, dt),
+               "macro_f1": f1_cpu}
+
+    line = {"metric": "flow-records/sec fit+transform", "value": value, "unit": "records/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 bins / uint32 histograms / f64 split scoring (f32 feature matrix)", "data": "synthetic",
+            "config": workload_config(a, world), "macro_f1": f1, "forest_nodes": n_nodes,
+            "train_levels": stats["levels"], "bagged_entries": stats["entries"],
+            "clocks": sampler.summary() if sampler else None, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

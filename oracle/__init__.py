@@ -163,8 +163,11 @@ class Forest:
         self._h, self.C, self.T = handle, Cc, T
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_forest_free(C.c_void_p(self._h)); self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().orc_forest_free(C.c_void_p(self._h)); self._h = None
+        except Exception:          # interpreter shutdown
+            pass
 
     def num_nodes(self):
         return int(lib().orc_forest_num_nodes(C.c_void_p(self._h)))

@@ -55,7 +55,8 @@ _SIGNATURES = {
 EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version"])
 
 _lib = None
-launches = 0   # number of C-ABI calls issued (every call launches >= 1 of our kernels); bench.py reads this
+launches = 0   # kernels of OURS launched so far (counted per C-ABI call); bench.py reads the delta over the timed region
+_KERNELS_PER_CALL = {"b200flow_grow_level": 3, "b200flow_compact_rows": 3}
 
 
 def load():
@@ -97,7 +98,7 @@ def call(name, *args):
     global launches
     lib = load()
     rc = getattr(lib, name)(*args, stream())
-    launches += 1
+    launches += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise B200FlowError("%s failed (%d): %s" % (name, rc, lib.b200flow_last_error().decode()))
 

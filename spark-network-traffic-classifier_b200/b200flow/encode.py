@@ -143,7 +143,8 @@ class EncodePlan:
         label_out = torch.empty(n, dtype=torch.int32, device=records.device) if (self.label and want_label) else None
         valid = torch.empty(n, dtype=torch.uint8, device=records.device) if want_valid else None
         loff, llo, lln = self.label if self.label else (-1, 0, 0)
-        call("b200flow_encode", ptr(records), n, self.schema.row_bytes, ptr(slots), self.n_out, ptr(lut_t), lut_total,
+        from .forest import _timed
+        _timed("encode", "b200flow_encode", ptr(records), n, self.schema.row_bytes, ptr(slots), self.n_out, ptr(lut_t), lut_total,
              loff, llo, lln, int(self.check_nan), ptr(out), _lib.dtype_code(out), ptr(label_out), ptr(valid))
         return out, label_out, valid
 

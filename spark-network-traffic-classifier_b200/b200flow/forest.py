@@ -19,6 +19,24 @@ from . import _lib
 from ._lib import NODE_DTYPE, SPLIT_DTYPE, B200FlowError, call, ptr
 
 CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_level (<= 2048)
+PROFILE = None                     # set to a dict to collect per-kernel CUDA-event timings (bench.py)
+
+
+def _timed(name, fn, *args):
+    """run one C-ABI call; when PROFILE is a dict, bracket it with CUDA events on the launching stream."""
+    if PROFILE is None:
+        return call(fn, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(fn, *args)
+    e1.record()
+    PROFILE.setdefault(name, []).append((e0, e1))
+
+
+def profile_totals():
+    """-> {kernel: (launches, total_ms)} from the recorded events (synchronises)."""
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (PROFILE or {}).items()}
 HIST_BUDGET_BYTES = 4 << 30        # node-group cap for the histogram buffer (MLlib: maxMemoryInMB)
 
 
@@ -120,7 +138,7 @@ class ForestModel:
         raw = torch.empty((n, self.C), dtype=torch.float64, device=dev) if want_raw else None
         prob = torch.empty((n, self.C), dtype=torch.float64, device=dev) if want_prob else None
         pred = torch.empty(n, dtype=torch.float64, device=dev)
-        call("b200flow_predict", ptr(tp), tp.shape[1], n, ptr(self.nodes), ptr(self.node_mask), ptr(self.leaf_prob),
+        _timed("predict", "b200flow_predict", ptr(tp), tp.shape[1], n, ptr(self.nodes), ptr(self.node_mask), ptr(self.leaf_prob),
              ptr(self.pool_counts), self.T, self.C, 1 if self.dt_mode else 0, ptr(raw), ptr(prob), ptr(pred))
         return raw, prob, pred
 
@@ -238,8 +256,8 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     stride = tp_stride(F)
     tp = torch.empty((n, stride), dtype=torch.uint8, device=dev)
     bad = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("b200flow_bin_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), ptr(thresholds), ptr(n_thr), ptr(arity_dev),
-         mpb, ptr(labels), ptr(tp), stride, ptr(bad))
+    _timed("bin_rows", "b200flow_bin_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), ptr(thresholds), ptr(n_thr),
+           ptr(arity_dev), mpb, ptr(labels), ptr(tp), stride, ptr(bad))
     feat_bins = torch.where(arity_dev > 0, arity_dev, n_thr + 1).to(torch.int32).contiguous()
     head = torch.cat([bad, feat_bins.max().reshape(1).to(torch.int32)]).cpu()
     if int(head[0]) != 0:
@@ -333,13 +351,16 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                 coff = (chunk_off[g0:g1 + 1] - chunk_off[g0]).contiguous()
                 gch = int((chunk_off[g1] - chunk_off[g0]).item())
             # R7 HOT LOOP A
-            call("b200flow_hist_level", ptr(tp), stride, F, ptr(ent_row), ptr(ent_w), gs, ptr(seg_begin[g0:g1]),
-                 ptr(seg_end[g0:g1]), ptr(coff), gch, CHUNK_ROWS, ptr(subset[g0:g1]), m, n_bins, C, ptr(h))
+            _timed("hist_level", "b200flow_hist_level", ptr(tp), stride, F, ptr(ent_row), ptr(ent_w), gs, ptr(seg_begin[g0:g1]),
+                   ptr(seg_end[g0:g1]), ptr(coff), gch, CHUNK_ROWS, ptr(subset[g0:g1]), m, n_bins, C, ptr(h))
             stats["hist_launches"] += 1
+            if PROFILE is not None:
+                PROFILE.setdefault("_hist_entries", []).append(lens[g0:g1].sum())
+                PROFILE.setdefault("_hist_slots", []).append(gs)
             if group is not None:                       # R7r: the one data-path collective
                 dist.all_reduce(h, group=group)
             # R8 HOT LOOP B
-            call("b200flow_score_level", ptr(h), gs, ptr(subset[g0:g1]), m, n_bins, C, ptr(feat_bins), ptr(feat_kind),
+            _timed("score_level", "b200flow_score_level", ptr(h), gs, ptr(subset[g0:g1]), m, n_bins, C, ptr(feat_bins), ptr(feat_kind),
                  level, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(split[g0:g1]),
                  ptr(node_counts[g0:g1]), ptr(left_counts[g0:g1]), ptr(right_counts[g0:g1]))
         del hist
@@ -351,7 +372,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         next_nid = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_node = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_parent = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
-        call("b200flow_grow_level", n_slots, ptr(slot_tree), ptr(slot_nid), ptr(slot_node), ptr(split), ptr(node_counts),
+        _timed("grow_level", "b200flow_grow_level", n_slots, ptr(slot_tree), ptr(slot_nid), ptr(slot_node), ptr(split), ptr(node_counts),
              ptr(left_counts), ptr(right_counts), C, ptr(nodes), ptr(node_mask), ptr(pool_counts), ptr(node_tree),
              cap_nodes, ptr(next_tree), ptr(next_nid), ptr(next_node), ptr(next_parent), ptr(counters))
         node_gain[slot_node.long()] = split.view(torch.float64)[:, 2]
@@ -364,7 +385,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
             break
         # route every entry to its child segment
         cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
-        call("b200flow_partition_level", ptr(tp), stride, ptr(ent_row), ptr(ent_w), ptr(ent_row2), ptr(ent_w2), n_slots,
+        _timed("partition_level", "b200flow_partition_level", ptr(tp), stride, ptr(ent_row), ptr(ent_w), ptr(ent_row2), ptr(ent_w2), n_slots,
              ptr(seg_begin), ptr(seg_end), ptr(chunk_off), n_chunks, CHUNK_ROWS, ptr(split), ptr(cursors))
         next_begin = torch.empty(n_next, dtype=torch.int64, device=dev)
         next_end = torch.empty(n_next, dtype=torch.int64, device=dev)

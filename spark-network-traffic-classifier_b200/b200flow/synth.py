@@ -142,8 +142,8 @@ def make_cicids(n, n_classes=15, seed=2019, device="cpu", label_noise=0.01, nan_
     flip = torch.rand(n, device=dev, generator=g) < label_noise
     y = torch.where(flip, torch.randint(0, L, (n,), device=dev, generator=g), z)
     loc = torch.tensor(pg.uniform(0.0, 1.0, (L, n_features)), device=dev, dtype=torch.float32)
-    informative = set(pg.choice(n_features, 14, replace=False).tolist())
-    zero_cols = set(pg.choice([i for i in range(n_features) if i not in informative], 8, replace=False).tolist())
+    informative = set(pg.choice(n_features, min(14, n_features // 2), replace=False).tolist())
+    zero_cols = set(pg.choice([i for i in range(n_features) if i not in informative], min(8, n_features // 5), replace=False).tolist())
     schema = cicids_schema(n_features)
     rec = torch.empty((n, schema.row_bytes), dtype=torch.uint8, device=dev)
     rec32 = rec.view(torch.int32)

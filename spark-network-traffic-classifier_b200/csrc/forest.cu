@@ -64,33 +64,38 @@ __global__ void __launch_bounds__(256) hist_level_kernel(const uint8_t* __restri
                                                          int n_slots, const int64_t* __restrict__ seg_begin,
                                                          const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off,
                                                          int chunk_rows, const uint16_t* __restrict__ subset, int m, int n_bins,
-                                                         int C, uint32_t* hist) {
+                                                         int C, int m_pass, uint32_t* hist) {
     extern __shared__ uint32_t sh_hist[];              // [m][n_bins][C]
     __shared__ int sh_feat[256];
     const int64_t c = blockIdx.x;
     const int s = find_slot(chunk_off, n_slots, c);
     const int64_t b = seg_begin[s] + (c - chunk_off[s]) * chunk_rows;
     const int64_t e = min(seg_end[s], b + chunk_rows);
-    const int hsz = m * n_bins * C;
-    for (int i = threadIdx.x; i < hsz; i += blockDim.x) sh_hist[i] = 0;
-    for (int j = threadIdx.x; j < m; j += blockDim.x) sh_feat[j] = subset[(int64_t)s * m + j];
-    __syncthreads();
     const int nbC = n_bins * C;
-    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
-        const int row = ent_row[i];
-        const uint32_t w = ent_w[i];
-        const uint8_t* rec = tp + (int64_t)row * stride;
-        const int lab = rec[F];
-        for (int j = 0; j < m; ++j) {
-            const int bin = rec[sh_feat[j]];
-            atomicAdd(&sh_hist[j * nbC + bin * C + lab], w);
+    for (int j = threadIdx.x; j < m; j += blockDim.x) sh_feat[j] = subset[(int64_t)s * m + j];
+    uint32_t* gh = hist + (int64_t)s * m * nbC;
+    // features are processed m_pass at a time so that the shared histogram fits (wide nodes: DecisionTree, many classes)
+    for (int j0 = 0; j0 < m; j0 += m_pass) {
+        const int mp = min(m_pass, m - j0);
+        const int hsz = mp * nbC;
+        __syncthreads();
+        for (int i = threadIdx.x; i < hsz; i += blockDim.x) sh_hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+            const int row = ent_row[i];
+            const uint32_t w = ent_w[i];
+            const uint8_t* rec = tp + (int64_t)row * stride;
+            const int lab = rec[F];
+            for (int j = 0; j < mp; ++j) {
+                const int bin = rec[sh_feat[j0 + j]];
+                atomicAdd(&sh_hist[j * nbC + bin * C + lab], w);
+            }
         }
-    }
-    __syncthreads();
-    uint32_t* gh = hist + (int64_t)s * hsz;
-    for (int i = threadIdx.x; i < hsz; i += blockDim.x) {
-        uint32_t v = sh_hist[i];
-        if (v) atomicAdd(gh + i, v);
+        __syncthreads();
+        for (int i = threadIdx.x; i < hsz; i += blockDim.x) {
+            uint32_t v = sh_hist[i];
+            if (v) atomicAdd(gh + (int64_t)j0 * nbC + i, v);
+        }
     }
 }
 
@@ -447,14 +452,18 @@ extern "C" int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t
                                    int32_t C, uint32_t* hist, void* stream) {
     B2F_REQUIRE(tp && ent_row && ent_w && seg_begin && seg_end && chunk_off && subset && hist, "hist_level: null pointer");
     B2F_REQUIRE(m > 0 && m <= 256 && n_bins > 0 && n_bins <= 256 && C > 0 && C <= 256 && chunk_rows > 0, "hist_level: bad shape");
-    size_t smem = (size_t)m * n_bins * C * 4;
-    B2F_REQUIRE(smem <= 200 * 1024, "hist_level: per-node histogram (%zu B) exceeds shared memory", smem);
+    const size_t per_feat = (size_t)n_bins * C * 4;
+    B2F_REQUIRE(per_feat <= 200 * 1024, "hist_level: one feature's histogram (%zu B) exceeds shared memory", per_feat);
+    int m_pass = (int)((64 * 1024) / per_feat);            // <= 64 KB per CTA keeps >= 3 CTAs resident per SM
+    if (m_pass < 1) m_pass = 1;
+    if (m_pass > m) m_pass = m;
+    size_t smem = per_feat * m_pass;
     if (n_slots <= 0 || n_chunks <= 0) return B200FLOW_OK;
     B2F_REQUIRE(n_chunks < ((int64_t)1 << 31), "hist_level: too many chunks");
     cudaError_t e = cudaFuncSetAttribute(hist_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
     hist_level_kernel<<<(unsigned)n_chunks, 256, smem, (cudaStream_t)stream>>>(tp, tp_stride, F, ent_row, ent_w, n_slots, seg_begin,
-                                                                             seg_end, chunk_off, chunk_rows, subset, m, n_bins, C, hist);
+                                                                             seg_end, chunk_off, chunk_rows, subset, m, n_bins, C, m_pass, hist);
     return check_launch("hist_level");
 }
 

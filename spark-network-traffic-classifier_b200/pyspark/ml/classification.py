@@ -10,6 +10,7 @@ import zlib
 import numpy as np
 import torch
 
+from b200flow import dist as bdist
 from b200flow import forest as fr
 
 from . import Estimator, Model
@@ -73,7 +74,10 @@ class _TreeClassifierBase(Estimator, _TreeParams):
         if C > 100:
             raise IllegalArgumentException("Classifier inferred %d classes; maximum is 100" % C)
         try:
-            forest = fr.fit_forest(x, y.to(torch.int32), C, _arity_from_attrs(attrs, x.shape[1]), params)
+            grp = bdist.group()
+            off, _ = bdist.global_offset(x.shape[0], x.device, grp)
+            forest = fr.fit_forest(x, y.to(torch.int32), C, _arity_from_attrs(attrs, x.shape[1]), params,
+                                   row_offset=off, group=grp)
         except ValueError as e:
             raise IllegalArgumentException(str(e))
         return forest

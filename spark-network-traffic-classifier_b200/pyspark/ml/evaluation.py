@@ -2,6 +2,7 @@
 confusion counts by the b200flow kernel (R10), metrics per MulticlassMetrics (A.8) + macro-F1."""
 import torch
 
+from b200flow import dist as bdist
 from b200flow import forest as fr
 
 from .param import Params
@@ -19,8 +20,12 @@ class MulticlassClassificationEvaluator(Params):
         lab = dataset._column_tensor(self.getOrDefault("labelCol")).to(torch.float64).contiguous()
         if pred.numel() == 0:
             return torch.zeros((1, 1), dtype=torch.int64)
-        C = int(torch.maximum(pred.max(), lab.max()).item()) + 1
-        return fr.confusion_matrix(pred, lab, C).cpu()
+        mx = torch.maximum(pred.max(), lab.max()).reshape(1)
+        if bdist.group() is not None:
+            import torch.distributed as dist
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=bdist.group())
+        C = int(mx.item()) + 1
+        return bdist.all_reduce_sum_(fr.confusion_matrix(pred, lab, C)).cpu()
 
     def evaluate(self, dataset, params=None):
         ev = self.copy(params) if params else self

@@ -9,6 +9,7 @@ import copy
 import numpy as np
 import torch
 
+from b200flow import dist as bdist
 from b200flow import encode as enc
 from b200flow._lib import B200FlowError
 from b200flow.encode import EncodePlan, RecordSchema
@@ -59,7 +60,8 @@ class StringIndexer(Estimator):
         order = self.getOrDefault("stringOrderType")
         if c.kind == "field" and df._schema.type_of[col] == "code":
             strings = df._dicts[col]
-            counts = enc.category_counts(df._rec, df._schema, col, max(len(strings), 1)).cpu().numpy()[:len(strings)]
+            counts = enc.category_counts(df._rec, df._schema, col, max(len(strings), 1))
+            counts = bdist.all_reduce_sum_(counts).cpu().numpy()[:len(strings)]     # ranks share the dictionaries
         else:                                              # numeric column: cast to string like Spark does
             vals, cnt = torch.unique(_materialize(df, col)[:, 0], return_counts=True)
             keep = ~torch.isnan(vals)
@@ -288,7 +290,7 @@ class StandardScaler(Estimator):
 
     def _fit(self, df):
         x = _materialize(df, self.getOrDefault("inputCol"))
-        mean, std = enc.column_moments(x)                  # R3c: corrected two-pass, unbiased (n-1)
+        mean, std = enc.column_moments(x, bdist.group())   # R3c: corrected two-pass, unbiased (n-1)
         m = StandardScalerModel(mean.cpu().numpy(), std.cpu().numpy())
         m._paramMap = dict(self._paramMap)
         return m

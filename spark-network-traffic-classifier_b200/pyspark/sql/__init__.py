@@ -179,6 +179,16 @@ class DataFrame:
 
     # ---- construction helpers
     @staticmethod
+    def fromRecords(records, schema, dicts, session=None):
+        """b200flow extension: DataFrame over already-parsed AoS flow records (uint8 [n, row_bytes] torch tensor,
+        host or device; host buffers are copied to the current CUDA device), a RecordSchema and the string
+        dictionaries of its 'code' fields — the entry point that skips CSV parsing."""
+        _lib.require_cuda()
+        if not records.is_cuda:
+            records = records.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+        return DataFrame._from_records(records, schema, dicts, session)
+
+    @staticmethod
     def _from_records(rec, schema, dicts, session=None):
         cols = {name: ColumnData("field", dtype=schema.type_of[name], prov=("field", name)) for name in schema.names}
         return DataFrame(rec.shape[0], rec, schema, dicts, cols, session)
@@ -296,38 +306,20 @@ class DataFrame:
         return c.data
 
     def _compact(self, flag):
-        """keep rows with flag != 0 in every column (order preserved)."""
-        dev = flag.device
-        n = self._n
-        nb = (n + 1023) // 1024
-        scratch = torch.zeros(nb + 1 + (nb + 1) // 2 + 1, dtype=torch.int64, device=dev)
-        kept = torch.zeros(1, dtype=torch.int64, device=dev)
-        flag = flag.to(torch.uint8).contiguous()
-        outs = []
-
-        def run(buf, row_bytes):
-            out = torch.empty_like(buf)
-            call("b200flow_compact_rows", ptr(buf), n, row_bytes, ptr(flag), 1, ptr(out), ptr(scratch), ptr(kept))
-            outs.append(out)
-            return out
-
-        rec = None
-        needs_rec = any(c.kind == "field" for c in self._cols.values())
-        if self._rec is not None and needs_rec and n > 0:
-            rec = run(self._rec, self._schema.row_bytes)
+        """keep rows with flag != 0 in every column (order preserved) — b200flow compaction kernel."""
+        from b200flow.rows import compact_many
+        needs_rec = self._rec is not None and any(c.kind == "field" for c in self._cols.values())
+        names = [k for k, c in self._cols.items() if c.kind != "field"]
+        bufs = ([self._rec] if needs_rec else []) + [self._cols[k].data for k in names]
+        outs, k = compact_many(bufs, flag)
+        rec = outs[0] if needs_rec else None
+        outs = outs[1:] if needs_rec else outs
         cols = {}
         for name, c in self._cols.items():
             if c.kind == "field":
                 cols[name] = c
             else:
-                d = c.data.contiguous()
-                rb = d.element_size() * (d.shape[1] if d.dim() == 2 else 1)
-                cols[name] = ColumnData(c.kind, run(d, rb) if n > 0 else d, c.dtype, c.meta, c.prov if rec is not None else None)
-        k = int(kept.item()) if (outs) else int(flag.sum().item())
-        rec = rec[:k] if rec is not None else None
-        for name, c in cols.items():
-            if c.kind != "field":
-                c.data = c.data[:k]
+                cols[name] = ColumnData(c.kind, outs[names.index(name)], c.dtype, c.meta, c.prov if rec is not None else None)
         return DataFrame(k, rec, self._schema if rec is not None else None, self._dicts if rec is not None else {}, cols,
                          self._session)
 
@@ -342,20 +334,16 @@ class DataFrame:
     filter = where
 
     def randomSplit(self, weights, seed=None):
-        """Bernoulli split keyed by (seed, row index) (A.9 build rule; Spark's own draw is irreproducible)."""
-        w = np.asarray(weights, np.float64)
-        if (w < 0).any() or w.sum() <= 0:
-            raise ValueError("Weights must be positive. Found weights: %s" % list(weights))
-        cum = np.cumsum(w / w.sum())
-        cum[-1] = 1.0
+        """Bernoulli split keyed by (seed, global row index) (A.9 build rule; Spark's own draw is irreproducible).
+        Under torch.distributed the row index is global over the ranks' shards."""
+        from b200flow import dist as bdist
+        from b200flow.rows import random_split_ids
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")
         dev = self._device()
-        sid = torch.empty(max(self._n, 1), dtype=torch.uint8, device=dev)
-        cum_c = np.ascontiguousarray(cum)
-        call("b200flow_random_split", int(seed) & 0xFFFFFFFFFFFFFFFF, 0, self._n, cum_c.ctypes.data, len(cum_c), ptr(sid))
-        sid = sid[:self._n]
-        return [self._compact(sid == k) for k in range(len(cum))]
+        off, _ = bdist.global_offset(self._n, dev)
+        sid = random_split_ids(self._n, weights, seed, off, dev)
+        return [self._compact(sid == k) for k in range(len(weights))]
 
     def groupBy(self, *cols):
         cols = [c for cc in cols for c in (cc if isinstance(cc, (list, tuple)) else [cc])]
@@ -434,7 +422,7 @@ def _read_csv(paths, header, inferSchema, strip_lead, strip_trail, device):
     fields, arrays, dicts = [], {}, {}
     for name in pdf.columns:
         s = pdf[name]
-        if s.dtype == object:
+        if _is_str(s):
             if strip_trail or strip_lead:
                 s = s.str.strip() if strip_trail and strip_lead else (s.str.rstrip() if strip_trail else s.str.lstrip())
             codes, uniques = pd.factorize(s, sort=False)           # null -> -1
@@ -484,6 +472,11 @@ class DataFrameReader:
         rec, rschema, dicts = _read_csv(paths, header, infer, _truthy(ignoreLeadingWhiteSpace), _truthy(ignoreTrailingWhiteSpace),
                                         torch.device("cuda", torch.cuda.current_device()))
         return DataFrame._from_records(rec, rschema, dicts, self._session)
+
+
+def _is_str(s):
+    import pandas as pd
+    return s.dtype == object or pd.api.types.is_string_dtype(s.dtype)
 
 
 def _truthy(v):
@@ -563,7 +556,7 @@ class SparkSession:
             s = pdf[name]
             if s.dtype == object and len(s) and not isinstance(s.iloc[0], str):
                 raise NotImplementedError("createDataFrame: vector/object columns are not supported; use numeric/string columns")
-            if s.dtype == object:
+            if _is_str(s):
                 codes, uniq = pd.factorize(s, sort=False)
                 fields.append((str(name), "code")); host_cols[str(name)] = codes.astype(np.int32); dicts[str(name)] = [str(u) for u in uniq]
             else:

@@ -269,6 +269,14 @@ def test_decision_tree_cicids_all_features_and_min_instances():
     _check_predictions(model, fo, meta, x[:5000], dt_mode=True)
 
 
+def test_decision_tree_wide_histogram_multipass():
+    # 23 classes x 41 features x 70 bins = 264 KB per node: the histogram kernel must tile features over passes
+    x, y, arity, C = _features(25000, 23, 91)
+    model, fo, meta = _fit_both(x, y, C, arity, num_trees=1, max_bins=70, max_depth=5, bootstrap=False, seed=1)
+    assert forests_equal(model.export(), fo.export()) == []
+    _check_predictions(model, fo, meta, x[:4000], dt_mode=True)
+
+
 def test_forest_fp32_features_equal_fp64_features():
     x, y, arity, C = _features(30000, 5, 55)
     p = fr.ForestParams(num_trees=4, max_bins=70, max_depth=6, seed=5)
