@@ -262,6 +262,7 @@ def main():
     launches = (_lib.launches - k0) // a.steps
     prof = fr.profile_totals()
     hist_entries = float(sum(float(t.item()) for t in fr.PROFILE.get("_hist_entries", [])))
+    route_entries = float(sum(float(t.item()) for t in fr.PROFILE.get("_route_entries", [])))
     fr.PROFILE = None
     global_rows = a.rows * world
     value = global_rows / (ms_step / 1e3)
@@ -299,10 +300,11 @@ def main():
     ent_per_step = hist_entries / a.steps
     alg = {  # algorithmic bytes per step of each kernel
         "encode": a.rows * (168 + 41 * 4 + 4),
-        "bin_rows": (ntr_rows + nte) * (41 * 4 + 48),
+        "bin_rows": (ntr_rows + nte) * (41 * 4 + 64),
         "hist_level": ent_per_step * (4 + 1) + min(ent_per_step, float(ntr_rows) * kern.get("hist_level", {}).get("launches_per_step", 1)) * (F + 1),
         "partition_level": ent_per_step * (4 + 1 + 1 + 5),
-        "predict": nte * (48 + 8 + 2 * 8 * a.classes),
+        "route_hist_level": route_entries / a.steps * (4 + 1 + (F + 1) + 4 + 1),
+        "predict": nte * (64 + 8 + 2 * 8 * a.classes),
     }
     for k in kern:
         if k in alg and kern[k]["ms_per_step"] > 0:

@@ -197,7 +197,8 @@ typedef struct b200flow_node {
 
 /* grows the pool by one level: for each slot writes its node record (+ mask, counts), creates
  * two children per split (counts from left/right_counts), and emits the next level's slots for
- * the non-leaf children (next_* arrays, capacity 2*n_slots; next_parent = parent slot*2+side).
+ * the non-leaf children (next_* arrays, capacity 2*n_slots; next_parent = parent slot*2+side;
+ * child_slot[2*s+side] = index of that child among the next slots, -1 when it is a leaf; may be NULL).
  * counters: int64[4] {node pool size (in/out), number of next slots (out), overflow flag (out: 1 =
  * pool_capacity too small, nothing written), pool size before the call} followed by
  * 2*ceil(n_slots/256) int32 of scratch. */
@@ -208,7 +209,7 @@ int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, const uint32_
                         b200flow_node* nodes, uint64_t* node_mask, uint32_t* pool_counts,
                         int32_t* node_tree, int64_t pool_capacity,
                         int32_t* next_tree, uint32_t* next_nid, int32_t* next_node,
-                        int32_t* next_parent, int64_t* counters, void* stream);
+                        int32_t* next_parent, int32_t* child_slot, int64_t* counters, void* stream);
 
 /* routes every entry of every split slot to its child: left entries grow up from seg_begin,
  * right entries grow down from seg_end inside the same range of the destination buffers;
@@ -220,6 +221,22 @@ int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
                              int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
                              const b200flow_split* split, int32_t* cursors, void* stream);
+
+/* R7 fused with the row routing: partition_level(L) + hist_level(L+1) in ONE pass — every entry's TreePoint
+ * record is gathered once, routed by its parent's split and accumulated into its CHILD's histogram
+ * (hist_next[child_slot][j][bin][class], child feature subsets in subset_next, caller zeroes hist_next and
+ * cursors).  chunk_off counts chunks of chunk_rows entries (multiple of 32, <= 4096) per parent slot; leaf
+ * parents may have 0 chunks.  b200flow_route_hist_fits() tells whether the shapes fit shared memory; when
+ * they do not, use partition_level followed by hist_level. */
+int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows);
+int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
+                              const int32_t* ent_row, const uint8_t* ent_w,
+                              int32_t* ent_row_out, uint8_t* ent_w_out,
+                              int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
+                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
+                              const b200flow_split* split, const int32_t* child_slot, int32_t* cursors,
+                              const uint16_t* subset_next, int32_t m, int32_t n_bins, int32_t C,
+                              uint32_t* hist_next, void* stream);
 
 /* segment table of the next level from the parents' ranges and the partition cursors */
 int b200flow_next_segments(int32_t n_next, const int32_t* next_parent,

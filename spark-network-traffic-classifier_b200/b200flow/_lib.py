@@ -43,7 +43,9 @@ _SIGNATURES = {
     "b200flow_feature_subsets": [_U64, _I32, _P, _P, _I32, _I32, _P, _P],
     "b200flow_hist_level": [_P, _I32, _I32, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _I32, _I32, _I32, _P, _P],
     "b200flow_score_level": [_P, _I32, _P, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _F64, _P, _P, _P, _P, _P],
-    "b200flow_grow_level": [_I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P],
+    "b200flow_grow_level": [_I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P],
+    "b200flow_route_hist_level": [_P, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _I32, _I32, _I32,
+                                  _P, _P],
     "b200flow_partition_level": [_P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P],
     "b200flow_next_segments": [_I32, _P, _P, _P, _P, _P, _P, _P],
     "b200flow_finalize_forest": [_I64, _P, _I32, _P, _P],
@@ -52,7 +54,7 @@ _SIGNATURES = {
     "b200flow_random_split": [_U64, _I64, _I64, _P, _I32, _P, _P],
     "b200flow_compact_rows": [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version"])
+EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version", "b200flow_route_hist_fits"])
 
 _lib = None
 launches = 0   # kernels of OURS launched so far (counted per C-ABI call); bench.py reads the delta over the timed region
@@ -74,6 +76,8 @@ def load():
             fn.restype = C.c_int
         lib.b200flow_last_error.restype = C.c_char_p
         lib.b200flow_version.restype = C.c_int
+        lib.b200flow_route_hist_fits.argtypes = [_I32] * 5
+        lib.b200flow_route_hist_fits.restype = C.c_int
         _lib = lib
     return _lib
 

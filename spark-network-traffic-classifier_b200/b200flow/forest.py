@@ -19,6 +19,8 @@ from . import _lib
 from ._lib import NODE_DTYPE, SPLIT_DTYPE, B200FlowError, call, ptr
 
 CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_level (<= 2048)
+ROUTE_CHUNK_ROWS = 1024            # entries per CTA in the fused route_hist_level kernel
+FUSED = True                       # use route_hist_level (partition + next-level histogram in one pass) when it fits
 PROFILE = None                     # set to a dict to collect per-kernel CUDA-event timings (bench.py)
 
 
@@ -36,7 +38,10 @@ def _timed(name, fn, *args):
 def profile_totals():
     """-> {kernel: (launches, total_ms)} from the recorded events (synchronises)."""
     torch.cuda.synchronize()
-    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (PROFILE or {}).items()}
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (PROFILE or {}).items()
+            if not k.startswith("_")}
+
+
 HIST_BUDGET_BYTES = 4 << 30        # node-group cap for the histogram buffer (MLlib: maxMemoryInMB)
 
 
@@ -56,7 +61,9 @@ class ForestParams:
 
 
 def tp_stride(F):
-    return (F + 1 + 15) // 16 * 16
+    """TreePoint record stride: F bins + label, padded to whole 64-byte HBM bursts so that one random
+    record gather costs exactly ceil((F+1)/64) bursts (profiles/: both level kernels are gather-bound)."""
+    return (F + 1 + 63) // 64 * 64
 
 
 def poisson_cdf_table(rate=1.0):
@@ -325,45 +332,62 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     group_slots = max(1, HIST_BUDGET_BYTES // per_slot_hist)
     stats = dict(levels=0, slots=0, entries=E, hist_launches=0)
 
+    route_ch = ROUTE_CHUNK_ROWS
+    while route_ch > 128 and not _lib.load().b200flow_route_hist_fits(F, m, n_bins, C, route_ch):
+        route_ch //= 2
+    fused = FUSED and bool(_lib.load().b200flow_route_hist_fits(F, m, n_bins, C, route_ch))
+    hsz = m * n_bins * C
+
+    def chunk_table(nch):
+        off = torch.empty(nch.shape[0] + 1, dtype=torch.int64, device=dev)
+        call("b200flow_exclusive_scan_i32_to_i64", ptr(nch), nch.shape[0], ptr(off), ptr(total))
+        return off, int(total.item())
+
+    def level_subsets(ns, s_tree, s_nid):
+        sub = torch.empty((ns, m), dtype=torch.int16, device=dev)
+        call("b200flow_feature_subsets", seed, ns, ptr(s_tree), ptr(s_nid), F, m, ptr(sub))
+        return sub
+
+    subset = level_subsets(n_slots, slot_tree, slot_nid)
+    hist_ready = None                  # histogram of the CURRENT level when the fused kernel already built it
     while n_slots > 0:
         grow_pool(pool_size + 2 * n_slots)
-        subset = torch.empty((n_slots, m), dtype=torch.int16, device=dev)
-        call("b200flow_feature_subsets", seed, n_slots, ptr(slot_tree), ptr(slot_nid), F, m, ptr(subset))
         lens = seg_end - seg_begin
-        nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()
-        chunk_off = torch.empty(n_slots + 1, dtype=torch.int64, device=dev)
-        call("b200flow_exclusive_scan_i32_to_i64", ptr(nch), n_slots, ptr(chunk_off), ptr(total))
-        n_chunks = int(total.item())
         split = torch.empty((n_slots, 64), dtype=torch.uint8, device=dev)
         node_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
         left_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
         right_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
-        g_rows = min(group_slots, n_slots)
-        hist = torch.empty(g_rows * m * n_bins * C, dtype=torch.int32, device=dev)
-        for g0 in range(0, n_slots, group_slots):
-            g1 = min(n_slots, g0 + group_slots)
+        chunk_off = None
+        if hist_ready is None:
+            nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()
+            chunk_off, n_chunks = chunk_table(nch)
+        groups = [(0, n_slots)] if hist_ready is not None else \
+            [(g0, min(n_slots, g0 + group_slots)) for g0 in range(0, n_slots, group_slots)]
+        for g0, g1 in groups:
             gs = g1 - g0
-            h = hist[:gs * m * n_bins * C]
-            h.zero_()
-            if g0 == 0 and g1 == n_slots:
-                coff, gch = chunk_off, n_chunks
+            if hist_ready is not None:
+                h = hist_ready
             else:
-                coff = (chunk_off[g0:g1 + 1] - chunk_off[g0]).contiguous()
-                gch = int((chunk_off[g1] - chunk_off[g0]).item())
-            # R7 HOT LOOP A
-            _timed("hist_level", "b200flow_hist_level", ptr(tp), stride, F, ptr(ent_row), ptr(ent_w), gs, ptr(seg_begin[g0:g1]),
-                   ptr(seg_end[g0:g1]), ptr(coff), gch, CHUNK_ROWS, ptr(subset[g0:g1]), m, n_bins, C, ptr(h))
-            stats["hist_launches"] += 1
-            if PROFILE is not None:
-                PROFILE.setdefault("_hist_entries", []).append(lens[g0:g1].sum())
-                PROFILE.setdefault("_hist_slots", []).append(gs)
+                h = torch.zeros(gs * hsz, dtype=torch.int32, device=dev)
+                if g0 == 0 and g1 == n_slots:
+                    coff, gch = chunk_off, n_chunks
+                else:
+                    coff = (chunk_off[g0:g1 + 1] - chunk_off[g0]).contiguous()
+                    gch = int((chunk_off[g1] - chunk_off[g0]).item())
+                # R7 HOT LOOP A (unfused form: level 0, and levels whose histograms exceed the fused budget)
+                _timed("hist_level", "b200flow_hist_level", ptr(tp), stride, F, ptr(ent_row), ptr(ent_w), gs,
+                       ptr(seg_begin[g0:g1]), ptr(seg_end[g0:g1]), ptr(coff), gch, CHUNK_ROWS, ptr(subset[g0:g1]), m, n_bins, C, ptr(h))
+                stats["hist_launches"] += 1
+                if PROFILE is not None:
+                    PROFILE.setdefault("_hist_entries", []).append(lens[g0:g1].sum())
             if group is not None:                       # R7r: the one data-path collective
                 dist.all_reduce(h, group=group)
             # R8 HOT LOOP B
             _timed("score_level", "b200flow_score_level", ptr(h), gs, ptr(subset[g0:g1]), m, n_bins, C, ptr(feat_bins), ptr(feat_kind),
-                 level, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(split[g0:g1]),
-                 ptr(node_counts[g0:g1]), ptr(left_counts[g0:g1]), ptr(right_counts[g0:g1]))
-        del hist
+                   level, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(split[g0:g1]),
+                   ptr(node_counts[g0:g1]), ptr(left_counts[g0:g1]), ptr(right_counts[g0:g1]))
+            del h
+        hist_ready = None
         # grow the pool by this level's children and emit the next level's slots
         nblk = (n_slots + 255) // 256
         counters = torch.zeros(4 + nblk + 1, dtype=torch.int64, device=dev)
@@ -372,9 +396,10 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         next_nid = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_node = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_parent = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
+        child_slot = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         _timed("grow_level", "b200flow_grow_level", n_slots, ptr(slot_tree), ptr(slot_nid), ptr(slot_node), ptr(split), ptr(node_counts),
-             ptr(left_counts), ptr(right_counts), C, ptr(nodes), ptr(node_mask), ptr(pool_counts), ptr(node_tree),
-             cap_nodes, ptr(next_tree), ptr(next_nid), ptr(next_node), ptr(next_parent), ptr(counters))
+               ptr(left_counts), ptr(right_counts), C, ptr(nodes), ptr(node_mask), ptr(pool_counts), ptr(node_tree),
+               cap_nodes, ptr(next_tree), ptr(next_nid), ptr(next_node), ptr(next_parent), ptr(child_slot), ptr(counters))
         node_gain[slot_node.long()] = split.view(torch.float64)[:, 2]
         cnt = counters[:3].cpu()
         if int(cnt[2]) != 0:
@@ -383,17 +408,34 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         stats["levels"] += 1; stats["slots"] += n_slots
         if n_next == 0:
             break
-        # route every entry to its child segment
+        next_tree, next_nid, next_node = next_tree[:n_next], next_nid[:n_next], next_node[:n_next]
+        next_subset = level_subsets(n_next, next_tree, next_nid)
         cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
-        _timed("partition_level", "b200flow_partition_level", ptr(tp), stride, ptr(ent_row), ptr(ent_w), ptr(ent_row2), ptr(ent_w2), n_slots,
-             ptr(seg_begin), ptr(seg_end), ptr(chunk_off), n_chunks, CHUNK_ROWS, ptr(split), ptr(cursors))
+        if fused and n_next * hsz * 4 <= HIST_BUDGET_BYTES:
+            # route every entry to its child AND build the children's histograms in the same pass
+            is_split = (split.view(torch.int32)[:, 3] & 1) == 0
+            nch = torch.where(is_split, (lens + (route_ch - 1)) // route_ch, torch.zeros_like(lens)).to(torch.int32).contiguous()
+            roff, rch = chunk_table(nch)
+            hist_ready = torch.zeros(n_next * hsz, dtype=torch.int32, device=dev)
+            _timed("route_hist_level", "b200flow_route_hist_level", ptr(tp), stride, F, ptr(ent_row), ptr(ent_w), ptr(ent_row2),
+                   ptr(ent_w2), n_slots, ptr(seg_begin), ptr(seg_end), ptr(roff), rch, route_ch, ptr(split), ptr(child_slot),
+                   ptr(cursors), ptr(next_subset), m, n_bins, C, ptr(hist_ready))
+            stats["hist_launches"] += 1
+            if PROFILE is not None:
+                PROFILE.setdefault("_route_entries", []).append(torch.where(is_split, lens, torch.zeros_like(lens)).sum())
+        else:
+            if chunk_off is None:
+                nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()
+                chunk_off, n_chunks = chunk_table(nch)
+            _timed("partition_level", "b200flow_partition_level", ptr(tp), stride, ptr(ent_row), ptr(ent_w), ptr(ent_row2), ptr(ent_w2),
+                   n_slots, ptr(seg_begin), ptr(seg_end), ptr(chunk_off), n_chunks, CHUNK_ROWS, ptr(split), ptr(cursors))
         next_begin = torch.empty(n_next, dtype=torch.int64, device=dev)
         next_end = torch.empty(n_next, dtype=torch.int64, device=dev)
         call("b200flow_next_segments", n_next, ptr(next_parent), ptr(seg_begin), ptr(seg_end), ptr(cursors),
              ptr(next_begin), ptr(next_end))
         ent_row, ent_row2 = ent_row2, ent_row
         ent_w, ent_w2 = ent_w2, ent_w
-        slot_tree, slot_nid, slot_node = next_tree[:n_next], next_nid[:n_next], next_node[:n_next]
+        slot_tree, slot_nid, slot_node, subset = next_tree, next_nid, next_node, next_subset
         seg_begin, seg_end = next_begin, next_end
         n_slots = n_next
         level += 1

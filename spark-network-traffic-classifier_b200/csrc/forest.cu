@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kGrowBlock) grow_write_kernel(
     const uint32_t* __restrict__ node_counts, const uint32_t* __restrict__ left_counts,
     const uint32_t* __restrict__ right_counts, int C, b200flow_node* nodes, uint64_t* node_mask, uint32_t* pool_counts,
     int32_t* node_tree, const int32_t* __restrict__ blk, const int64_t* __restrict__ counters, int32_t* next_tree,
-    uint32_t* next_nid, int32_t* next_node, int32_t* next_parent) {
+    uint32_t* next_nid, int32_t* next_node, int32_t* next_parent, int32_t* child_slot) {
     __shared__ int sh[33];
     if (counters[2]) return;
     const int s = blockIdx.x * kGrowBlock + threadIdx.x;
@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(kGrowBlock) grow_write_kernel(
     const int tree = slot_tree[s];
     b200flow_node nd;
     nd.nid = nid; nd.feat = -1; nd.kind_bin = 0; nd.left = -1;
+    int csl = -1, csr = -1;
     for (int k = 0; k < C; ++k) pool_counts[(int64_t)node * C + k] = node_counts[(int64_t)s * C + k];
     if (is) {
         const int64_t child = counters[3] + 2 * ((int64_t)blk[2 * blockIdx.x] + e0);
@@ -357,9 +358,10 @@ __global__ void __launch_bounds__(kGrowBlock) grow_write_kernel(
             pool_counts[(child + 1) * C + k] = right_counts[(int64_t)s * C + k];
         }
         int64_t ns = (int64_t)blk[2 * blockIdx.x + 1] + e1;
-        if (!(sp.flags & 2)) { next_tree[ns] = tree; next_nid[ns] = nid * 2u; next_node[ns] = (int32_t)child; next_parent[ns] = s * 2; ++ns; }
-        if (!(sp.flags & 4)) { next_tree[ns] = tree; next_nid[ns] = nid * 2u + 1; next_node[ns] = (int32_t)child + 1; next_parent[ns] = s * 2 + 1; }
+        if (!(sp.flags & 2)) { next_tree[ns] = tree; next_nid[ns] = nid * 2u; next_node[ns] = (int32_t)child; next_parent[ns] = s * 2; csl = (int)ns; ++ns; }
+        if (!(sp.flags & 4)) { next_tree[ns] = tree; next_nid[ns] = nid * 2u + 1; next_node[ns] = (int32_t)child + 1; next_parent[ns] = s * 2 + 1; csr = (int)ns; }
     }
+    if (child_slot) { child_slot[2 * s] = csl; child_slot[2 * s + 1] = csr; }
     nodes[node] = nd;
 }
 
@@ -413,6 +415,188 @@ __global__ void __launch_bounds__(256) partition_level_kernel(
         else if (d == 2) { int64_t p = se - 1 - (baseR + __popc(mR & lt)); ent_row_out[p] = rows[k]; ent_w_out[p] = (uint8_t)w; }
         baseL += __popc(mL); baseR += __popc(mR);
     }
+}
+
+
+// ------------------------------------------------------------------ fused row routing + next-level histogram
+// One CTA = one chunk (<= CH entries) of one SPLIT parent slot.
+//   A. entries (row, w) -> smem; each entry's TreePoint record (64-byte aligned in HBM: exactly one DRAM burst)
+//      is gathered ONCE with 128-bit loads into a word-transposed smem tile (conflict-free per-lane byte reads);
+//   B. every entry is routed by the parent's split; its child's histogram (feature subset of the CHILD) is
+//      accumulated in shared memory.  Lanes whose (child, bins, label) key is identical — the duplicate-heavy
+//      smurf/neptune flows — are merged with match.any + redux so one lane issues the shared atomics;
+//   C. kept entries are written to the child's range (left grows up from seg_begin, right grows down from seg_end;
+//      one cursor reservation per CTA and side) and the two child histograms are flushed with sparse global REDs.
+// This replaces partition_level(L) + hist_level(L+1): the record gather, which is what both kernels were bound by
+// (HBM 64-byte bursts, ncu profiles/r01), happens once per entry per level instead of twice.
+constexpr int kRouteThreads = 256;
+
+__device__ __forceinline__ void hist_add_keyed(uint32_t* hist, int m, int nbC, int C, const uint32_t (&keys)[4], int nwords,
+                                               uint32_t w, uint32_t active) {
+    // merge lanes with identical keys, then the group leader adds the summed weight for each of the m features
+    uint32_t g = active;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (q < nwords) g &= __match_any_sync(active, keys[q]);
+    const uint32_t sum = __reduce_add_sync(g, w);
+    if ((int)(__ffs(g) - 1) != lane_id()) return;
+    const int lab = (keys[m >> 2] >> ((m & 3) * 8)) & 0x7f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int j = q * 4 + r;
+            if (j < m) atomicAdd(&hist[j * nbC + ((keys[q] >> (8 * r)) & 0xff) * C + lab], sum);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRouteThreads) route_hist_level_kernel(
+    const uint8_t* __restrict__ tp, int stride, int F, const int32_t* __restrict__ ent_row, const uint8_t* __restrict__ ent_w,
+    int32_t* ent_row_out, uint8_t* ent_w_out, int n_slots, const int64_t* __restrict__ seg_begin,
+    const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off, int CH, const b200flow_split* __restrict__ split,
+    const int32_t* __restrict__ child_slot, int32_t* cursors, const uint16_t* __restrict__ subset_next, int m, int n_bins,
+    int C, uint32_t* hist_next) {
+    extern __shared__ __align__(16) uint32_t sm_u32[];
+    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const int recw = (F + 1 + 15) / 16 * 4;                 // staged words per record (whole 16-byte quads)
+    const int nbC = n_bins * C, hsz = m * nbC;
+    uint32_t* words = sm_u32;                                // [recw][CH]
+    uint32_t* sh_hist = words + (size_t)recw * CH;           // [2][hsz]
+    int* sh_rows = (int*)(sh_hist + 2 * hsz);                // [CH]
+    int* sh_feat = sh_rows + CH;                             // [2][m]
+    uint8_t* sh_w = (uint8_t*)(sh_feat + 2 * m);             // [CH]
+    __shared__ int sh_cnt[kRouteThreads / 32][2];
+    __shared__ int sh_base[2];
+
+    const int64_t c = blockIdx.x;
+    const int s = find_slot(chunk_off, n_slots, c);
+    const b200flow_split sp = split[s];
+    if (sp.flags & 1) return;
+    const int cl = child_slot[2 * s], cr = child_slot[2 * s + 1];
+    if (cl < 0 && cr < 0) return;
+    const int64_t sb = seg_begin[s], se = seg_end[s];
+    const int64_t b = sb + (c - chunk_off[s]) * CH;
+    const int n = (int)(min(se, b + CH) - b);
+
+    for (int i = tid; i < n; i += kRouteThreads) { sh_rows[i] = ent_row[b + i]; sh_w[i] = ent_w[b + i]; }
+    for (int i = tid; i < 2 * hsz; i += kRouteThreads) sh_hist[i] = 0;
+    for (int j = tid; j < 2 * m; j += kRouteThreads) {
+        const int cs = j < m ? cl : cr;
+        sh_feat[j] = cs >= 0 ? subset_next[(int64_t)cs * m + (j < m ? j : j - m)] : 0;
+    }
+    __syncthreads();
+    // A. gather: 128-bit loads, quad-major so that all loads of a thread are independent (MLP)
+    const int nq = recw / 4;
+    for (int i0 = 0; i0 < n; i0 += kRouteThreads * 4) {
+        uint4 v[4][4];                                       // up to 4 entries x 4 quads in flight per thread
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * kRouteThreads + tid;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i < n && q < nq) v[k][q] = __ldg((const uint4*)(tp + (int64_t)sh_rows[i] * stride) + q);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * kRouteThreads + tid;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i < n && q < nq) {
+                    words[(4 * q + 0) * CH + i] = v[k][q].x; words[(4 * q + 1) * CH + i] = v[k][q].y;
+                    words[(4 * q + 2) * CH + i] = v[k][q].z; words[(4 * q + 3) * CH + i] = v[k][q].w;
+                }
+        }
+        for (int q = 4; q < nq; ++q)                         // records wider than 64 bytes: remaining quads
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k * kRouteThreads + tid;
+                if (i < n) {
+                    const uint4 x = __ldg((const uint4*)(tp + (int64_t)sh_rows[i] * stride) + q);
+                    words[(4 * q + 0) * CH + i] = x.x; words[(4 * q + 1) * CH + i] = x.y;
+                    words[(4 * q + 2) * CH + i] = x.z; words[(4 * q + 3) * CH + i] = x.w;
+                }
+            }
+    }
+    __syncthreads();
+    // B. route + accumulate.  Iteration k handles entries k*256 + tid (warp-contiguous)
+    const int fs = sp.feat;
+    const int nwords = (m + 1 + 3) / 4;                      // m bins + (label | side << 7)
+    const bool keyed = m <= 15 && C <= 128;
+    const int iters = (n + kRouteThreads - 1) / kRouteThreads;
+    int nL = 0, nR = 0;
+    uint32_t dec = 0;                                        // 2 bits per iteration (<= 16 iterations: CH <= 4096)
+    for (int k = 0; k < iters; ++k) {
+        const int i = k * kRouteThreads + tid;
+        int d = 0;
+        if (i < n) {
+            const int bin = (words[(fs >> 2) * CH + i] >> ((fs & 3) * 8)) & 0xff;
+            const bool left = sp.kind == 0 ? (bin <= sp.bin_thr) : ((sp.mask[bin >> 6] >> (bin & 63)) & 1ull);
+            d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
+        }
+        dec |= (uint32_t)d << (2 * k);
+        const uint32_t active = __ballot_sync(0xffffffffu, d != 0);
+        nL += __popc(__ballot_sync(0xffffffffu, d == 1));
+        nR += __popc(__ballot_sync(0xffffffffu, d == 2));
+        if (d != 0) {
+            const int side = d - 1;
+            const int* feats = sh_feat + side * m;
+            uint32_t* hist = sh_hist + side * hsz;
+            const int lab = (words[(F >> 2) * CH + i] >> ((F & 3) * 8)) & 0xff;
+            const uint32_t w = sh_w[i];
+            if (keyed) {
+                uint32_t keys[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int j = q * 4 + r;
+                        if (j < m) { const int f = feats[j]; keys[q] |= ((words[(f >> 2) * CH + i] >> ((f & 3) * 8)) & 0xffu) << (8 * r); }
+                        else if (j == m) keys[q] |= (uint32_t)(lab | (side << 7)) << (8 * r);
+                    }
+                }
+                hist_add_keyed(hist, m, nbC, C, keys, nwords, w, active);
+            } else {
+                for (int j = 0; j < m; ++j) {
+                    const int f = feats[j];
+                    const int bin = (words[(f >> 2) * CH + i] >> ((f & 3) * 8)) & 0xff;
+                    atomicAdd(&hist[j * nbC + bin * C + lab], w);
+                }
+            }
+        }
+    }
+    // C. positions: warp totals -> CTA reservation -> per-warp bases
+    if (lane == 0) { sh_cnt[wid][0] = nL; sh_cnt[wid][1] = nR; }
+    __syncthreads();
+    if (tid == 0) {
+        int tl = 0, tr = 0;
+        for (int q = 0; q < kRouteThreads / 32; ++q) { int a = sh_cnt[q][0], r = sh_cnt[q][1]; sh_cnt[q][0] = tl; sh_cnt[q][1] = tr; tl += a; tr += r; }
+        sh_base[0] = tl ? atomicAdd(&cursors[2 * s], tl) : 0;
+        sh_base[1] = tr ? atomicAdd(&cursors[2 * s + 1], tr) : 0;
+    }
+    __syncthreads();
+    int baseL = sh_base[0] + sh_cnt[wid][0], baseR = sh_base[1] + sh_cnt[wid][1];
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int k = 0; k < iters; ++k) {
+        const int i = k * kRouteThreads + tid;
+        const int d = (dec >> (2 * k)) & 3;
+        const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
+        if (d == 1) { const int64_t p = sb + baseL + __popc(mL & lt); ent_row_out[p] = sh_rows[i]; ent_w_out[p] = sh_w[i]; }
+        else if (d == 2) { const int64_t p = se - 1 - (baseR + __popc(mR & lt)); ent_row_out[p] = sh_rows[i]; ent_w_out[p] = sh_w[i]; }
+        baseL += __popc(mL); baseR += __popc(mR);
+    }
+    // flush the two child histograms (sparse)
+    for (int i = tid; i < 2 * hsz; i += kRouteThreads) {
+        const uint32_t v = sh_hist[i];
+        if (v) {
+            const int side = i >= hsz;
+            const int cs = side ? cr : cl;
+            atomicAdd(hist_next + (int64_t)cs * hsz + (i - side * hsz), v);
+        }
+    }
+}
+
+static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
+    const size_t recw = (size_t)(F + 1 + 15) / 16 * 4;
+    return recw * CH * 4 + 2 * (size_t)m * n_bins * C * 4 + (size_t)CH * 4 + 2 * (size_t)m * 4 + (size_t)CH + 64;
 }
 
 __global__ void next_segments_kernel(int n_next, const int32_t* __restrict__ next_parent, const int64_t* __restrict__ seg_begin,
@@ -491,7 +675,8 @@ extern "C" int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, co
                                    const b200flow_split* split, const uint32_t* node_counts, const uint32_t* left_counts,
                                    const uint32_t* right_counts, int32_t C, b200flow_node* nodes, uint64_t* node_mask,
                                    uint32_t* pool_counts, int32_t* node_tree, int64_t pool_capacity, int32_t* next_tree,
-                                   uint32_t* next_nid, int32_t* next_node, int32_t* next_parent, int64_t* counters, void* stream) {
+                                   uint32_t* next_nid, int32_t* next_node, int32_t* next_parent, int32_t* child_slot,
+                                   int64_t* counters, void* stream) {
     B2F_REQUIRE(slot_tree && slot_nid && slot_node && split && node_counts && left_counts && right_counts && nodes && pool_counts &&
                     node_tree && next_tree && next_nid && next_node && next_parent && counters, "grow_level: null pointer");
     if (n_slots <= 0) return B200FLOW_OK;
@@ -503,7 +688,7 @@ extern "C" int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, co
     grow_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nb, blk, counters, pool_capacity);
     grow_write_kernel<<<nb, kGrowBlock, 0, (cudaStream_t)stream>>>(n_slots, slot_tree, slot_nid, slot_node, split, node_counts, left_counts,
                                                                   right_counts, C, nodes, node_mask, pool_counts, node_tree, blk, counters,
-                                                                  next_tree, next_nid, next_node, next_parent);
+                                                                  next_tree, next_nid, next_node, next_parent, child_slot);
     return check_launch("grow_level");
 }
 
@@ -533,4 +718,30 @@ extern "C" int b200flow_finalize_forest(int64_t n_nodes, const uint32_t* pool_co
     if (n_nodes <= 0) return B200FLOW_OK;
     finalize_forest_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_nodes, pool_counts, C, leaf_prob);
     return check_launch("finalize_forest");
+}
+
+extern "C" int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows) {
+    if (F <= 0 || m <= 0 || n_bins <= 0 || C <= 0 || chunk_rows <= 0 || chunk_rows > 4096 || (chunk_rows & 31)) return 0;
+    return route_hist_smem(F, m, n_bins, C, chunk_rows) <= 100 * 1024 ? 1 : 0;    // >= 2 CTAs per SM
+}
+
+extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const int32_t* ent_row, const uint8_t* ent_w,
+                                         int32_t* ent_row_out, uint8_t* ent_w_out, int32_t n_slots, const int64_t* seg_begin,
+                                         const int64_t* seg_end, const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
+                                         const b200flow_split* split, const int32_t* child_slot, int32_t* cursors,
+                                         const uint16_t* subset_next, int32_t m, int32_t n_bins, int32_t C, uint32_t* hist_next,
+                                         void* stream) {
+    B2F_REQUIRE(tp && ent_row && ent_w && ent_row_out && ent_w_out && seg_begin && seg_end && chunk_off && split && child_slot && cursors &&
+                    subset_next && hist_next, "route_hist_level: null pointer");
+    B2F_REQUIRE((tp_stride & 15) == 0 && tp_stride >= (F + 1 + 15) / 16 * 16 && ((uintptr_t)tp & 15) == 0, "route_hist_level: bad TreePoint stride/alignment");
+    B2F_REQUIRE(b200flow_route_hist_fits(F, m, n_bins, C, chunk_rows), "route_hist_level: does not fit shared memory (use partition_level + hist_level)");
+    if (n_slots <= 0 || n_chunks <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(n_chunks < ((int64_t)1 << 31), "route_hist_level: too many chunks");
+    const size_t smem = route_hist_smem(F, m, n_bins, C, chunk_rows);
+    cudaError_t e = cudaFuncSetAttribute(route_hist_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("route_hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
+    route_hist_level_kernel<<<(unsigned)n_chunks, kRouteThreads, smem, (cudaStream_t)stream>>>(
+        tp, tp_stride, F, ent_row, ent_w, ent_row_out, ent_w_out, n_slots, seg_begin, seg_end, chunk_off, chunk_rows, split, child_slot, cursors,
+        subset_next, m, n_bins, C, hist_next);
+    return check_launch("route_hist_level");
 }

@@ -123,12 +123,13 @@ def test_find_splits_and_binning_exact():
     tp_o, bad = oracle.bin_rows(xs, thr, n_thr, arity, 70, y.cpu().numpy())
     tp_g, bad_g = m.bin(x, y)
     assert bad == 0 and int(bad_g.item()) == 0
-    assert np.array_equal(tp_g.cpu().numpy(), tp_o)
+    F = x.shape[1]
+    assert np.array_equal(tp_g.cpu().numpy()[:, :F + 1], tp_o[:, :F + 1]) and not tp_g[:, F + 1:].any()
     # float32 features bin identically to their widened fp64 values
     x32 = x.to(torch.float32)
     tp32, _ = m.bin(x32, y)
     tp_o32, _ = oracle.bin_rows(x32.cpu().numpy().astype(np.float64), thr, n_thr, arity, 70, y.cpu().numpy())
-    assert np.array_equal(tp32.cpu().numpy(), tp_o32)
+    assert np.array_equal(tp32.cpu().numpy()[:, :F + 1], tp_o32[:, :F + 1])
 
 
 def test_bagging_entries_match_oracle_weights():
@@ -275,6 +276,17 @@ def test_decision_tree_wide_histogram_multipass():
     model, fo, meta = _fit_both(x, y, C, arity, num_trees=1, max_bins=70, max_depth=5, bootstrap=False, seed=1)
     assert forests_equal(model.export(), fo.export()) == []
     _check_predictions(model, fo, meta, x[:4000], dt_mode=True)
+
+
+def test_unfused_level_loop_equals_fused(monkeypatch):
+    # route_hist_level (fused) and partition_level + hist_level (fallback for wide nodes) must build the same forest
+    x, y, arity, C = _features(40000, 5, 64)
+    p = fr.ForestParams(num_trees=6, max_bins=70, max_depth=9, seed=13)
+    a = fr.fit_forest(x, y, C, arity, p).export()
+    monkeypatch.setattr(fr, "FUSED", False)
+    b = fr.fit_forest(x, y, C, arity, p).export()
+    assert forests_equal(a, b) == []
+    assert np.array_equal(a["gain"], b["gain"])
 
 
 def test_forest_fp32_features_equal_fp64_features():

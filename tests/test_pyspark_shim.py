@@ -153,8 +153,8 @@ def test_cicids_script_flow(tmp_path):
     ds = ds.withColumn("Label", regexp_replace("Label", u"� ", ""))
     ds.select("Label").groupBy("Label").count().orderBy("count", ascending=False).show()
     n0 = ds.count()
-    ds = ds.where(col("Flow Duration") > 0).where(col("Init_Win_bytes_forward") > 0)
-    keep = (a["f00"] > 0) & (a["f01"] > 0)
+    ds = ds.where(col("Flow Duration") > 20).where(col("Init_Win_bytes_forward") > 1000.0)
+    keep = (a["f00"] > 20) & (a["f01"] > 1000.0)
     assert ds.count() == int(keep.sum()) < n0
     feats = [f for f in ds.columns if f not in ["Label"]]
     ds = VectorAssembler(inputCols=feats, outputCol="features").setHandleInvalid("skip").transform(ds)
