@@ -124,16 +124,17 @@ int b200flow_bin_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, i
                       uint8_t* tp, int32_t tp_stride, int32_t* bad_rows, void* stream);
 
 /* R6  BaggedPoint.convertToBaggedRDD, pass 1: per (tree, block of 1024 rows) number of
- * rows with Poisson weight > 0.  poisson_cdf: 32 uint32 thresholds, weight = #{k: r >= cdf[k]};
+ * rows with Poisson weight > 0.  poisson_cdf: 32 uint32 thresholds, weight = #{k: cdf[k] != 2^32-1 && r >= cdf[k]};
  * NULL = no bagging (weight 1 for every row, numTrees==1).  blk_cnt[T][n_blocks] int32. */
 int b200flow_bag_count(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows,
                        const uint32_t* poisson_cdf, int32_t* blk_cnt, void* stream);
 
 /* R6 pass 2: given blk_off = exclusive scan of blk_cnt (int64, tree-major), write the
- * bagged entries (row index, weight) of every tree in row order. */
+ * bagged entries of every tree in row order.  One entry = one uint32: local row index in the
+ * low 27 bits (=> at most 2^27 rows per GPU), bag weight in the high 5 bits. */
 int b200flow_bag_fill(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows,
                       const uint32_t* poisson_cdf, const int64_t* blk_off,
-                      int32_t* ent_row, uint8_t* ent_w, void* stream);
+                      uint32_t* ent, void* stream);
 
 /* exclusive prefix sum utilities used by the trainer (single launch, any n) */
 int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* out,
@@ -143,7 +144,7 @@ int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* ou
  * One LEVEL of every tree is processed at once.  An active node is a "slot":
  *   slot_tree[s], slot_nid[s] (MLlib node id: root 1, children 2i/2i+1),
  *   slot_node[s]  index of the node in the forest node pool,
- *   seg_begin/seg_end[s]  its bagged entries inside ent_row/ent_w.                */
+ *   seg_begin/seg_end[s]  its bagged entries inside ent (packed row|weight words).  */
 
 /* per-node feature subsets (RandomForest.selectNodesToSplit): m of F features by a
  * partial Fisher-Yates keyed by (seed, tree, nid), sorted ascending -> subset[s*m..].
@@ -157,7 +158,7 @@ int b200flow_feature_subsets(uint64_t seed, int32_t n_slots, const int32_t* slot
  * the caller; layout stride = m * n_bins * C.  chunk_off = exclusive scan over slots of
  * ceil(len/chunk_rows) (int64[n_slots+1]); the grid is one CTA per chunk. */
 int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
-                        const int32_t* ent_row, const uint8_t* ent_w,
+                        const uint32_t* ent,
                         int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
                         const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
                         const uint16_t* subset, int32_t m, int32_t n_bins, int32_t C,
@@ -216,8 +217,7 @@ int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, const uint32_
  * cursors[s*2+{0,1}] (int32, caller zeroes) end as (#left, #right).  Entries of children
  * that are leaves are dropped. */
 int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
-                             const int32_t* ent_row, const uint8_t* ent_w,
-                             int32_t* ent_row_out, uint8_t* ent_w_out,
+                             const uint32_t* ent, uint32_t* ent_out,
                              int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
                              const b200flow_split* split, int32_t* cursors, void* stream);
@@ -226,15 +226,16 @@ int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
  * record is gathered once, routed by its parent's split and accumulated into its CHILD's histogram
  * (hist_next[child_slot][j][bin][class], child feature subsets in subset_next, caller zeroes hist_next and
  * cursors).  chunk_off counts chunks of chunk_rows entries (multiple of 32, <= 4096) per parent slot; leaf
- * parents may have 0 chunks.  b200flow_route_hist_fits() tells whether the shapes fit shared memory; when
+ * parents must have 0 chunks.  The kernel is persistent (148 x k CTAs) and software-pipelined with
+ * asynchronous copies: entries(t+2) -> record gather(t+1) -> route + histogram(t).  b200flow_route_hist_fits() tells whether the shapes fit shared memory; when
  * they do not, use partition_level followed by hist_level. */
 int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows);
 int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
-                              const int32_t* ent_row, const uint8_t* ent_w,
-                              int32_t* ent_row_out, uint8_t* ent_w_out,
+                              const uint32_t* ent, uint32_t* ent_out,
                               int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
                               const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
                               const b200flow_split* split, const int32_t* child_slot, int32_t* cursors,
+                              void* chunk_scratch /* 16 bytes per chunk, 16-byte aligned */,
                               const uint16_t* subset_next, int32_t m, int32_t n_bins, int32_t C,
                               uint32_t* hist_next, void* stream);
 

@@ -38,15 +38,15 @@ _SIGNATURES = {
     "b200flow_find_splits": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P],
     "b200flow_bin_rows": [_P, _I32, _I64, _I32, _I64, _P, _P, _P, _I32, _P, _P, _I32, _P, _P],
     "b200flow_bag_count": [_U64, _I32, _I64, _I64, _P, _P, _P],
-    "b200flow_bag_fill": [_U64, _I32, _I64, _I64, _P, _P, _P, _P, _P],
+    "b200flow_bag_fill": [_U64, _I32, _I64, _I64, _P, _P, _P, _P],
     "b200flow_exclusive_scan_i32_to_i64": [_P, _I64, _P, _P, _P],
     "b200flow_feature_subsets": [_U64, _I32, _P, _P, _I32, _I32, _P, _P],
-    "b200flow_hist_level": [_P, _I32, _I32, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _I32, _I32, _I32, _P, _P],
+    "b200flow_hist_level": [_P, _I32, _I32, _P, _I32, _P, _P, _P, _I64, _I32, _P, _I32, _I32, _I32, _P, _P],
     "b200flow_score_level": [_P, _I32, _P, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _F64, _P, _P, _P, _P, _P],
     "b200flow_grow_level": [_I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P],
-    "b200flow_route_hist_level": [_P, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _I32, _I32, _I32,
-                                  _P, _P],
-    "b200flow_partition_level": [_P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P],
+    "b200flow_route_hist_level": [_P, _I32, _I32, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _I32, _I32,
+                                  _I32, _P, _P],
+    "b200flow_partition_level": [_P, _I32, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P],
     "b200flow_next_segments": [_I32, _P, _P, _P, _P, _P, _P, _P],
     "b200flow_finalize_forest": [_I64, _P, _I32, _P, _P],
     "b200flow_predict": [_P, _I32, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
@@ -58,7 +58,7 @@ EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version",
 
 _lib = None
 launches = 0   # kernels of OURS launched so far (counted per C-ABI call); bench.py reads the delta over the timed region
-_KERNELS_PER_CALL = {"b200flow_grow_level": 3, "b200flow_compact_rows": 3}
+_KERNELS_PER_CALL = {"b200flow_grow_level": 3, "b200flow_compact_rows": 3, "b200flow_route_hist_level": 2}
 
 
 def load():

@@ -19,7 +19,8 @@ from . import _lib
 from ._lib import NODE_DTYPE, SPLIT_DTYPE, B200FlowError, call, ptr
 
 CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_level (<= 2048)
-ROUTE_CHUNK_ROWS = 1024            # entries per CTA in the fused route_hist_level kernel
+import os as _os
+ROUTE_CHUNK_ROWS = int(_os.environ.get("B200FLOW_ROUTE_CHUNK", "512"))   # entries per CTA in the fused route_hist_level kernel
 FUSED = True                       # use route_hist_level (partition + next-level histogram in one pass) when it fits
 PROFILE = None                     # set to a dict to collect per-kernel CUDA-event timings (bench.py)
 
@@ -74,6 +75,8 @@ def poisson_cdf_table(rate=1.0):
         cdf += term
         out[k] = min(int(math.floor(cdf * 4294967296.0)), 0xFFFFFFFF)
         term = term * rate / (k + 1)
+    if out[30] != 0xFFFFFFFF:
+        raise B200FlowError("subsamplingRate %.3f too large: bag weights must stay below 31" % rate)
     return out
 
 
@@ -283,11 +286,12 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         call("b200flow_bag_count", seed, T, int(row_offset), n, ptr(cdf), ptr(blk_cnt))
     call("b200flow_exclusive_scan_i32_to_i64", ptr(blk_cnt), T * nb, ptr(blk_off), ptr(total))
     E = int(total.item())
-    ent_row = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-    ent_w = torch.empty(max(E, 1), dtype=torch.uint8, device=dev)
-    ent_row2 = torch.empty_like(ent_row); ent_w2 = torch.empty_like(ent_w)
+    if n > (1 << 27):
+        raise B200FlowError("at most 2^27 rows per GPU (bagged entries pack the row index into 27 bits); shard the rows")
+    ent = torch.empty(max(E, 1), dtype=torch.int32, device=dev)          # packed: row | weight << 27
+    ent2 = torch.empty_like(ent)
     if n > 0:
-        call("b200flow_bag_fill", seed, T, int(row_offset), n, ptr(cdf), ptr(blk_off), ptr(ent_row), ptr(ent_w))
+        call("b200flow_bag_fill", seed, T, int(row_offset), n, ptr(cdf), ptr(blk_off), ptr(ent))
 
     # ---- node pool
     cap_nodes = max(4096, 4 * T)
@@ -348,8 +352,33 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         call("b200flow_feature_subsets", seed, ns, ptr(s_tree), ptr(s_nid), F, m, ptr(sub))
         return sub
 
+    def route_and_hist(routed, lens_, split_, child_slot_, cursors_, next_subset_, n_next_):
+        """fused pass: route the entries of the `routed` parent slots to their children and build the children's
+        histograms (returns the zero-initialised, now filled, histogram buffer of the next level)."""
+        nch = torch.where(routed, (lens_ + (route_ch - 1)) // route_ch, torch.zeros_like(lens_)).to(torch.int32).contiguous()
+        roff, rch = chunk_table(nch)
+        hist_next = torch.zeros(n_next_ * hsz, dtype=torch.int32, device=dev)
+        scratch = torch.empty(max(rch, 1) * 4, dtype=torch.int32, device=dev)
+        _timed("route_hist_level", "b200flow_route_hist_level", ptr(tp), stride, F, ptr(ent), ptr(ent2), lens_.shape[0],
+               ptr(seg_begin), ptr(seg_end), ptr(roff), rch, route_ch, ptr(split_), ptr(child_slot_), ptr(cursors_), ptr(scratch),
+               ptr(next_subset_), m, n_bins, C, ptr(hist_next))
+        stats["hist_launches"] += 1
+        if PROFILE is not None:
+            PROFILE.setdefault("_route_entries", []).append(torch.where(routed, lens_, torch.zeros_like(lens_)).sum())
+        return hist_next
+
     subset = level_subsets(n_slots, slot_tree, slot_nid)
     hist_ready = None                  # histogram of the CURRENT level when the fused kernel already built it
+    if fused and n_slots * hsz * 4 <= HIST_BUDGET_BYTES and E > 0:
+        # level 0 through the same kernel: T pseudo-parents whose split sends every entry "left" into the tree's root
+        pseudo = np.zeros(T, SPLIT_DTYPE); pseudo["bin_thr"] = 255; pseudo["flags"] = 4
+        pseudo_t = torch.from_numpy(pseudo.view(np.uint8).reshape(T, 64).copy()).to(dev)
+        child0 = torch.stack([torch.arange(T, dtype=torch.int32, device=dev),
+                              torch.full((T,), -1, dtype=torch.int32, device=dev)], 1).contiguous().view(-1)
+        cursors0 = torch.zeros(2 * T, dtype=torch.int32, device=dev)
+        hist_ready = route_and_hist(torch.ones(T, dtype=torch.bool, device=dev), seg_end - seg_begin, pseudo_t, child0,
+                                    cursors0, subset, T)
+        ent, ent2 = ent2, ent          # the pass copied every entry into the other buffer, same segments
     while n_slots > 0:
         grow_pool(pool_size + 2 * n_slots)
         lens = seg_end - seg_begin
@@ -375,7 +404,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                     coff = (chunk_off[g0:g1 + 1] - chunk_off[g0]).contiguous()
                     gch = int((chunk_off[g1] - chunk_off[g0]).item())
                 # R7 HOT LOOP A (unfused form: level 0, and levels whose histograms exceed the fused budget)
-                _timed("hist_level", "b200flow_hist_level", ptr(tp), stride, F, ptr(ent_row), ptr(ent_w), gs,
+                _timed("hist_level", "b200flow_hist_level", ptr(tp), stride, F, ptr(ent), gs,
                        ptr(seg_begin[g0:g1]), ptr(seg_end[g0:g1]), ptr(coff), gch, CHUNK_ROWS, ptr(subset[g0:g1]), m, n_bins, C, ptr(h))
                 stats["hist_launches"] += 1
                 if PROFILE is not None:
@@ -413,28 +442,20 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
         if fused and n_next * hsz * 4 <= HIST_BUDGET_BYTES:
             # route every entry to its child AND build the children's histograms in the same pass
-            is_split = (split.view(torch.int32)[:, 3] & 1) == 0
-            nch = torch.where(is_split, (lens + (route_ch - 1)) // route_ch, torch.zeros_like(lens)).to(torch.int32).contiguous()
-            roff, rch = chunk_table(nch)
-            hist_ready = torch.zeros(n_next * hsz, dtype=torch.int32, device=dev)
-            _timed("route_hist_level", "b200flow_route_hist_level", ptr(tp), stride, F, ptr(ent_row), ptr(ent_w), ptr(ent_row2),
-                   ptr(ent_w2), n_slots, ptr(seg_begin), ptr(seg_end), ptr(roff), rch, route_ch, ptr(split), ptr(child_slot),
-                   ptr(cursors), ptr(next_subset), m, n_bins, C, ptr(hist_ready))
-            stats["hist_launches"] += 1
-            if PROFILE is not None:
-                PROFILE.setdefault("_route_entries", []).append(torch.where(is_split, lens, torch.zeros_like(lens)).sum())
+            flags = split.view(torch.int32)[:, 3]
+            routed = ((flags & 1) == 0) & ((flags & 6) != 6)          # split parents with at least one non-leaf child
+            hist_ready = route_and_hist(routed, lens, split, child_slot, cursors, next_subset, n_next)
         else:
             if chunk_off is None:
                 nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()
                 chunk_off, n_chunks = chunk_table(nch)
-            _timed("partition_level", "b200flow_partition_level", ptr(tp), stride, ptr(ent_row), ptr(ent_w), ptr(ent_row2), ptr(ent_w2),
+            _timed("partition_level", "b200flow_partition_level", ptr(tp), stride, ptr(ent), ptr(ent2),
                    n_slots, ptr(seg_begin), ptr(seg_end), ptr(chunk_off), n_chunks, CHUNK_ROWS, ptr(split), ptr(cursors))
         next_begin = torch.empty(n_next, dtype=torch.int64, device=dev)
         next_end = torch.empty(n_next, dtype=torch.int64, device=dev)
         call("b200flow_next_segments", n_next, ptr(next_parent), ptr(seg_begin), ptr(seg_end), ptr(cursors),
              ptr(next_begin), ptr(next_end))
-        ent_row, ent_row2 = ent_row2, ent_row
-        ent_w, ent_w2 = ent_w2, ent_w
+        ent, ent2 = ent2, ent
         slot_tree, slot_nid, slot_node, subset = next_tree, next_nid, next_node, next_subset
         seg_begin, seg_end = next_begin, next_end
         n_slots = n_next

@@ -46,9 +46,15 @@ __device__ __forceinline__ uint32_t bag_weight(uint64_t seed, int tree, uint64_t
     uint4 r = philox_keyed(seed, PURPOSE_BAG, (uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)tree, 0u);
     uint32_t k = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) k += (r.x >= cdf_sh[j]) ? 1u : 0u;
+    for (int j = 0; j < 32; ++j) k += (cdf_sh[j] != 0xFFFFFFFFu && r.x >= cdf_sh[j]) ? 1u : 0u;   // saturated = unreachable
     return k;
 }
+
+// bagged entry = row index (27 bits) | bag weight (5 bits): one 32-bit word per (tree, row) pair
+constexpr uint32_t kEntRowMask = (1u << 27) - 1u;
+__device__ __forceinline__ uint32_t ent_pack(uint32_t row, uint32_t w) { return row | (w << 27); }
+__device__ __forceinline__ int ent_row_of(uint32_t e) { return (int)(e & kEntRowMask); }
+__device__ __forceinline__ uint32_t ent_weight_of(uint32_t e) { return e >> 27; }
 
 // ------------------------------------------------------------------ warp / block helpers
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -128,6 +134,16 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // make generic-proxy smem writes visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Ampere-style asynchronous global->shared copies (LDGSTS): no register staging, tracked by commit groups
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // streaming (read-once) 128-bit load / store that do not pollute L1
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {

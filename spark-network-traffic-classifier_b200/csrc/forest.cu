@@ -60,8 +60,7 @@ __device__ __forceinline__ int find_slot(const int64_t* __restrict__ chunk_off, 
 
 // ------------------------------------------------------------------ R7 histogram build (HOT LOOP A)
 __global__ void __launch_bounds__(256) hist_level_kernel(const uint8_t* __restrict__ tp, int stride, int F,
-                                                         const int32_t* __restrict__ ent_row, const uint8_t* __restrict__ ent_w,
-                                                         int n_slots, const int64_t* __restrict__ seg_begin,
+                                                         const uint32_t* __restrict__ ent, int n_slots, const int64_t* __restrict__ seg_begin,
                                                          const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off,
                                                          int chunk_rows, const uint16_t* __restrict__ subset, int m, int n_bins,
                                                          int C, int m_pass, uint32_t* hist) {
@@ -82,9 +81,9 @@ __global__ void __launch_bounds__(256) hist_level_kernel(const uint8_t* __restri
         for (int i = threadIdx.x; i < hsz; i += blockDim.x) sh_hist[i] = 0;
         __syncthreads();
         for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
-            const int row = ent_row[i];
-            const uint32_t w = ent_w[i];
-            const uint8_t* rec = tp + (int64_t)row * stride;
+            const uint32_t en = ent[i];
+            const uint32_t w = ent_weight_of(en);
+            const uint8_t* rec = tp + (int64_t)ent_row_of(en) * stride;
             const int lab = rec[F];
             for (int j = 0; j < mp; ++j) {
                 const int bin = rec[sh_feat[j0 + j]];
@@ -369,10 +368,9 @@ __global__ void __launch_bounds__(kGrowBlock) grow_write_kernel(
 constexpr int kPartPerThread = 8;      // chunk_rows <= 256 * 8
 
 __global__ void __launch_bounds__(256) partition_level_kernel(
-    const uint8_t* __restrict__ tp, int stride, const int32_t* __restrict__ ent_row, const uint8_t* __restrict__ ent_w,
-    int32_t* ent_row_out, uint8_t* ent_w_out, int n_slots, const int64_t* __restrict__ seg_begin,
-    const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off, int chunk_rows,
-    const b200flow_split* __restrict__ split, int32_t* cursors) {
+    const uint8_t* __restrict__ tp, int stride, const uint32_t* __restrict__ ent, uint32_t* ent_out, int n_slots,
+    const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off,
+    int chunk_rows, const b200flow_split* __restrict__ split, int32_t* cursors) {
     const int64_t c = blockIdx.x;
     const int s = find_slot(chunk_off, n_slots, c);
     const b200flow_split sp = split[s];
@@ -383,18 +381,15 @@ __global__ void __launch_bounds__(256) partition_level_kernel(
     const int64_t b = sb + (c - chunk_off[s]) * chunk_rows;
     const int64_t e = min(se, b + chunk_rows);
     const int lane = lane_id();
-    int rows[kPartPerThread]; uint32_t wts = 0, wts2 = 0; uint32_t dec = 0;   // dec: 2 bits per entry (1 = left kept, 2 = right kept)
+    uint32_t ents[kPartPerThread]; uint32_t dec = 0;   // dec: 2 bits per entry (1 = left kept, 2 = right kept)
     int nL = 0, nR = 0;
 #pragma unroll
     for (int k = 0; k < kPartPerThread; ++k) {
         const int64_t i = b + threadIdx.x + (int64_t)k * blockDim.x;
-        int d = 0; rows[k] = 0;
+        int d = 0; ents[k] = 0;
         if (i < e) {
-            const int row = ent_row[i];
-            const uint32_t w = ent_w[i];
-            rows[k] = row;
-            if (k < 4) wts |= w << (8 * k); else wts2 |= w << (8 * (k - 4));
-            const int bin = tp[(int64_t)row * stride + sp.feat];
+            ents[k] = ent[i];
+            const int bin = tp[(int64_t)ent_row_of(ents[k]) * stride + sp.feat];
             const bool left = sp.kind == 0 ? (bin <= sp.bin_thr) : ((sp.mask[bin >> 6] >> (bin & 63)) & 1ull);
             d = left ? (keepL ? 1 : 0) : (keepR ? 2 : 0);
         }
@@ -410,193 +405,224 @@ __global__ void __launch_bounds__(256) partition_level_kernel(
         const int d = (dec >> (2 * k)) & 3;
         const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
         const uint32_t lt = (1u << lane) - 1u;
-        const uint32_t w = k < 4 ? (wts >> (8 * k)) & 0xffu : (wts2 >> (8 * (k - 4))) & 0xffu;
-        if (d == 1) { int64_t p = sb + baseL + __popc(mL & lt); ent_row_out[p] = rows[k]; ent_w_out[p] = (uint8_t)w; }
-        else if (d == 2) { int64_t p = se - 1 - (baseR + __popc(mR & lt)); ent_row_out[p] = rows[k]; ent_w_out[p] = (uint8_t)w; }
+        if (d == 1) ent_out[sb + baseL + __popc(mL & lt)] = ents[k];
+        else if (d == 2) ent_out[se - 1 - (baseR + __popc(mR & lt))] = ents[k];
         baseL += __popc(mL); baseR += __popc(mR);
     }
 }
-
 
 // ------------------------------------------------------------------ fused row routing + next-level histogram
-// One CTA = one chunk (<= CH entries) of one SPLIT parent slot.
-//   A. entries (row, w) -> smem; each entry's TreePoint record (64-byte aligned in HBM: exactly one DRAM burst)
-//      is gathered ONCE with 128-bit loads into a word-transposed smem tile (conflict-free per-lane byte reads);
-//   B. every entry is routed by the parent's split; its child's histogram (feature subset of the CHILD) is
-//      accumulated in shared memory.  Lanes whose (child, bins, label) key is identical — the duplicate-heavy
-//      smurf/neptune flows — are merged with match.any + redux so one lane issues the shared atomics;
-//   C. kept entries are written to the child's range (left grows up from seg_begin, right grows down from seg_end;
-//      one cursor reservation per CTA and side) and the two child histograms are flushed with sparse global REDs.
-// This replaces partition_level(L) + hist_level(L+1): the record gather, which is what both kernels were bound by
-// (HBM 64-byte bursts, ncu profiles/r01), happens once per entry per level instead of twice.
+// Persistent CTAs (a multiple of 148), each owning a contiguous range of chunks (<= CH entries of one SPLIT parent).
+// Software pipeline per CTA, all copies asynchronous (LDGSTS, no register staging):
+//     entries(t+2)  -->  record gather(t+1)  -->  route + histogram(t)
+//   * the gather brings each entry's 64-byte-aligned TreePoint record (one HBM burst) into a shared-memory tile,
+//     ONCE per entry per level — partition_level + hist_level gathered it twice and were bound by exactly that;
+//   * every entry is routed by the parent's split and accumulated into its CHILD's histogram (child feature subset)
+//     in shared memory; lanes with identical (child, bins, label) keys — the duplicate-heavy smurf/neptune flows —
+//     are merged with match.any + ballots so that one lane issues the shared atomics;
+//   * kept entries go to the child's range (left grows up from seg_begin, right grows down from seg_end; one cursor
+//     reservation per chunk and side); the two child histograms stay in shared memory while consecutive chunks belong
+//     to the same parent and are flushed with sparse global REDs when the parent changes.
 constexpr int kRouteThreads = 256;
 
-__device__ __forceinline__ void hist_add_keyed(uint32_t* hist, int m, int nbC, int C, const uint32_t (&keys)[4], int nwords,
-                                               uint32_t w, uint32_t active) {
-    // merge lanes with identical keys, then the group leader adds the summed weight for each of the m features
-    uint32_t g = active;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) if (q < nwords) g &= __match_any_sync(active, keys[q]);
-    const uint32_t sum = __reduce_add_sync(g, w);
-    if ((int)(__ffs(g) - 1) != lane_id()) return;
-    const int lab = (keys[m >> 2] >> ((m & 3) * 8)) & 0x7f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int j = q * 4 + r;
-            if (j < m) atomicAdd(&hist[j * nbC + ((keys[q] >> (8 * r)) & 0xff) * C + lab], sum);
-        }
-    }
+struct RouteChunk { int32_t slot; int32_t n; long long begin; };   // 16 bytes, one per chunk
+
+__global__ void route_chunks_kernel(const int64_t* __restrict__ chunk_off, int n_slots, int64_t n_chunks,
+                                    const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end, int CH,
+                                    RouteChunk* out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const int s = find_slot(chunk_off, n_slots, c);
+    RouteChunk rc; rc.slot = s; rc.begin = seg_begin[s] + (c - chunk_off[s]) * CH;
+    rc.n = (int)(min(seg_end[s], (int64_t)rc.begin + CH) - rc.begin);
+    out[c] = rc;
 }
 
-__global__ void __launch_bounds__(kRouteThreads) route_hist_level_kernel(
-    const uint8_t* __restrict__ tp, int stride, int F, const int32_t* __restrict__ ent_row, const uint8_t* __restrict__ ent_w,
-    int32_t* ent_row_out, uint8_t* ent_w_out, int n_slots, const int64_t* __restrict__ seg_begin,
-    const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off, int CH, const b200flow_split* __restrict__ split,
-    const int32_t* __restrict__ child_slot, int32_t* cursors, const uint16_t* __restrict__ subset_next, int m, int n_bins,
-    int C, uint32_t* hist_next) {
+// Σ of the (small integer) bag weights over the lanes of `g`, for every lane of `active` at once, from three ballots.
+// Lanes with w > 3 (3 % of bagged rows) are not merged: they add their own weight.
+__device__ __forceinline__ uint32_t group_weight(uint32_t g, uint32_t w, uint32_t active, bool* leader) {
+    const uint32_t b1 = __ballot_sync(active, w == 1), b2 = __ballot_sync(active, w == 2), b3 = __ballot_sync(active, w == 3);
+    const uint32_t gg = g & (b1 | b2 | b3);
+    if (w > 3) { *leader = true; return w; }
+    *leader = (int)(__ffs(gg) - 1) == lane_id();
+    return __popc(gg & b1) + 2 * __popc(gg & b2) + 3 * __popc(gg & b3);
+}
+
+struct RouteArgs {
+    const uint8_t* tp; int stride; int F;
+    const uint32_t* ent; uint32_t* ent_out;
+    const RouteChunk* chunks; int64_t n_chunks; int CH;
+    const int64_t* seg_begin; const int64_t* seg_end;
+    const b200flow_split* split; const int32_t* child_slot; int32_t* cursors;
+    const uint16_t* subset_next; int m; int n_bins; int C; uint32_t* hist_next;
+};
+
+// M = compile-time size of the per-node feature subset (keyed, merged shared atomics); M = 0: generic path
+template <int M>
+__global__ void __launch_bounds__(kRouteThreads, 3) route_hist_level_kernel(const RouteArgs a) {
     extern __shared__ __align__(16) uint32_t sm_u32[];
+    const int m = M > 0 ? M : a.m;
+    const int CH = a.CH, F = a.F;
     const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
-    const int recw = (F + 1 + 15) / 16 * 4;                 // staged words per record (whole 16-byte quads)
-    const int nbC = n_bins * C, hsz = m * nbC;
-    uint32_t* words = sm_u32;                                // [recw][CH]
-    uint32_t* sh_hist = words + (size_t)recw * CH;           // [2][hsz]
-    int* sh_rows = (int*)(sh_hist + 2 * hsz);                // [CH]
-    int* sh_feat = sh_rows + CH;                             // [2][m]
-    uint8_t* sh_w = (uint8_t*)(sh_feat + 2 * m);             // [CH]
+    const int nq = (F + 1 + 15) / 16;                        // staged 16-byte quads per record
+    const int nbC = a.n_bins * a.C, hsz = m * nbC;
+    uint32_t* tile = sm_u32;                                 // [2][nq][CH] quads (4 words each)
+    uint32_t* sh_ent = tile + (size_t)2 * nq * CH * 4;       // [3][CH]
+    uint32_t* sh_hist = sh_ent + 3 * CH;                     // [2][hsz]
+    int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: (word offset of the feature's byte in a tile << 5) | shift
     __shared__ int sh_cnt[kRouteThreads / 32][2];
     __shared__ int sh_base[2];
+    __shared__ b200flow_split sh_split;
+    __shared__ int sh_child[2];
 
-    const int64_t c = blockIdx.x;
-    const int s = find_slot(chunk_off, n_slots, c);
-    const b200flow_split sp = split[s];
-    if (sp.flags & 1) return;
-    const int cl = child_slot[2 * s], cr = child_slot[2 * s + 1];
-    if (cl < 0 && cr < 0) return;
-    const int64_t sb = seg_begin[s], se = seg_end[s];
-    const int64_t b = sb + (c - chunk_off[s]) * CH;
-    const int n = (int)(min(se, b + CH) - b);
+    const int64_t c0 = a.n_chunks * blockIdx.x / gridDim.x, c1 = a.n_chunks * (blockIdx.x + 1) / gridDim.x;
+    if (c0 >= c1) return;
+    auto chunk_at = [&](int64_t c) {
+        RouteChunk rc; rc.slot = -1; rc.n = 0; rc.begin = 0;
+        if (c < c1) { const int4 v = __ldg((const int4*)(a.chunks + c)); rc.slot = v.x; rc.n = v.y; rc.begin = ((long long)(uint32_t)v.z) | ((long long)v.w << 32); }
+        return rc;
+    };
+    auto issue_entries = [&](const RouteChunk& rc, int buf) {
+        for (int i = tid; i < rc.n; i += kRouteThreads) cp_async4(sh_ent + buf * CH + i, a.ent + rc.begin + i);
+    };
+    auto issue_gather = [&](const RouteChunk& rc, int ebuf, int tbuf) {
+        for (int i = tid; i < rc.n; i += kRouteThreads) {
+            const uint8_t* src = a.tp + (int64_t)ent_row_of(sh_ent[ebuf * CH + i]) * a.stride;
+            for (int q = 0; q < nq; ++q) cp_async16(tile + ((size_t)(tbuf * nq + q) * CH + i) * 4, src + q * 16);
+        }
+    };
+    auto flush = [&]() {
+        for (int side = 0; side < 2; ++side) {
+            const int cs = sh_child[side];
+            if (cs < 0) continue;
+            uint32_t* gh = a.hist_next + (int64_t)cs * hsz;
+            const uint32_t* sh = sh_hist + side * hsz;
+            for (int i = tid; i < hsz; i += kRouteThreads) { const uint32_t v = sh[i]; if (v) atomicAdd(gh + i, v); }
+        }
+    };
 
-    for (int i = tid; i < n; i += kRouteThreads) { sh_rows[i] = ent_row[b + i]; sh_w[i] = ent_w[b + i]; }
-    for (int i = tid; i < 2 * hsz; i += kRouteThreads) sh_hist[i] = 0;
-    for (int j = tid; j < 2 * m; j += kRouteThreads) {
-        const int cs = j < m ? cl : cr;
-        sh_feat[j] = cs >= 0 ? subset_next[(int64_t)cs * m + (j < m ? j : j - m)] : 0;
-    }
+    // prologue: entries(0), entries(1) -> gather(0)
+    RouteChunk r0 = chunk_at(c0), r1 = chunk_at(c0 + 1), r2 = chunk_at(c0 + 2);
+    issue_entries(r0, 0); issue_entries(r1, 1);
+    cp_async_commit(); cp_async_wait_all();
     __syncthreads();
-    // A. gather: 128-bit loads, quad-major so that all loads of a thread are independent (MLP)
-    const int nq = recw / 4;
-    for (int i0 = 0; i0 < n; i0 += kRouteThreads * 4) {
-        uint4 v[4][4];                                       // up to 4 entries x 4 quads in flight per thread
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = i0 + k * kRouteThreads + tid;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (i < n && q < nq) v[k][q] = __ldg((const uint4*)(tp + (int64_t)sh_rows[i] * stride) + q);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = i0 + k * kRouteThreads + tid;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (i < n && q < nq) {
-                    words[(4 * q + 0) * CH + i] = v[k][q].x; words[(4 * q + 1) * CH + i] = v[k][q].y;
-                    words[(4 * q + 2) * CH + i] = v[k][q].z; words[(4 * q + 3) * CH + i] = v[k][q].w;
-                }
-        }
-        for (int q = 4; q < nq; ++q)                         // records wider than 64 bytes: remaining quads
-            for (int k = 0; k < 4; ++k) {
-                const int i = i0 + k * kRouteThreads + tid;
-                if (i < n) {
-                    const uint4 x = __ldg((const uint4*)(tp + (int64_t)sh_rows[i] * stride) + q);
-                    words[(4 * q + 0) * CH + i] = x.x; words[(4 * q + 1) * CH + i] = x.y;
-                    words[(4 * q + 2) * CH + i] = x.z; words[(4 * q + 3) * CH + i] = x.w;
-                }
+    issue_gather(r0, 0, 0);
+    cp_async_commit();
+
+    int cur_slot = -1;
+    constexpr int NW = M > 0 ? (M + 1 + 3) / 4 : 1;
+    const int lab_pos = ((F >> 4) * CH * 4 + ((F >> 2) & 3)), lab_sh = (F & 3) * 8;
+    for (int64_t t = 0; c0 + t < c1; ++t) {
+        const int tb = (int)(t & 1), eb = (int)(t % 3);
+        cp_async_wait_all();
+        __syncthreads();                                       // gather(t), entries(t+1) landed; compute(t-1) finished
+        issue_gather(r1, (int)((t + 1) % 3), tb ^ 1);          // flies during compute(t)
+        issue_entries(r2, (int)((t + 2) % 3));
+        cp_async_commit();
+        const RouteChunk r3 = chunk_at(c0 + t + 3);
+
+        // ---- compute(t)
+        const int s = r0.slot, n = r0.n;
+        if (s != cur_slot) {                                   // CTA-uniform
+            if (cur_slot >= 0) flush();
+            __syncthreads();
+            for (int i = tid; i < 2 * hsz; i += kRouteThreads) sh_hist[i] = 0;
+            if (tid < 16) ((uint32_t*)&sh_split)[tid] = ((const uint32_t*)(a.split + s))[tid];
+            if (tid < 2) sh_child[tid] = a.child_slot[2 * s + tid];
+            for (int j = tid; j < 2 * m; j += kRouteThreads) {
+                const int cs = a.child_slot[2 * s + (j >= m)];
+                const int f = cs >= 0 ? a.subset_next[(int64_t)cs * m + (j < m ? j : j - m)] : 0;
+                sh_fpos[j] = (((f >> 4) * CH * 4 + ((f >> 2) & 3)) << 5) | ((f & 3) * 8);
             }
-    }
-    __syncthreads();
-    // B. route + accumulate.  Iteration k handles entries k*256 + tid (warp-contiguous)
-    const int fs = sp.feat;
-    const int nwords = (m + 1 + 3) / 4;                      // m bins + (label | side << 7)
-    const bool keyed = m <= 15 && C <= 128;
-    const int iters = (n + kRouteThreads - 1) / kRouteThreads;
-    int nL = 0, nR = 0;
-    uint32_t dec = 0;                                        // 2 bits per iteration (<= 16 iterations: CH <= 4096)
-    for (int k = 0; k < iters; ++k) {
-        const int i = k * kRouteThreads + tid;
-        int d = 0;
-        if (i < n) {
-            const int bin = (words[(fs >> 2) * CH + i] >> ((fs & 3) * 8)) & 0xff;
-            const bool left = sp.kind == 0 ? (bin <= sp.bin_thr) : ((sp.mask[bin >> 6] >> (bin & 63)) & 1ull);
-            d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
+            cur_slot = s;
+            __syncthreads();
         }
-        dec |= (uint32_t)d << (2 * k);
-        const uint32_t active = __ballot_sync(0xffffffffu, d != 0);
-        nL += __popc(__ballot_sync(0xffffffffu, d == 1));
-        nR += __popc(__ballot_sync(0xffffffffu, d == 2));
-        if (d != 0) {
-            const int side = d - 1;
-            const int* feats = sh_feat + side * m;
-            uint32_t* hist = sh_hist + side * hsz;
-            const int lab = (words[(F >> 2) * CH + i] >> ((F & 3) * 8)) & 0xff;
-            const uint32_t w = sh_w[i];
-            if (keyed) {
-                uint32_t keys[4] = {0, 0, 0, 0};
+        const int cl = sh_child[0], cr = sh_child[1];
+        const int fs = sh_split.feat, kind = sh_split.kind, thr = sh_split.bin_thr;
+        const int fs_pos = (fs >> 4) * CH * 4 + ((fs >> 2) & 3), fs_sh = (fs & 3) * 8;
+        const uint32_t* tl = tile + (size_t)tb * nq * CH * 4;
+        const uint32_t* en = sh_ent + eb * CH;
+        const int iters = (n + kRouteThreads - 1) / kRouteThreads;
+        int nL = 0, nR = 0;
+        uint32_t dec = 0;                                      // 2 bits per iteration (CH <= 4096)
+        for (int k = 0; k < iters; ++k) {
+            const int i = k * kRouteThreads + tid;
+            int d = 0;
+            if (i < n) {
+                const int bin = (tl[fs_pos + i * 4] >> fs_sh) & 0xff;
+                const bool left = kind == 0 ? (bin <= thr) : ((sh_split.mask[bin >> 6] >> (bin & 63)) & 1ull);
+                d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
+            }
+            dec |= (uint32_t)d << (2 * k);
+            const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
+            nL += __popc(mL); nR += __popc(mR);
+            if (d != 0) {
+                const uint32_t active = mL | mR;
+                const int side = d - 1;
+                const int* fpos = sh_fpos + side * m;
+                uint32_t* hist = sh_hist + side * hsz;
+                const int lab = (tl[lab_pos + i * 4] >> lab_sh) & 0xff;
+                const uint32_t w = ent_weight_of(en[i]);
+                if (M > 0) {
+                    uint32_t keys[NW];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < NW; ++q) keys[q] = 0;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int j = q * 4 + r;
-                        if (j < m) { const int f = feats[j]; keys[q] |= ((words[(f >> 2) * CH + i] >> ((f & 3) * 8)) & 0xffu) << (8 * r); }
-                        else if (j == m) keys[q] |= (uint32_t)(lab | (side << 7)) << (8 * r);
+                    for (int j = 0; j < M; ++j) {
+                        const int fp = fpos[j];
+                        keys[j >> 2] |= ((tl[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu) << (8 * (j & 3));
+                    }
+                    keys[M >> 2] |= (uint32_t)(lab | (side << 7)) << (8 * (M & 3));
+                    uint32_t g = active;
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) g &= __match_any_sync(active, keys[q]);
+                    bool leader;
+                    const uint32_t sum = group_weight(g, w, active, &leader);
+                    if (leader) {
+#pragma unroll
+                        for (int j = 0; j < M; ++j)
+                            atomicAdd(&hist[j * nbC + ((keys[j >> 2] >> (8 * (j & 3))) & 0xff) * a.C + lab], sum);
+                    }
+                } else {
+                    for (int j = 0; j < m; ++j) {
+                        const int fp = fpos[j];
+                        const int bin = (tl[(fp >> 5) + i * 4] >> (fp & 31)) & 0xff;
+                        atomicAdd(&hist[j * nbC + bin * a.C + lab], w);
                     }
                 }
-                hist_add_keyed(hist, m, nbC, C, keys, nwords, w, active);
-            } else {
-                for (int j = 0; j < m; ++j) {
-                    const int f = feats[j];
-                    const int bin = (words[(f >> 2) * CH + i] >> ((f & 3) * 8)) & 0xff;
-                    atomicAdd(&hist[j * nbC + bin * C + lab], w);
-                }
             }
         }
-    }
-    // C. positions: warp totals -> CTA reservation -> per-warp bases
-    if (lane == 0) { sh_cnt[wid][0] = nL; sh_cnt[wid][1] = nR; }
-    __syncthreads();
-    if (tid == 0) {
-        int tl = 0, tr = 0;
-        for (int q = 0; q < kRouteThreads / 32; ++q) { int a = sh_cnt[q][0], r = sh_cnt[q][1]; sh_cnt[q][0] = tl; sh_cnt[q][1] = tr; tl += a; tr += r; }
-        sh_base[0] = tl ? atomicAdd(&cursors[2 * s], tl) : 0;
-        sh_base[1] = tr ? atomicAdd(&cursors[2 * s + 1], tr) : 0;
-    }
-    __syncthreads();
-    int baseL = sh_base[0] + sh_cnt[wid][0], baseR = sh_base[1] + sh_cnt[wid][1];
-    const uint32_t lt = (1u << lane) - 1u;
-    for (int k = 0; k < iters; ++k) {
-        const int i = k * kRouteThreads + tid;
-        const int d = (dec >> (2 * k)) & 3;
-        const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
-        if (d == 1) { const int64_t p = sb + baseL + __popc(mL & lt); ent_row_out[p] = sh_rows[i]; ent_w_out[p] = sh_w[i]; }
-        else if (d == 2) { const int64_t p = se - 1 - (baseR + __popc(mR & lt)); ent_row_out[p] = sh_rows[i]; ent_w_out[p] = sh_w[i]; }
-        baseL += __popc(mL); baseR += __popc(mR);
-    }
-    // flush the two child histograms (sparse)
-    for (int i = tid; i < 2 * hsz; i += kRouteThreads) {
-        const uint32_t v = sh_hist[i];
-        if (v) {
-            const int side = i >= hsz;
-            const int cs = side ? cr : cl;
-            atomicAdd(hist_next + (int64_t)cs * hsz + (i - side * hsz), v);
+        // positions: warp totals -> one cursor reservation per chunk and side -> per-warp bases
+        if (lane == 0) { sh_cnt[wid][0] = nL; sh_cnt[wid][1] = nR; }
+        __syncthreads();
+        if (tid == 0) {
+            int tlc = 0, trc = 0;
+            for (int q = 0; q < kRouteThreads / 32; ++q) { int x = sh_cnt[q][0], y = sh_cnt[q][1]; sh_cnt[q][0] = tlc; sh_cnt[q][1] = trc; tlc += x; trc += y; }
+            sh_base[0] = tlc ? atomicAdd(&a.cursors[2 * s], tlc) : 0;
+            sh_base[1] = trc ? atomicAdd(&a.cursors[2 * s + 1], trc) : 0;
         }
+        __syncthreads();
+        const int64_t sb = a.seg_begin[s], se = a.seg_end[s];
+        int baseL = sh_base[0] + sh_cnt[wid][0], baseR = sh_base[1] + sh_cnt[wid][1];
+        const uint32_t lt = (1u << lane) - 1u;
+        for (int k = 0; k < iters; ++k) {
+            const int i = k * kRouteThreads + tid;
+            const int d = (dec >> (2 * k)) & 3;
+            const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
+            if (d == 1) a.ent_out[sb + baseL + __popc(mL & lt)] = en[i];
+            else if (d == 2) a.ent_out[se - 1 - (baseR + __popc(mR & lt))] = en[i];
+            baseL += __popc(mL); baseR += __popc(mR);
+        }
+        r0 = r1; r1 = r2; r2 = r3;
     }
+    cp_async_wait_all();
+    __syncthreads();
+    flush();
 }
 
 static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
-    const size_t recw = (size_t)(F + 1 + 15) / 16 * 4;
-    return recw * CH * 4 + 2 * (size_t)m * n_bins * C * 4 + (size_t)CH * 4 + 2 * (size_t)m * 4 + (size_t)CH + 64;
+    const size_t nq = (size_t)(F + 1 + 15) / 16;
+    return 2 * nq * CH * 16 + 3 * (size_t)CH * 4 + 2 * (size_t)m * n_bins * C * 4 + 2 * (size_t)m * 4 + 64;
 }
 
 __global__ void next_segments_kernel(int n_next, const int32_t* __restrict__ next_parent, const int64_t* __restrict__ seg_begin,
@@ -630,11 +656,11 @@ extern "C" int b200flow_feature_subsets(uint64_t seed, int32_t n_slots, const in
     return check_launch("feature_subsets");
 }
 
-extern "C" int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const int32_t* ent_row, const uint8_t* ent_w,
+extern "C" int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const uint32_t* ent,
                                    int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end, const int64_t* chunk_off,
                                    int64_t n_chunks, int32_t chunk_rows, const uint16_t* subset, int32_t m, int32_t n_bins,
                                    int32_t C, uint32_t* hist, void* stream) {
-    B2F_REQUIRE(tp && ent_row && ent_w && seg_begin && seg_end && chunk_off && subset && hist, "hist_level: null pointer");
+    B2F_REQUIRE(tp && ent && seg_begin && seg_end && chunk_off && subset && hist, "hist_level: null pointer");
     B2F_REQUIRE(m > 0 && m <= 256 && n_bins > 0 && n_bins <= 256 && C > 0 && C <= 256 && chunk_rows > 0, "hist_level: bad shape");
     const size_t per_feat = (size_t)n_bins * C * 4;
     B2F_REQUIRE(per_feat <= 200 * 1024, "hist_level: one feature's histogram (%zu B) exceeds shared memory", per_feat);
@@ -646,7 +672,7 @@ extern "C" int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t
     B2F_REQUIRE(n_chunks < ((int64_t)1 << 31), "hist_level: too many chunks");
     cudaError_t e = cudaFuncSetAttribute(hist_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
-    hist_level_kernel<<<(unsigned)n_chunks, 256, smem, (cudaStream_t)stream>>>(tp, tp_stride, F, ent_row, ent_w, n_slots, seg_begin,
+    hist_level_kernel<<<(unsigned)n_chunks, 256, smem, (cudaStream_t)stream>>>(tp, tp_stride, F, ent, n_slots, seg_begin,
                                                                              seg_end, chunk_off, chunk_rows, subset, m, n_bins, C, m_pass, hist);
     return check_launch("hist_level");
 }
@@ -692,16 +718,14 @@ extern "C" int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, co
     return check_launch("grow_level");
 }
 
-extern "C" int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride, const int32_t* ent_row, const uint8_t* ent_w,
-                                        int32_t* ent_row_out, uint8_t* ent_w_out, int32_t n_slots, const int64_t* seg_begin,
-                                        const int64_t* seg_end, const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
-                                        const b200flow_split* split, int32_t* cursors, void* stream) {
-    B2F_REQUIRE(tp && ent_row && ent_w && ent_row_out && ent_w_out && seg_begin && seg_end && chunk_off && split && cursors,
-                "partition_level: null pointer");
+extern "C" int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride, const uint32_t* ent, uint32_t* ent_out, int32_t n_slots,
+                                        const int64_t* seg_begin, const int64_t* seg_end, const int64_t* chunk_off, int64_t n_chunks,
+                                        int32_t chunk_rows, const b200flow_split* split, int32_t* cursors, void* stream) {
+    B2F_REQUIRE(tp && ent && ent_out && seg_begin && seg_end && chunk_off && split && cursors, "partition_level: null pointer");
     B2F_REQUIRE(chunk_rows > 0 && chunk_rows <= 256 * kPartPerThread, "partition_level: chunk_rows must be <= %d", 256 * kPartPerThread);
     if (n_slots <= 0 || n_chunks <= 0) return B200FLOW_OK;
-    partition_level_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(tp, tp_stride, ent_row, ent_w, ent_row_out, ent_w_out, n_slots,
-                                                                               seg_begin, seg_end, chunk_off, chunk_rows, split, cursors);
+    partition_level_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(tp, tp_stride, ent, ent_out, n_slots, seg_begin, seg_end,
+                                                                               chunk_off, chunk_rows, split, cursors);
     return check_launch("partition_level");
 }
 
@@ -722,26 +746,44 @@ extern "C" int b200flow_finalize_forest(int64_t n_nodes, const uint32_t* pool_co
 
 extern "C" int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows) {
     if (F <= 0 || m <= 0 || n_bins <= 0 || C <= 0 || chunk_rows <= 0 || chunk_rows > 4096 || (chunk_rows & 31)) return 0;
-    return route_hist_smem(F, m, n_bins, C, chunk_rows) <= 100 * 1024 ? 1 : 0;    // >= 2 CTAs per SM
+    return route_hist_smem(F, m, n_bins, C, chunk_rows) <= 110 * 1024 ? 1 : 0;    // >= 2 CTAs per SM
 }
 
-extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const int32_t* ent_row, const uint8_t* ent_w,
-                                         int32_t* ent_row_out, uint8_t* ent_w_out, int32_t n_slots, const int64_t* seg_begin,
-                                         const int64_t* seg_end, const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
-                                         const b200flow_split* split, const int32_t* child_slot, int32_t* cursors,
-                                         const uint16_t* subset_next, int32_t m, int32_t n_bins, int32_t C, uint32_t* hist_next,
-                                         void* stream) {
-    B2F_REQUIRE(tp && ent_row && ent_w && ent_row_out && ent_w_out && seg_begin && seg_end && chunk_off && split && child_slot && cursors &&
+extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const uint32_t* ent, uint32_t* ent_out,
+                                         int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end, const int64_t* chunk_off,
+                                         int64_t n_chunks, int32_t chunk_rows, const b200flow_split* split, const int32_t* child_slot,
+                                         int32_t* cursors, void* chunk_scratch, const uint16_t* subset_next, int32_t m, int32_t n_bins,
+                                         int32_t C, uint32_t* hist_next, void* stream) {
+    B2F_REQUIRE(tp && ent && ent_out && seg_begin && seg_end && chunk_off && split && child_slot && cursors && chunk_scratch &&
                     subset_next && hist_next, "route_hist_level: null pointer");
     B2F_REQUIRE((tp_stride & 15) == 0 && tp_stride >= (F + 1 + 15) / 16 * 16 && ((uintptr_t)tp & 15) == 0, "route_hist_level: bad TreePoint stride/alignment");
+    B2F_REQUIRE(((uintptr_t)chunk_scratch & 15) == 0, "route_hist_level: chunk_scratch must be 16-byte aligned");
     B2F_REQUIRE(b200flow_route_hist_fits(F, m, n_bins, C, chunk_rows), "route_hist_level: does not fit shared memory (use partition_level + hist_level)");
     if (n_slots <= 0 || n_chunks <= 0) return B200FLOW_OK;
-    B2F_REQUIRE(n_chunks < ((int64_t)1 << 31), "route_hist_level: too many chunks");
     const size_t smem = route_hist_smem(F, m, n_bins, C, chunk_rows);
-    cudaError_t e = cudaFuncSetAttribute(route_hist_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("route_hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
-    route_hist_level_kernel<<<(unsigned)n_chunks, kRouteThreads, smem, (cudaStream_t)stream>>>(
-        tp, tp_stride, F, ent_row, ent_w, ent_row_out, ent_w_out, n_slots, seg_begin, seg_end, chunk_off, chunk_rows, split, child_slot, cursors,
-        subset_next, m, n_bins, C, hist_next);
+    RouteChunk* chunks = (RouteChunk*)chunk_scratch;
+    route_chunks_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chunk_off, n_slots, n_chunks, seg_begin, seg_end,
+                                                                                            chunk_rows, chunks);
+    RouteArgs a;
+    a.tp = tp; a.stride = tp_stride; a.F = F; a.ent = ent; a.ent_out = ent_out; a.chunks = chunks; a.n_chunks = n_chunks; a.CH = chunk_rows;
+    a.seg_begin = seg_begin; a.seg_end = seg_end; a.split = split; a.child_slot = child_slot; a.cursors = cursors;
+    a.subset_next = subset_next; a.m = m; a.n_bins = n_bins; a.C = C; a.hist_next = hist_next;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 3) per_sm = 3;                             // __launch_bounds__(256, 3)
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (int64_t)kNumSMs * per_sm;
+    const unsigned grid = (unsigned)(n_chunks < want ? n_chunks : want);
+#define B2F_ROUTE_CASE(MM)                                                                                                     \
+    case MM: {                                                                                                                 \
+        cudaError_t e = cudaFuncSetAttribute(route_hist_level_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) { set_error("route_hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }       \
+        route_hist_level_kernel<MM><<<grid, kRouteThreads, smem, (cudaStream_t)stream>>>(a);                                   \
+    } break;
+    switch ((m <= 12 && C <= 128) ? m : 0) {
+        B2F_ROUTE_CASE(1) B2F_ROUTE_CASE(2) B2F_ROUTE_CASE(3) B2F_ROUTE_CASE(4) B2F_ROUTE_CASE(5) B2F_ROUTE_CASE(6)
+        B2F_ROUTE_CASE(7) B2F_ROUTE_CASE(8) B2F_ROUTE_CASE(9) B2F_ROUTE_CASE(10) B2F_ROUTE_CASE(11) B2F_ROUTE_CASE(12)
+        default: B2F_ROUTE_CASE(0)
+    }
+#undef B2F_ROUTE_CASE
     return check_launch("route_hist_level");
 }

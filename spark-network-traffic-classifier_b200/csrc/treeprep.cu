@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) bag_count_kernel(uint64_t seed, int64_t r
 
 __global__ void __launch_bounds__(256) bag_fill_kernel(uint64_t seed, int64_t row_offset, int64_t n,
                                                        const uint32_t* __restrict__ cdf, const int64_t* __restrict__ blk_off,
-                                                       int64_t n_blocks, int32_t* ent_row, uint8_t* ent_w) {
+                                                       int64_t n_blocks, uint32_t* ent) {
     __shared__ uint32_t cdf_sh[32];
     __shared__ int sh[33];
     const int t = blockIdx.y;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) bag_fill_kernel(uint64_t seed, int64_t ro
     int64_t pos = blk_off[(int64_t)t * n_blocks + blockIdx.x] + ex;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (w[k] > 0) { ent_row[pos] = (int32_t)(rb + k); ent_w[pos] = (uint8_t)min(w[k], 255u); ++pos; }
+        if (w[k] > 0) { ent[pos] = ent_pack((uint32_t)(rb + k), min(w[k], 31u)); ++pos; }
 }
 
 }  // namespace b200flow
@@ -277,10 +277,11 @@ extern "C" int b200flow_bag_count(uint64_t seed, int32_t T, int64_t row_offset, 
 }
 
 extern "C" int b200flow_bag_fill(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows, const uint32_t* poisson_cdf,
-                                 const int64_t* blk_off, int32_t* ent_row, uint8_t* ent_w, void* stream) {
-    B2F_REQUIRE(blk_off && ent_row && ent_w && T > 0 && T <= 65535 && n_rows >= 0 && n_rows < ((int64_t)1 << 31), "bag_fill: bad arguments");
+                                 const int64_t* blk_off, uint32_t* ent, void* stream) {
+    B2F_REQUIRE(blk_off && ent && T > 0 && T <= 65535 && n_rows >= 0, "bag_fill: bad arguments");
+    B2F_REQUIRE(n_rows <= (int64_t)kEntRowMask + 1, "bag_fill: at most 2^27 rows per GPU (row index is packed into 27 bits)");
     if (n_rows == 0) return B200FLOW_OK;
     int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
-    bag_fill_kernel<<<dim3((unsigned)nb, (unsigned)T), 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n_rows, poisson_cdf, blk_off, nb, ent_row, ent_w);
+    bag_fill_kernel<<<dim3((unsigned)nb, (unsigned)T), 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n_rows, poisson_cdf, blk_off, nb, ent);
     return check_launch("bag_fill");
 }

@@ -145,9 +145,10 @@ def test_bagging_entries_match_oracle_weights():
     _lib.call("b200flow_exclusive_scan_i32_to_i64", _lib.ptr(blk), T * nb, _lib.ptr(off), _lib.ptr(tot))
     E = int(tot.item())
     assert E == int((w > 0).sum())
-    rows = torch.empty(E, dtype=torch.int32, device=DEV); wt = torch.empty(E, dtype=torch.uint8, device=DEV)
-    _lib.call("b200flow_bag_fill", seed, T, 17, n, _lib.ptr(cdf_t), _lib.ptr(off), _lib.ptr(rows), _lib.ptr(wt))
-    rows, wt, off = rows.cpu().numpy(), wt.cpu().numpy(), off.cpu().numpy()
+    ent = torch.empty(E, dtype=torch.int32, device=DEV)
+    _lib.call("b200flow_bag_fill", seed, T, 17, n, _lib.ptr(cdf_t), _lib.ptr(off), _lib.ptr(ent))
+    ent = ent.cpu().numpy().view(np.uint32)
+    rows, wt, off = (ent & ((1 << 27) - 1)).astype(np.int64), (ent >> 27).astype(np.uint8), off.cpu().numpy()
     for t in range(T):
         b, e = off[t * nb], off[(t + 1) * nb]
         idx = np.nonzero(w[t])[0]
@@ -192,7 +193,8 @@ def test_hist_level_direct():
     _lib.call("b200flow_exclusive_scan_i32_to_i64", _lib.ptr(nch), S, _lib.ptr(coff), _lib.ptr(tot))
     sub = torch.stack([torch.sort(torch.randperm(F, device=DEV, generator=g)[:m])[0] for _ in range(S)]).to(torch.int16)
     hist = torch.zeros(S * m * NB * C, dtype=torch.int32, device=DEV)
-    _lib.call("b200flow_hist_level", _lib.ptr(tp), stride, F, _lib.ptr(ent), _lib.ptr(w), S, _lib.ptr(seg_b), _lib.ptr(seg_e),
+    packed = (ent.to(torch.int64) | (w.to(torch.int64) << 27)).to(torch.int32)
+    _lib.call("b200flow_hist_level", _lib.ptr(tp), stride, F, _lib.ptr(packed), S, _lib.ptr(seg_b), _lib.ptr(seg_e),
               _lib.ptr(coff), int(tot.item()), 2048, _lib.ptr(sub), m, NB, C, _lib.ptr(hist))
     hist = hist.cpu().numpy().reshape(S, m, NB, C)
     tp_n, ent_n, w_n, sub_n = tp.cpu().numpy(), ent.cpu().numpy(), w.cpu().numpy(), sub.cpu().numpy()
