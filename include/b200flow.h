@@ -225,9 +225,10 @@ int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
 /* R7 fused with the row routing: partition_level(L) + hist_level(L+1) in ONE pass — every entry's TreePoint
  * record is gathered once, routed by its parent's split and accumulated into its CHILD's histogram
  * (hist_next[child_slot][j][bin][class], child feature subsets in subset_next, caller zeroes hist_next and
- * cursors).  chunk_off counts chunks of chunk_rows entries (multiple of 32, <= 4096) per parent slot; leaf
- * parents must have 0 chunks.  The kernel is persistent (148 x k CTAs) and software-pipelined with
- * asynchronous copies: entries(t+2) -> record gather(t+1) -> route + histogram(t).  b200flow_route_hist_fits() tells whether the shapes fit shared memory; when
+ * cursors).  chunk_off counts chunks of chunk_rows = 512 entries (8 warps x 64) per parent slot; leaf
+ * parents must have 0 chunks.  The kernel is persistent (148 x k CTAs); each warp gathers the records of
+ * its 64 entries with asynchronous copies into a private shared-memory tile and there is no CTA barrier
+ * except when the parent slot changes.  b200flow_route_hist_fits() tells whether the shapes fit shared memory; when
  * they do not, use partition_level followed by hist_level. */
 int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows);
 int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,

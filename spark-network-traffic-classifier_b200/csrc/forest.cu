@@ -457,40 +457,30 @@ struct RouteArgs {
     const uint16_t* subset_next; int m; int n_bins; int C; uint32_t* hist_next;
 };
 
-// M = compile-time size of the per-node feature subset (keyed, merged shared atomics); M = 0: generic path
+// M = compile-time size of the per-node feature subset (keyed, merged shared atomics); M = 0: generic path.
+// Barrier-free inner loop: a chunk is kRouteWarps sub-chunks of 64 entries, one per warp.  Each warp loads its 64
+// entries, gathers their records with LDGSTS into its private tile, and — while the gather is in flight — writes out
+// the PREVIOUS sub-chunk (whose cursor reservation, a global atomic issued one step earlier, has landed by then).
+// Latency is hidden by the 32 resident warps per SM; CTA-wide barriers happen only when the parent slot changes.
+constexpr int kRouteWarps = kRouteThreads / 32;
+constexpr int kSub = 64;                                    // entries per warp step (2 per lane)
+
 template <int M>
-__global__ void __launch_bounds__(kRouteThreads, 3) route_hist_level_kernel(const RouteArgs a) {
+__global__ void __launch_bounds__(kRouteThreads, 4) route_hist_level_kernel(const RouteArgs a) {
     extern __shared__ __align__(16) uint32_t sm_u32[];
     const int m = M > 0 ? M : a.m;
-    const int CH = a.CH, F = a.F;
+    const int F = a.F;
     const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     const int nq = (F + 1 + 15) / 16;                        // staged 16-byte quads per record
     const int nbC = a.n_bins * a.C, hsz = m * nbC;
-    uint32_t* tile = sm_u32;                                 // [2][nq][CH] quads (4 words each)
-    uint32_t* sh_ent = tile + (size_t)2 * nq * CH * 4;       // [3][CH]
-    uint32_t* sh_hist = sh_ent + 3 * CH;                     // [2][hsz]
+    uint32_t* tile = sm_u32 + (size_t)wid * nq * kSub * 4;   // this warp's [nq][64] quads
+    uint32_t* sh_hist = sm_u32 + (size_t)kRouteWarps * nq * kSub * 4;   // [2][hsz]
     int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: (word offset of the feature's byte in a tile << 5) | shift
-    __shared__ int sh_cnt[kRouteThreads / 32][2];
-    __shared__ int sh_base[2];
     __shared__ b200flow_split sh_split;
     __shared__ int sh_child[2];
 
     const int64_t c0 = a.n_chunks * blockIdx.x / gridDim.x, c1 = a.n_chunks * (blockIdx.x + 1) / gridDim.x;
     if (c0 >= c1) return;
-    auto chunk_at = [&](int64_t c) {
-        RouteChunk rc; rc.slot = -1; rc.n = 0; rc.begin = 0;
-        if (c < c1) { const int4 v = __ldg((const int4*)(a.chunks + c)); rc.slot = v.x; rc.n = v.y; rc.begin = ((long long)(uint32_t)v.z) | ((long long)v.w << 32); }
-        return rc;
-    };
-    auto issue_entries = [&](const RouteChunk& rc, int buf) {
-        for (int i = tid; i < rc.n; i += kRouteThreads) cp_async4(sh_ent + buf * CH + i, a.ent + rc.begin + i);
-    };
-    auto issue_gather = [&](const RouteChunk& rc, int ebuf, int tbuf) {
-        for (int i = tid; i < rc.n; i += kRouteThreads) {
-            const uint8_t* src = a.tp + (int64_t)ent_row_of(sh_ent[ebuf * CH + i]) * a.stride;
-            for (int q = 0; q < nq; ++q) cp_async16(tile + ((size_t)(tbuf * nq + q) * CH + i) * 4, src + q * 16);
-        }
-    };
     auto flush = [&]() {
         for (int side = 0; side < 2; ++side) {
             const int cs = sh_child[side];
@@ -500,30 +490,33 @@ __global__ void __launch_bounds__(kRouteThreads, 3) route_hist_level_kernel(cons
             for (int i = tid; i < hsz; i += kRouteThreads) { const uint32_t v = sh[i]; if (v) atomicAdd(gh + i, v); }
         }
     };
-
-    // prologue: entries(0), entries(1) -> gather(0)
-    RouteChunk r0 = chunk_at(c0), r1 = chunk_at(c0 + 1), r2 = chunk_at(c0 + 2);
-    issue_entries(r0, 0); issue_entries(r1, 1);
-    cp_async_commit(); cp_async_wait_all();
-    __syncthreads();
-    issue_gather(r0, 0, 0);
-    cp_async_commit();
+    // pending write of the previous sub-chunk (registers only)
+    bool pending = false;
+    uint32_t p_e0 = 0, p_e1 = 0, p_dec = 0; int p_bl = 0, p_br = 0; int64_t p_sb = 0, p_se = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    auto write_pending = [&]() {
+        int baseL = __shfl_sync(0xffffffffu, p_bl, 0), baseR = __shfl_sync(0xffffffffu, p_br, 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int d = (p_dec >> (2 * k)) & 3;
+            const uint32_t e = k ? p_e1 : p_e0;
+            const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
+            if (d == 1) a.ent_out[p_sb + baseL + __popc(mL & lt)] = e;
+            else if (d == 2) a.ent_out[p_se - 1 - (baseR + __popc(mR & lt))] = e;
+            baseL += __popc(mL); baseR += __popc(mR);
+        }
+        pending = false;
+    };
 
     int cur_slot = -1;
     constexpr int NW = M > 0 ? (M + 1 + 3) / 4 : 1;
-    const int lab_pos = ((F >> 4) * CH * 4 + ((F >> 2) & 3)), lab_sh = (F & 3) * 8;
-    for (int64_t t = 0; c0 + t < c1; ++t) {
-        const int tb = (int)(t & 1), eb = (int)(t % 3);
-        cp_async_wait_all();
-        __syncthreads();                                       // gather(t), entries(t+1) landed; compute(t-1) finished
-        issue_gather(r1, (int)((t + 1) % 3), tb ^ 1);          // flies during compute(t)
-        issue_entries(r2, (int)((t + 2) % 3));
-        cp_async_commit();
-        const RouteChunk r3 = chunk_at(c0 + t + 3);
-
-        // ---- compute(t)
-        const int s = r0.slot, n = r0.n;
-        if (s != cur_slot) {                                   // CTA-uniform
+    const int lab_pos = (F >> 4) * kSub * 4 + ((F >> 2) & 3), lab_sh = (F & 3) * 8;
+    for (int64_t c = c0; c < c1; ++c) {
+        const int4 rcv = __ldg((const int4*)(a.chunks + c));
+        const int s = rcv.x, n = rcv.y;
+        const int64_t begin = ((long long)(uint32_t)rcv.z) | ((long long)rcv.w << 32);
+        if (s != cur_slot) {                                   // same decision in every warp: all iterate the same chunks
+            __syncthreads();
             if (cur_slot >= 0) flush();
             __syncthreads();
             for (int i = tid; i < 2 * hsz; i += kRouteThreads) sh_hist[i] = 0;
@@ -532,24 +525,42 @@ __global__ void __launch_bounds__(kRouteThreads, 3) route_hist_level_kernel(cons
             for (int j = tid; j < 2 * m; j += kRouteThreads) {
                 const int cs = a.child_slot[2 * s + (j >= m)];
                 const int f = cs >= 0 ? a.subset_next[(int64_t)cs * m + (j < m ? j : j - m)] : 0;
-                sh_fpos[j] = (((f >> 4) * CH * 4 + ((f >> 2) & 3)) << 5) | ((f & 3) * 8);
+                sh_fpos[j] = (((f >> 4) * kSub * 4 + ((f >> 2) & 3)) << 5) | ((f & 3) * 8);
             }
             cur_slot = s;
             __syncthreads();
         }
+        const int i0 = wid * kSub;
+        const int cnt = min(kSub, n - i0);
+        if (cnt <= 0) continue;
+        // entries of this warp's sub-chunk (coalesced), then the record gather (asynchronous, into the private tile)
+        const uint32_t* ep = a.ent + begin + i0;
+        const uint32_t e0 = lane < cnt ? __ldg(ep + lane) : 0u;
+        const uint32_t e1 = lane + 32 < cnt ? __ldg(ep + 32 + lane) : 0u;
+        if (lane < cnt) {
+            const uint8_t* src = a.tp + (int64_t)ent_row_of(e0) * a.stride;
+            for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + lane) * 4, src + q * 16);
+        }
+        if (lane + 32 < cnt) {
+            const uint8_t* src = a.tp + (int64_t)ent_row_of(e1) * a.stride;
+            for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + 32 + lane) * 4, src + q * 16);
+        }
+        cp_async_commit();
+        if (pending) write_pending();                          // overlaps with the gather in flight
+        cp_async_wait_all();
+        __syncwarp();
+        // route + accumulate
         const int cl = sh_child[0], cr = sh_child[1];
         const int fs = sh_split.feat, kind = sh_split.kind, thr = sh_split.bin_thr;
-        const int fs_pos = (fs >> 4) * CH * 4 + ((fs >> 2) & 3), fs_sh = (fs & 3) * 8;
-        const uint32_t* tl = tile + (size_t)tb * nq * CH * 4;
-        const uint32_t* en = sh_ent + eb * CH;
-        const int iters = (n + kRouteThreads - 1) / kRouteThreads;
+        const int fs_pos = (fs >> 4) * kSub * 4 + ((fs >> 2) & 3), fs_sh = (fs & 3) * 8;
         int nL = 0, nR = 0;
-        uint32_t dec = 0;                                      // 2 bits per iteration (CH <= 4096)
-        for (int k = 0; k < iters; ++k) {
-            const int i = k * kRouteThreads + tid;
+        uint32_t dec = 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = k * 32 + lane;
             int d = 0;
-            if (i < n) {
-                const int bin = (tl[fs_pos + i * 4] >> fs_sh) & 0xff;
+            if (i < cnt) {
+                const int bin = (tile[fs_pos + i * 4] >> fs_sh) & 0xff;
                 const bool left = kind == 0 ? (bin <= thr) : ((sh_split.mask[bin >> 6] >> (bin & 63)) & 1ull);
                 d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
             }
@@ -561,8 +572,8 @@ __global__ void __launch_bounds__(kRouteThreads, 3) route_hist_level_kernel(cons
                 const int side = d - 1;
                 const int* fpos = sh_fpos + side * m;
                 uint32_t* hist = sh_hist + side * hsz;
-                const int lab = (tl[lab_pos + i * 4] >> lab_sh) & 0xff;
-                const uint32_t w = ent_weight_of(en[i]);
+                const int lab = (tile[lab_pos + i * 4] >> lab_sh) & 0xff;
+                const uint32_t w = ent_weight_of(k ? e1 : e0);
                 if (M > 0) {
                     uint32_t keys[NW];
 #pragma unroll
@@ -570,7 +581,7 @@ __global__ void __launch_bounds__(kRouteThreads, 3) route_hist_level_kernel(cons
 #pragma unroll
                     for (int j = 0; j < M; ++j) {
                         const int fp = fpos[j];
-                        keys[j >> 2] |= ((tl[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu) << (8 * (j & 3));
+                        keys[j >> 2] |= ((tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu) << (8 * (j & 3));
                     }
                     keys[M >> 2] |= (uint32_t)(lab | (side << 7)) << (8 * (M & 3));
                     uint32_t g = active;
@@ -586,43 +597,29 @@ __global__ void __launch_bounds__(kRouteThreads, 3) route_hist_level_kernel(cons
                 } else {
                     for (int j = 0; j < m; ++j) {
                         const int fp = fpos[j];
-                        const int bin = (tl[(fp >> 5) + i * 4] >> (fp & 31)) & 0xff;
+                        const int bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xff;
                         atomicAdd(&hist[j * nbC + bin * a.C + lab], w);
                     }
                 }
             }
         }
-        // positions: warp totals -> one cursor reservation per chunk and side -> per-warp bases
-        if (lane == 0) { sh_cnt[wid][0] = nL; sh_cnt[wid][1] = nR; }
-        __syncthreads();
-        if (tid == 0) {
-            int tlc = 0, trc = 0;
-            for (int q = 0; q < kRouteThreads / 32; ++q) { int x = sh_cnt[q][0], y = sh_cnt[q][1]; sh_cnt[q][0] = tlc; sh_cnt[q][1] = trc; tlc += x; trc += y; }
-            sh_base[0] = tlc ? atomicAdd(&a.cursors[2 * s], tlc) : 0;
-            sh_base[1] = trc ? atomicAdd(&a.cursors[2 * s + 1], trc) : 0;
+        __syncwarp();
+        // reserve output positions (one atomic pair per warp step); the result is consumed one step later
+        if (nL | nR) {
+            if (lane == 0) { p_bl = nL ? atomicAdd(&a.cursors[2 * s], nL) : 0; p_br = nR ? atomicAdd(&a.cursors[2 * s + 1], nR) : 0; }
+            p_e0 = e0; p_e1 = e1; p_dec = dec; p_sb = a.seg_begin[s]; p_se = a.seg_end[s];
+            pending = true;
         }
-        __syncthreads();
-        const int64_t sb = a.seg_begin[s], se = a.seg_end[s];
-        int baseL = sh_base[0] + sh_cnt[wid][0], baseR = sh_base[1] + sh_cnt[wid][1];
-        const uint32_t lt = (1u << lane) - 1u;
-        for (int k = 0; k < iters; ++k) {
-            const int i = k * kRouteThreads + tid;
-            const int d = (dec >> (2 * k)) & 3;
-            const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
-            if (d == 1) a.ent_out[sb + baseL + __popc(mL & lt)] = en[i];
-            else if (d == 2) a.ent_out[se - 1 - (baseR + __popc(mR & lt))] = en[i];
-            baseL += __popc(mL); baseR += __popc(mR);
-        }
-        r0 = r1; r1 = r2; r2 = r3;
     }
-    cp_async_wait_all();
+    if (pending) write_pending();
     __syncthreads();
     flush();
 }
 
 static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
     const size_t nq = (size_t)(F + 1 + 15) / 16;
-    return 2 * nq * CH * 16 + 3 * (size_t)CH * 4 + 2 * (size_t)m * n_bins * C * 4 + 2 * (size_t)m * 4 + 64;
+    (void)CH;                                               // a chunk is always kRouteWarps * kSub entries
+    return (size_t)kRouteWarps * nq * kSub * 16 + 2 * (size_t)m * n_bins * C * 4 + 2 * (size_t)m * 4 + 64;
 }
 
 __global__ void next_segments_kernel(int n_next, const int32_t* __restrict__ next_parent, const int64_t* __restrict__ seg_begin,
@@ -745,7 +742,7 @@ extern "C" int b200flow_finalize_forest(int64_t n_nodes, const uint32_t* pool_co
 }
 
 extern "C" int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows) {
-    if (F <= 0 || m <= 0 || n_bins <= 0 || C <= 0 || chunk_rows <= 0 || chunk_rows > 4096 || (chunk_rows & 31)) return 0;
+    if (F <= 0 || m <= 0 || n_bins <= 0 || C <= 0 || chunk_rows != kRouteWarps * kSub) return 0;
     return route_hist_smem(F, m, n_bins, C, chunk_rows) <= 110 * 1024 ? 1 : 0;    // >= 2 CTAs per SM
 }
 
@@ -769,7 +766,7 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     a.seg_begin = seg_begin; a.seg_end = seg_end; a.split = split; a.child_slot = child_slot; a.cursors = cursors;
     a.subset_next = subset_next; a.m = m; a.n_bins = n_bins; a.C = C; a.hist_next = hist_next;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > 3) per_sm = 3;                             // __launch_bounds__(256, 3)
+    if (per_sm > 4) per_sm = 4;                             // __launch_bounds__(256, 4)
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (int64_t)kNumSMs * per_sm;
     const unsigned grid = (unsigned)(n_chunks < want ? n_chunks : want);
