@@ -11,6 +11,7 @@
 // walk as in MLlib); histograms are accumulated in shared memory per (node, chunk) and flushed
 // with sparse global REDs, so the multi-GPU all-reduce sees one dense uint32 buffer per level.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -457,24 +458,27 @@ struct RouteArgs {
     const uint16_t* subset_next; int m; int n_bins; int C; uint32_t* hist_next;
 };
 
-// M = compile-time size of the per-node feature subset (keyed, merged shared atomics); M = 0: generic path.
-// Barrier-free inner loop: a chunk is kRouteWarps sub-chunks of 64 entries, one per warp.  Each warp loads its 64
-// entries, gathers their records with LDGSTS into its private tile, and — while the gather is in flight — writes out
-// the PREVIOUS sub-chunk (whose cursor reservation, a global atomic issued one step earlier, has landed by then).
-// Latency is hidden by the 32 resident warps per SM; CTA-wide barriers happen only when the parent slot changes.
+// M = compile-time size of the per-node feature subset (merged shared atomics); M = 0: generic path.
+// Barrier-free inner loop: a chunk is kRouteWarps sub-chunks of 64 entries, one per warp.  Per warp and step t:
+//     entries(t+2) -> registers (prefetch) | record gather(t+1) -> private tile[(t+1)&1] (LDGSTS, asynchronous)
+//     write-out of step t-1 (its cursor reservation, a global atomic issued one step earlier, has landed by now)
+//     route + histogram of step t from tile[t&1]
+// so every warp always has one gather (64 x 64-byte HBM bursts) in flight.  CTA-wide barriers happen only when the
+// parent slot changes (flush + re-zero of the two child histograms).
 constexpr int kRouteWarps = kRouteThreads / 32;
 constexpr int kSub = 64;                                    // entries per warp step (2 per lane)
 
-template <int M>
-__global__ void __launch_bounds__(kRouteThreads, 4) route_hist_level_kernel(const RouteArgs a) {
+template <int M, int NBUF, bool FULLKEY>
+__global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_level_kernel(const RouteArgs a) {
     extern __shared__ __align__(16) uint32_t sm_u32[];
     const int m = M > 0 ? M : a.m;
     const int F = a.F;
     const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     const int nq = (F + 1 + 15) / 16;                        // staged 16-byte quads per record
     const int nbC = a.n_bins * a.C, hsz = m * nbC;
-    uint32_t* tile = sm_u32 + (size_t)wid * nq * kSub * 4;   // this warp's [nq][64] quads
-    uint32_t* sh_hist = sm_u32 + (size_t)kRouteWarps * nq * kSub * 4;   // [2][hsz]
+    const int tile_words = nq * kSub * 4;
+    uint32_t* tiles = sm_u32 + (size_t)wid * NBUF * tile_words; // this warp's NBUF [nq][64] quad tiles
+    uint32_t* sh_hist = sm_u32 + (size_t)kRouteWarps * NBUF * tile_words;   // [2][hsz]
     int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: (word offset of the feature's byte in a tile << 5) | shift
     __shared__ b200flow_split sh_split;
     __shared__ int sh_child[2];
@@ -490,7 +494,27 @@ __global__ void __launch_bounds__(kRouteThreads, 4) route_hist_level_kernel(cons
             for (int i = tid; i < hsz; i += kRouteThreads) { const uint32_t v = sh[i]; if (v) atomicAdd(gh + i, v); }
         }
     };
-    // pending write of the previous sub-chunk (registers only)
+    auto desc_at = [&](int64_t c) { return c < c1 ? __ldg((const int4*)(a.chunks + c)) : make_int4(-1, 0, 0, 0); };
+    auto count_of = [&](const int4& d) { return min(kSub, d.y - wid * kSub); };
+    auto entries_of = [&](const int4& d, uint32_t* x0, uint32_t* x1) {
+        const int cn = count_of(d);
+        const uint32_t* ep = a.ent + (((long long)(uint32_t)d.z) | ((long long)d.w << 32)) + wid * kSub;
+        *x0 = lane < cn ? __ldg(ep + lane) : 0u;
+        *x1 = lane + 32 < cn ? __ldg(ep + 32 + lane) : 0u;
+    };
+    auto issue_gather = [&](const int4& d, uint32_t x0, uint32_t x1, uint32_t* tile) {
+        const int cn = count_of(d);
+        if (lane < cn) {
+            const uint8_t* src = a.tp + (int64_t)ent_row_of(x0) * a.stride;
+            for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + lane) * 4, src + q * 16);
+        }
+        if (lane + 32 < cn) {
+            const uint8_t* src = a.tp + (int64_t)ent_row_of(x1) * a.stride;
+            for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + 32 + lane) * 4, src + q * 16);
+        }
+        cp_async_commit();
+    };
+    // pending write of the previous step (registers only)
     bool pending = false;
     uint32_t p_e0 = 0, p_e1 = 0, p_dec = 0; int p_bl = 0, p_br = 0; int64_t p_sb = 0, p_se = 0;
     const uint32_t lt = (1u << lane) - 1u;
@@ -508,13 +532,25 @@ __global__ void __launch_bounds__(kRouteThreads, 4) route_hist_level_kernel(cons
         pending = false;
     };
 
+    int4 d0 = desc_at(c0), d1 = desc_at(c0 + 1), d2 = desc_at(c0 + 2);
+    uint32_t e0, e1, f0, f1, g0 = 0, g1 = 0;                 // entries of steps t, t+1, t+2
+    entries_of(d0, &e0, &e1);
+    entries_of(d1, &f0, &f1);
+    if (NBUF == 2) issue_gather(d0, e0, e1, tiles);
     int cur_slot = -1;
-    constexpr int NW = M > 0 ? (M + 1 + 3) / 4 : 1;
     const int lab_pos = (F >> 4) * kSub * 4 + ((F >> 2) & 3), lab_sh = (F & 3) * 8;
     for (int64_t c = c0; c < c1; ++c) {
-        const int4 rcv = __ldg((const int4*)(a.chunks + c));
-        const int s = rcv.x, n = rcv.y;
-        const int64_t begin = ((long long)(uint32_t)rcv.z) | ((long long)rcv.w << 32);
+        const int par = NBUF == 2 ? (int)((c - c0) & 1) : 0;
+        const uint32_t* tile = tiles + par * tile_words;
+        entries_of(d2, &g0, &g1);                              // prefetch, consumed two steps later
+        const int4 d3 = desc_at(c + 3);
+        if (NBUF == 2) issue_gather(d1, f0, f1, tiles + (par ^ 1) * tile_words);   // in flight during this step's compute
+        else issue_gather(d0, e0, e1, tiles);                  // single tile: latency hidden by the other resident warps
+        if (pending) write_pending();
+        if (NBUF == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");  // this step's gather has landed
+        else cp_async_wait_all();
+        __syncwarp();
+        const int s = d0.x;
         if (s != cur_slot) {                                   // same decision in every warp: all iterate the same chunks
             __syncthreads();
             if (cur_slot >= 0) flush();
@@ -530,96 +566,105 @@ __global__ void __launch_bounds__(kRouteThreads, 4) route_hist_level_kernel(cons
             cur_slot = s;
             __syncthreads();
         }
-        const int i0 = wid * kSub;
-        const int cnt = min(kSub, n - i0);
-        if (cnt <= 0) continue;
-        // entries of this warp's sub-chunk (coalesced), then the record gather (asynchronous, into the private tile)
-        const uint32_t* ep = a.ent + begin + i0;
-        const uint32_t e0 = lane < cnt ? __ldg(ep + lane) : 0u;
-        const uint32_t e1 = lane + 32 < cnt ? __ldg(ep + 32 + lane) : 0u;
-        if (lane < cnt) {
-            const uint8_t* src = a.tp + (int64_t)ent_row_of(e0) * a.stride;
-            for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + lane) * 4, src + q * 16);
-        }
-        if (lane + 32 < cnt) {
-            const uint8_t* src = a.tp + (int64_t)ent_row_of(e1) * a.stride;
-            for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + 32 + lane) * 4, src + q * 16);
-        }
-        cp_async_commit();
-        if (pending) write_pending();                          // overlaps with the gather in flight
-        cp_async_wait_all();
-        __syncwarp();
-        // route + accumulate
-        const int cl = sh_child[0], cr = sh_child[1];
-        const int fs = sh_split.feat, kind = sh_split.kind, thr = sh_split.bin_thr;
-        const int fs_pos = (fs >> 4) * kSub * 4 + ((fs >> 2) & 3), fs_sh = (fs & 3) * 8;
-        int nL = 0, nR = 0;
-        uint32_t dec = 0;
+        const int cnt = count_of(d0);
+        if (cnt > 0) {
+            const int cl = sh_child[0], cr = sh_child[1];
+            const int fs = sh_split.feat, kind = sh_split.kind, thr = sh_split.bin_thr;
+            const int fs_pos = (fs >> 4) * kSub * 4 + ((fs >> 2) & 3), fs_sh = (fs & 3) * 8;
+            int nL = 0, nR = 0;
+            uint32_t dec = 0;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int i = k * 32 + lane;
-            int d = 0;
-            if (i < cnt) {
-                const int bin = (tile[fs_pos + i * 4] >> fs_sh) & 0xff;
-                const bool left = kind == 0 ? (bin <= thr) : ((sh_split.mask[bin >> 6] >> (bin & 63)) & 1ull);
-                d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
-            }
-            dec |= (uint32_t)d << (2 * k);
-            const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
-            nL += __popc(mL); nR += __popc(mR);
-            if (d != 0) {
-                const uint32_t active = mL | mR;
-                const int side = d - 1;
-                const int* fpos = sh_fpos + side * m;
-                uint32_t* hist = sh_hist + side * hsz;
-                const int lab = (tile[lab_pos + i * 4] >> lab_sh) & 0xff;
-                const uint32_t w = ent_weight_of(k ? e1 : e0);
-                if (M > 0) {
-                    uint32_t keys[NW];
+            for (int k = 0; k < 2; ++k) {
+                const int i = k * 32 + lane;
+                int d = 0;
+                if (i < cnt) {
+                    const int bin = (tile[fs_pos + i * 4] >> fs_sh) & 0xff;
+                    const bool left = kind == 0 ? (bin <= thr) : ((sh_split.mask[bin >> 6] >> (bin & 63)) & 1ull);
+                    d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
+                }
+                dec |= (uint32_t)d << (2 * k);
+                const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
+                nL += __popc(mL); nR += __popc(mR);
+                if (d != 0) {
+                    const uint32_t active = mL | mR;
+                    const int side = d - 1;
+                    const int* fpos = sh_fpos + side * m;
+                    uint32_t* hist = sh_hist + side * hsz;
+                    const uint32_t lab = (tile[lab_pos + i * 4] >> lab_sh) & 0xffu;
+                    const uint32_t w = ent_weight_of(k ? e1 : e0);
+                    if (M > 0 && FULLKEY) {
+                        // whole-key merge: lanes with identical (child, all M bins, label) are combined
+                        constexpr int NW = (M + 1 + 3) / 4;
+                        uint32_t keys[NW];
 #pragma unroll
-                    for (int q = 0; q < NW; ++q) keys[q] = 0;
+                        for (int q = 0; q < NW; ++q) keys[q] = 0;
 #pragma unroll
-                    for (int j = 0; j < M; ++j) {
-                        const int fp = fpos[j];
-                        keys[j >> 2] |= ((tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu) << (8 * (j & 3));
-                    }
-                    keys[M >> 2] |= (uint32_t)(lab | (side << 7)) << (8 * (M & 3));
-                    uint32_t g = active;
+                        for (int j = 0; j < M; ++j) {
+                            const int fp = fpos[j];
+                            keys[j >> 2] |= ((tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu) << (8 * (j & 3));
+                        }
+                        keys[M >> 2] |= (lab | ((uint32_t)side << 7)) << (8 * (M & 3));
+                        uint32_t g = active;
 #pragma unroll
-                    for (int q = 0; q < NW; ++q) g &= __match_any_sync(active, keys[q]);
-                    bool leader;
-                    const uint32_t sum = group_weight(g, w, active, &leader);
-                    if (leader) {
+                        for (int q = 0; q < NW; ++q) g &= __match_any_sync(active, keys[q]);
+                        bool leader;
+                        const uint32_t sum = group_weight(g, w, active, &leader);
+                        if (leader) {
 #pragma unroll
-                        for (int j = 0; j < M; ++j)
-                            atomicAdd(&hist[j * nbC + ((keys[j >> 2] >> (8 * (j & 3))) & 0xff) * a.C + lab], sum);
-                    }
-                } else {
-                    for (int j = 0; j < m; ++j) {
-                        const int fp = fpos[j];
-                        const int bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xff;
-                        atomicAdd(&hist[j * nbC + bin * a.C + lab], w);
+                            for (int j = 0; j < M; ++j)
+                                atomicAdd(&hist[j * nbC + ((keys[j >> 2] >> (8 * (j & 3))) & 0xff) * a.C + lab], sum);
+                        }
+                    } else if (M > 0) {
+                        // per-feature merge: lanes that hit the same (child, feature, bin, label) counter are combined with
+                        // match.any; the group's bag-weight sum comes from three ballots shared by all features
+                        const uint32_t b1 = __ballot_sync(active, w == 1), b2 = __ballot_sync(active, w == 2), b3 = __ballot_sync(active, w == 3);
+                        const uint32_t small = b1 | b2 | b3;
+                        const uint32_t tag = (lab << 8) | ((uint32_t)side << 16);
+#pragma unroll
+                        for (int j = 0; j < M; ++j) {
+                            const int fp = fpos[j];
+                            const uint32_t bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu;
+                            const uint32_t gg = __match_any_sync(active, bin | tag) & small;
+                            uint32_t* addr = &hist[j * nbC + bin * a.C + lab];
+                            if (w > 3) atomicAdd(addr, w);
+                            else if ((int)(__ffs(gg) - 1) == lane) atomicAdd(addr, (uint32_t)(__popc(gg & b1) + 2 * __popc(gg & b2) + 3 * __popc(gg & b3)));
+                        }
+                    } else {
+                        for (int j = 0; j < m; ++j) {
+                            const int fp = fpos[j];
+                            const uint32_t bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu;
+                            atomicAdd(&hist[j * nbC + bin * a.C + lab], w);
+                        }
                     }
                 }
             }
+            __syncwarp();
+            // reserve output positions (one atomic pair per warp step); the result is consumed one step later
+            if (nL | nR) {
+                if (lane == 0) { p_bl = nL ? atomicAdd(&a.cursors[2 * s], nL) : 0; p_br = nR ? atomicAdd(&a.cursors[2 * s + 1], nR) : 0; }
+                p_e0 = e0; p_e1 = e1; p_dec = dec; p_sb = a.seg_begin[s]; p_se = a.seg_end[s];
+                pending = true;
+            }
         }
-        __syncwarp();
-        // reserve output positions (one atomic pair per warp step); the result is consumed one step later
-        if (nL | nR) {
-            if (lane == 0) { p_bl = nL ? atomicAdd(&a.cursors[2 * s], nL) : 0; p_br = nR ? atomicAdd(&a.cursors[2 * s + 1], nR) : 0; }
-            p_e0 = e0; p_e1 = e1; p_dec = dec; p_sb = a.seg_begin[s]; p_se = a.seg_end[s];
-            pending = true;
-        }
+        d0 = d1; d1 = d2; d2 = d3; e0 = f0; e1 = f1; f0 = g0; f1 = g1;
     }
     if (pending) write_pending();
+    cp_async_wait_all();
     __syncthreads();
     flush();
+}
+
+static int route_variant() {                                // tuning knob (tile buffers per warp, merge strategy)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;                                               // bit0: 2 tiles per warp, bit1: per-feature merge
 }
 
 static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
     const size_t nq = (size_t)(F + 1 + 15) / 16;
     (void)CH;                                               // a chunk is always kRouteWarps * kSub entries
-    return (size_t)kRouteWarps * nq * kSub * 16 + 2 * (size_t)m * n_bins * C * 4 + 2 * (size_t)m * 4 + 64;
+    const size_t nbuf = (route_variant() & 1) ? 2 : 1;
+    return (size_t)kRouteWarps * nbuf * nq * kSub * 16 + 2 * (size_t)m * n_bins * C * 4 + 2 * (size_t)m * 4 + 64;
 }
 
 __global__ void next_segments_kernel(int n_next, const int32_t* __restrict__ next_parent, const int64_t* __restrict__ seg_begin,
@@ -766,21 +811,32 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     a.seg_begin = seg_begin; a.seg_end = seg_end; a.split = split; a.child_slot = child_slot; a.cursors = cursors;
     a.subset_next = subset_next; a.m = m; a.n_bins = n_bins; a.C = C; a.hist_next = hist_next;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > 4) per_sm = 4;                             // __launch_bounds__(256, 4)
+    const int max_per_sm = (route_variant() & 1) ? 3 : 4;   // __launch_bounds__
+    if (per_sm > max_per_sm) per_sm = max_per_sm;
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (int64_t)kNumSMs * per_sm;
     const unsigned grid = (unsigned)(n_chunks < want ? n_chunks : want);
-#define B2F_ROUTE_CASE(MM)                                                                                                     \
-    case MM: {                                                                                                                 \
-        cudaError_t e = cudaFuncSetAttribute(route_hist_level_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+#define B2F_ROUTE_LAUNCH(KERNEL)                                                                                               \
+    {                                                                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
         if (e != cudaSuccess) { set_error("route_hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }       \
-        route_hist_level_kernel<MM><<<grid, kRouteThreads, smem, (cudaStream_t)stream>>>(a);                                   \
-    } break;
+        KERNEL<<<grid, kRouteThreads, smem, (cudaStream_t)stream>>>(a);                                                        \
+    }
+#define B2F_ROUTE_CASE(MM)                                                                                                     \
+    case MM:                                                                                                                   \
+        switch (route_variant() & 3) {                                                                                         \
+            case 0: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, true>)) break;                                            \
+            case 1: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, true>)) break;                                            \
+            case 2: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, false>)) break;                                           \
+            default: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, false>)) break;                                          \
+        }                                                                                                                      \
+        break;
     switch ((m <= 12 && C <= 128) ? m : 0) {
         B2F_ROUTE_CASE(1) B2F_ROUTE_CASE(2) B2F_ROUTE_CASE(3) B2F_ROUTE_CASE(4) B2F_ROUTE_CASE(5) B2F_ROUTE_CASE(6)
         B2F_ROUTE_CASE(7) B2F_ROUTE_CASE(8) B2F_ROUTE_CASE(9) B2F_ROUTE_CASE(10) B2F_ROUTE_CASE(11) B2F_ROUTE_CASE(12)
         default: B2F_ROUTE_CASE(0)
     }
 #undef B2F_ROUTE_CASE
+#undef B2F_ROUTE_LAUNCH
     return check_launch("route_hist_level");
 }
