@@ -8,7 +8,7 @@
 // encode kernel, data movement (HBM-bound; algorithmic bytes/row = row_bytes + n_out*sizeof(out) + 4):
 //   HBM --cp.async.bulk (TMA, UBLKCP) + mbarrier--> smem record tile [R x row_bytes], NS-deep ring
 //   threads: one fixed OUTPUT slot per thread, rows strided -> smem out tile [R x n_out] (bank-conflict free)
-//   smem out tile --cp.async.bulk store (bulk_group)--> HBM, double buffered
+//   smem out tile --cp.async.bulk store (bulk_group)--> HBM, triple buffered; ONE __syncthreads per tile
 // Arithmetic is fp64 ((v - mean) * scale, no FMA contraction) and rounded once to the output type.
 #include "common.cuh"
 
@@ -49,25 +49,17 @@ struct EncodeArgs {
     int out_stride;   // bytes per output stage (128-aligned)
 };
 
-constexpr int kEncStages = 4;     // TMA load ring depth
+constexpr int kEncStages = 3;     // TMA load ring depth
+constexpr int kEncOutBufs = 3;    // output tiles: two bulk stores may be in flight while the third tile is computed
 constexpr int kEncThreads = 256;
-
-__device__ __forceinline__ double enc_read_field(const uint8_t* rowp, int kind, int off) {
-    if (kind == B200FLOW_SRC_F32) return (double)(*(const float*)(rowp + off));
-    if (kind == B200FLOW_SRC_F64) {
-        const uint32_t* p = (const uint32_t*)(rowp + off);   // 4-byte aligned reads: fields need not be 8-aligned
-        return __hiloint2double((int)p[1], (int)p[0]);
-    }
-    return (double)(*(const int32_t*)(rowp + off));          // I32
-}
 
 template <typename OUT>
 __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [in ring][out x2][mbar x4][badtag 2*R][plan][lut]
+    // layout: [in ring][out x3][mbar][badtag 2*R][plan][lut]
     uint8_t* in_base = smem;
     uint8_t* out_base = in_base + (size_t)kEncStages * a.in_stride;
-    uint64_t* mbar = (uint64_t*)(out_base + 2 * (size_t)a.out_stride);
+    uint64_t* mbar = (uint64_t*)(out_base + kEncOutBufs * (size_t)a.out_stride);
     int32_t* badtag = (int32_t*)(mbar + kEncStages);
     b200flow_slot* plan_sh = (b200flow_slot*)(badtag + 2 * a.R + ((2 * a.R) & 1));   // keep 8-byte alignment
     int32_t* lut_sh = (int32_t*)(plan_sh + a.n_out);
@@ -103,24 +95,25 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
             if (t < n_tiles) issue_load(t, s);
         }
 
-    // thread -> output slot mapping: one fixed slot per thread when n_out <= blockDim
+    // thread -> output slot mapping: one fixed slot per thread when n_out <= blockDim, rows fastest, so that the lanes of
+    // a warp share their slot's source kind (no divergence between the numeric and the lookup loops)
     const bool fixed = n_out <= bd;
     const int rp = fixed ? bd / n_out : 1;
-    const int d0 = fixed ? tid % n_out : tid;
-    const int r0 = fixed ? tid / n_out : 0;
+    const int d0 = fixed ? tid / rp : tid;
+    const int r0 = fixed ? tid % rp : 0;
     const int dstep = fixed ? n_out : bd;
     const bool active = fixed ? (tid < rp * n_out) : true;
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % kEncStages, o = it & 1;
+        const int s = it % kEncStages, o = it % kEncOutBufs, ob = it & 1;
         const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
         const int64_t row_base = tile * R;
         const int rows = (int)min((int64_t)R, a.n_rows - row_base);
         const bool full = rows == R;
         uint8_t* in_t = in_base + (size_t)s * a.in_stride;
         OUT* out_t = (OUT*)(out_base + (size_t)o * a.out_stride);
-        int32_t* bad = badtag + o * R;
+        int32_t* bad = badtag + ob * R;
         const int tag = it + 1;
 
         mbar_wait(&mbar[s], ph);
@@ -131,21 +124,51 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
         }
 
         if (active) {
+            // one tight loop per source kind: the slot (and so the kind) is fixed per thread, rows are strided by rp
             for (int d = d0; d < n_out; d += dstep) {
                 const b200flow_slot sl = plan_sh[d];
-                for (int r = r0; r < rows; r += rp) {
-                    const uint8_t* rowp = in_t + r * row_bytes;
-                    double v;
-                    if (sl.kind <= B200FLOW_SRC_I32) {
-                        v = enc_read_field(rowp, sl.kind, sl.src_off);
-                        if (a.check_nan && v != v) bad[r] = tag;
+                const uint8_t* p = in_t + r0 * row_bytes + sl.src_off;
+                OUT* op = out_t + r0 * n_out + d;
+                const int pstep = rp * row_bytes, ostep = rp * n_out;
+                const bool ident = sl.mean == 0.0 && sl.scale == 1.0;
+                const double mean = sl.mean, scale = sl.scale;
+                if (sl.kind == B200FLOW_SRC_F32) {
+                    if (ident && sizeof(OUT) == 4 && !a.check_nan) {
+#pragma unroll 4
+                        for (int r = r0; r < rows; r += rp, p += pstep, op += ostep) *(uint32_t*)op = *(const uint32_t*)p;   // assemble = move
                     } else {
-                        int code = *(const int32_t*)(rowp + sl.src_off);
-                        int rank = (code >= 0 && code < sl.lut_len) ? lut[sl.lut_off + code] : -1;
-                        if (rank < 0) bad[r] = tag;
-                        v = (sl.kind == B200FLOW_SRC_INDEX) ? (double)rank : (rank == sl.hot ? 1.0 : 0.0);
+#pragma unroll 4
+                        for (int r = r0; r < rows; r += rp, p += pstep, op += ostep) {
+                            const double v = (double)(*(const float*)p);
+                            if (a.check_nan && v != v) bad[r] = tag;
+                            *op = ident ? (OUT)v : (OUT)((v - mean) * scale);
+                        }
                     }
-                    out_t[r * n_out + d] = (OUT)((v - sl.mean) * sl.scale);
+                } else if (sl.kind == B200FLOW_SRC_F64) {
+#pragma unroll 4
+                    for (int r = r0; r < rows; r += rp, p += pstep, op += ostep) {
+                        const uint32_t* q = (const uint32_t*)p;              // 4-byte aligned reads: fields need not be 8-aligned
+                        const double v = __hiloint2double((int)q[1], (int)q[0]);
+                        if (a.check_nan && v != v) bad[r] = tag;
+                        *op = ident ? (OUT)v : (OUT)((v - mean) * scale);
+                    }
+                } else if (sl.kind == B200FLOW_SRC_I32) {
+#pragma unroll 4
+                    for (int r = r0; r < rows; r += rp, p += pstep, op += ostep) {
+                        const double v = (double)(*(const int32_t*)p);
+                        *op = ident ? (OUT)v : (OUT)((v - mean) * scale);
+                    }
+                } else {
+                    const int32_t* lt = lut + sl.lut_off;
+                    const bool index = sl.kind == B200FLOW_SRC_INDEX;
+                    const OUT hot = (OUT)((1.0 - mean) * scale), cold = (OUT)((0.0 - mean) * scale);
+#pragma unroll 4
+                    for (int r = r0; r < rows; r += rp, p += pstep, op += ostep) {
+                        const int code = *(const int32_t*)p;
+                        const int rank = (code >= 0 && code < sl.lut_len) ? lt[code] : -1;
+                        if (rank < 0) bad[r] = tag;
+                        *op = index ? (OUT)(((double)rank - mean) * scale) : (rank == sl.hot ? hot : cold);
+                    }
                 }
             }
         }
@@ -163,20 +186,19 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
                 if (a.label_out) a.label_out[row_base + r] = rank;
             }
         }
+        if (tid == 0) bulk_wait_read<1>();           // all but the latest store have drained: the next tile's out buffer is free
         fence_proxy_async();
-        __syncthreads();                            // A: tile computed, input stage s consumed
+        __syncthreads();                            // the only barrier per tile: tile computed, input stage s consumed
         if (tid == 0) {
             if (full) { bulk_s2g((OUT*)a.out + row_base * n_out, out_t, tile_out_bytes); bulk_commit(); }
             int64_t next = tile + (int64_t)kEncStages * gridDim.x;
             if (next < n_tiles) issue_load(next, s);
-            bulk_wait_read<1>();                    // the store issued one tile ago has drained its buffer
         }
         if (!full) {
             OUT* dst = (OUT*)a.out + row_base * n_out;
             for (int i = tid; i < rows * n_out; i += bd) dst[i] = out_t[i];
         }
         if (a.valid_out) for (int r = tid; r < rows; r += bd) a.valid_out[row_base + r] = (bad[r] != tag) ? 1 : 0;
-        __syncthreads();                            // B: out buffer (o^1) and badtag reusable
     }
     if (tid == 0) bulk_wait_all<0>();
 }
@@ -246,7 +268,7 @@ extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_
     a.out = out; a.label_out = label_out; a.valid_out = valid_out;
     // tile rows: keep one CTA near 52 KB of smem so four CTAs share an SM (>= 64 KB of loads in flight per SM)
     const int fixed_bytes = kEncStages * 8 + n_out * (int)sizeof(b200flow_slot) + (a.lut_in_smem ? a.lut_total * 4 : 0) + 1024;
-    const int per_row = row_bytes * kEncStages + n_out * osz * 2 + 8;
+    const int per_row = row_bytes * kEncStages + n_out * osz * kEncOutBufs + 8;
     int budget = 52 * 1024 - fixed_bytes;
     int R = budget > 0 ? budget / per_row : 0;
     if (R < 4) R = 4;                    // very wide rows: fewer CTAs per SM
@@ -256,7 +278,7 @@ extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_
     a.R = R;
     a.in_stride = (R * row_bytes + 127) & ~127;
     a.out_stride = (R * n_out * osz + 127) & ~127;
-    size_t smem = (size_t)kEncStages * a.in_stride + 2 * (size_t)a.out_stride + kEncStages * 8 + (2 * R + 2) * 4 +
+    size_t smem = (size_t)kEncStages * a.in_stride + kEncOutBufs * (size_t)a.out_stride + kEncStages * 8 + (2 * R + 2) * 4 +
                   (size_t)n_out * sizeof(b200flow_slot) + (a.lut_in_smem ? (size_t)a.lut_total * 4 : 0) + 16;
     B2F_REQUIRE(smem <= 227 * 1024, "encode: record too wide for shared memory (row_bytes=%d n_out=%d)", row_bytes, n_out);
     const int64_t n_tiles = (n_rows + R - 1) / R;
