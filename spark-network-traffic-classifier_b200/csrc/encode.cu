@@ -10,6 +10,8 @@
 //   threads: one fixed OUTPUT slot per thread, rows strided -> smem out tile [R x n_out] (bank-conflict free)
 //   smem out tile --cp.async.bulk store (bulk_group)--> HBM, triple buffered; ONE __syncthreads per tile
 // Arithmetic is fp64 ((v - mean) * scale, no FMA contraction) and rounded once to the output type.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200flow {
@@ -52,6 +54,7 @@ struct EncodeArgs {
 constexpr int kEncStages = 3;     // TMA load ring depth
 constexpr int kEncOutBufs = 3;    // output tiles: two bulk stores may be in flight while the third tile is computed
 constexpr int kEncThreads = 256;
+constexpr int kEncMaxCat = 8;     // distinct categorical sources whose rank is shared through shared memory
 
 template <typename OUT>
 __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a) {
@@ -62,7 +65,12 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
     uint64_t* mbar = (uint64_t*)(out_base + kEncOutBufs * (size_t)a.out_stride);
     int32_t* badtag = (int32_t*)(mbar + kEncStages);
     b200flow_slot* plan_sh = (b200flow_slot*)(badtag + 2 * a.R + ((2 * a.R) & 1));   // keep 8-byte alignment
-    int32_t* lut_sh = (int32_t*)(plan_sh + a.n_out);
+    int32_t* cat_tab = (int32_t*)(plan_sh + a.n_out);          // [3][kEncMaxCat + 1]: field offset, LUT offset, LUT length
+    int32_t* rank_sh = cat_tab + 3 * (kEncMaxCat + 1);         // [R][kEncMaxCat]: StringIndexer rank per (row, categorical source)
+    int16_t* slot_cat = (int16_t*)(rank_sh + a.R * kEncMaxCat);   // [n_out]: categorical source of a slot, -1 numeric, -2 inline
+    int16_t* slot_rep = slot_cat + a.n_out + (a.n_out & 1);
+    int32_t* lut_sh = (int32_t*)(slot_rep + a.n_out + (a.n_out & 1));
+    __shared__ int sh_ncat;
 
     const int tid = threadIdx.x, bd = blockDim.x;
     const int R = a.R, n_out = a.n_out, row_bytes = a.row_bytes;
@@ -79,6 +87,47 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
     for (int i = tid; i < 2 * R; i += bd) badtag[i] = 0;
     __syncthreads();
     const int32_t* lut = a.lut_in_smem ? lut_sh : a.lut;
+    // distinct categorical sources (field, LUT): the code -> rank lookup is done ONCE per (row, source) in a pre-pass, not
+    // once per one-hot slot (70 slots share KDD's `service` lookup)
+    for (int d = tid; d < n_out; d += bd) {
+        int rep = -1;
+        if (plan_sh[d].kind >= B200FLOW_SRC_INDEX) {
+            rep = d;
+            if (n_out <= 1024)
+                for (int e = 0; e < d; ++e)
+                    if (plan_sh[e].kind >= B200FLOW_SRC_INDEX && plan_sh[e].src_off == plan_sh[d].src_off &&
+                        plan_sh[e].lut_off == plan_sh[d].lut_off && plan_sh[e].lut_len == plan_sh[d].lut_len) { rep = e; break; }
+        }
+        slot_rep[d] = (int16_t)rep;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nc = 0;
+        for (int d = 0; d < n_out; ++d) {
+            int id = -1;
+            if (slot_rep[d] == d) {
+                if (nc < kEncMaxCat && n_out <= 1024) {
+                    id = nc; cat_tab[nc] = plan_sh[d].src_off; cat_tab[(kEncMaxCat + 1) + nc] = plan_sh[d].lut_off;
+                    cat_tab[2 * (kEncMaxCat + 1) + nc] = plan_sh[d].lut_len; ++nc;
+                } else id = -2;
+            }
+            slot_cat[d] = (int16_t)id;
+        }
+        int n_cat_slots = 0;
+        for (int d = 0; d < n_out; ++d) n_cat_slots += slot_rep[d] >= 0 ? 1 : 0;
+        if (n_cat_slots < 3 * nc) {                          // few slots per source (plain StringIndexer columns): the shared
+            nc = 0;                                          // pre-pass and its barrier cost more than the inline lookups
+            for (int d = 0; d < n_out; ++d) if (slot_rep[d] >= 0) slot_cat[d] = -2;
+        }
+        if (a.label_off >= 0) {                              // the label column is one more source (index nc)
+            cat_tab[nc] = a.label_off; cat_tab[(kEncMaxCat + 1) + nc] = a.label_lut_off; cat_tab[2 * (kEncMaxCat + 1) + nc] = a.label_lut_len;
+        }
+        sh_ncat = nc;
+    }
+    __syncthreads();
+    for (int d = tid; d < n_out; d += bd) { const int rep = slot_rep[d]; if (rep >= 0 && rep != d) slot_cat[d] = slot_cat[rep]; }
+    __syncthreads();
+    const int ncat = sh_ncat, nsrc = ncat + (a.label_off >= 0 ? 1 : 0);
 
     auto issue_load = [&](int64_t tile, int s) {
         int64_t rows = a.n_rows - tile * R;
@@ -123,6 +172,17 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
             __syncthreads();
         }
 
+        if (nsrc > 0) {
+            for (int idx = tid; idx < rows * nsrc; idx += bd) {
+                const int r = idx / nsrc, c = idx - r * nsrc;
+                const int code = *(const int32_t*)(in_t + r * row_bytes + cat_tab[c]);
+                const int rank = (code >= 0 && code < cat_tab[2 * (kEncMaxCat + 1) + c]) ? lut[cat_tab[(kEncMaxCat + 1) + c] + code] : -1;
+                if (rank < 0) bad[r] = tag;
+                if (c < ncat) rank_sh[r * kEncMaxCat + c] = rank;
+                else if (a.label_out) a.label_out[row_base + r] = rank;
+            }
+            if (ncat > 0) __syncthreads();          // ranks visible to the slot loops (label-only: nothing to wait for)
+        }
         if (active) {
             // one tight loop per source kind: the slot (and so the kind) is fixed per thread, rows are strided by rp
             for (int d = d0; d < n_out; d += dstep) {
@@ -159,31 +219,30 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
                         *op = ident ? (OUT)v : (OUT)((v - mean) * scale);
                     }
                 } else {
-                    const int32_t* lt = lut + sl.lut_off;
                     const bool index = sl.kind == B200FLOW_SRC_INDEX;
                     const OUT hot = (OUT)((1.0 - mean) * scale), cold = (OUT)((0.0 - mean) * scale);
+                    const int cat = slot_cat[d];
+                    if (cat >= 0) {                  // rank looked up once per (row, source) by the pre-pass
+                        const int32_t* rk = rank_sh + r0 * kEncMaxCat + cat;
+                        const int rstep = rp * kEncMaxCat;
+                        if (index) {
 #pragma unroll 4
-                    for (int r = r0; r < rows; r += rp, p += pstep, op += ostep) {
-                        const int code = *(const int32_t*)p;
-                        const int rank = (code >= 0 && code < sl.lut_len) ? lt[code] : -1;
-                        if (rank < 0) bad[r] = tag;
-                        *op = index ? (OUT)(((double)rank - mean) * scale) : (rank == sl.hot ? hot : cold);
+                            for (int r = r0; r < rows; r += rp, rk += rstep, op += ostep) *op = (OUT)(((double)*rk - mean) * scale);
+                        } else {
+                            const int hotrank = sl.hot;
+#pragma unroll 4
+                            for (int r = r0; r < rows; r += rp, rk += rstep, op += ostep) *op = (*rk == hotrank) ? hot : cold;
+                        }
+                    } else {                         // more than kEncMaxCat distinct sources: inline lookup
+                        const int32_t* lt = lut + sl.lut_off;
+                        for (int r = r0; r < rows; r += rp, p += pstep, op += ostep) {
+                            const int code = *(const int32_t*)p;
+                            const int rank = (code >= 0 && code < sl.lut_len) ? lt[code] : -1;
+                            if (rank < 0) bad[r] = tag;
+                            *op = index ? (OUT)(((double)rank - mean) * scale) : (rank == sl.hot ? hot : cold);
+                        }
                     }
                 }
-            }
-        }
-        if (a.label_off >= 0 && tid < rows) {      // label column: one thread per row, straight to HBM
-            int code = *(const int32_t*)(in_t + tid * row_bytes + a.label_off);
-            int rank = (code >= 0 && code < a.label_lut_len) ? lut[a.label_lut_off + code] : -1;
-            if (rank < 0) bad[tid] = tag;
-            if (a.label_out) a.label_out[row_base + tid] = rank;
-        }
-        if (a.label_off >= 0 && bd < rows) {       // R > blockDim: remaining rows
-            for (int r = tid + bd; r < rows; r += bd) {
-                int code = *(const int32_t*)(in_t + r * row_bytes + a.label_off);
-                int rank = (code >= 0 && code < a.label_lut_len) ? lut[a.label_lut_off + code] : -1;
-                if (rank < 0) bad[r] = tag;
-                if (a.label_out) a.label_out[row_base + r] = rank;
             }
         }
         if (tid == 0) bulk_wait_read<1>();           // all but the latest store have drained: the next tile's out buffer is free
@@ -267,9 +326,12 @@ extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_
     a.label_off = label_off; a.label_lut_off = label_lut_off; a.label_lut_len = label_lut_len; a.check_nan = check_nan;
     a.out = out; a.label_out = label_out; a.valid_out = valid_out;
     // tile rows: keep one CTA near 52 KB of smem so four CTAs share an SM (>= 64 KB of loads in flight per SM)
-    const int fixed_bytes = kEncStages * 8 + n_out * (int)sizeof(b200flow_slot) + (a.lut_in_smem ? a.lut_total * 4 : 0) + 1024;
-    const int per_row = row_bytes * kEncStages + n_out * osz * kEncOutBufs + 8;
-    int budget = 52 * 1024 - fixed_bytes;
+    const int fixed_bytes = kEncStages * 8 + n_out * (int)sizeof(b200flow_slot) + (a.lut_in_smem ? a.lut_total * 4 : 0) + 1024 +
+                            3 * (kEncMaxCat + 1) * 4 + 4 * (n_out + 1);
+    const int per_row = row_bytes * kEncStages + n_out * osz * kEncOutBufs + 8 + kEncMaxCat * 4;
+    static int budget_kb = -1;                             // tuning knob: per-CTA shared memory target
+    if (budget_kb < 0) { const char* e = getenv("B200FLOW_ENC_SMEM_KB"); budget_kb = e ? atoi(e) : 52; }
+    int budget = budget_kb * 1024 - fixed_bytes;
     int R = budget > 0 ? budget / per_row : 0;
     if (R < 4) R = 4;                    // very wide rows: fewer CTAs per SM
     if (R > 512) R = 512;
@@ -279,7 +341,8 @@ extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_
     a.in_stride = (R * row_bytes + 127) & ~127;
     a.out_stride = (R * n_out * osz + 127) & ~127;
     size_t smem = (size_t)kEncStages * a.in_stride + kEncOutBufs * (size_t)a.out_stride + kEncStages * 8 + (2 * R + 2) * 4 +
-                  (size_t)n_out * sizeof(b200flow_slot) + (a.lut_in_smem ? (size_t)a.lut_total * 4 : 0) + 16;
+                  (size_t)n_out * sizeof(b200flow_slot) + (a.lut_in_smem ? (size_t)a.lut_total * 4 : 0) + 16 +
+                  3 * (kEncMaxCat + 1) * 4 + (size_t)R * kEncMaxCat * 4 + 4 * ((size_t)n_out + 1);
     B2F_REQUIRE(smem <= 227 * 1024, "encode: record too wide for shared memory (row_bytes=%d n_out=%d)", row_bytes, n_out);
     const int64_t n_tiles = (n_rows + R - 1) / R;
     int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
