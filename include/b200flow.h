@@ -200,9 +200,9 @@ typedef struct b200flow_node {
  * two children per split (counts from left/right_counts), and emits the next level's slots for
  * the non-leaf children (next_* arrays, capacity 2*n_slots; next_parent = parent slot*2+side;
  * child_slot[2*s+side] = index of that child among the next slots, -1 when it is a leaf; may be NULL).
- * counters: int64[4] {node pool size (in/out), number of next slots (out), overflow flag (out: 1 =
- * pool_capacity too small, nothing written), pool size before the call} followed by
- * 2*ceil(n_slots/256) int32 of scratch. */
+ * counters: int64[8] header {node pool size (in/out), number of next slots (out), overflow flag (out: 1 =
+ * pool_capacity too small, nothing written), pool size before the call, 4 entries free for the caller}
+ * followed by 2*ceil(n_slots/256) int32 of scratch. */
 int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, const uint32_t* slot_nid,
                         const int32_t* slot_node, const b200flow_split* split,
                         const uint32_t* node_counts, const uint32_t* left_counts,

@@ -352,19 +352,24 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         call("b200flow_feature_subsets", seed, ns, ptr(s_tree), ptr(s_nid), F, m, ptr(sub))
         return sub
 
-    def route_and_hist(routed, lens_, split_, child_slot_, cursors_, next_subset_, n_next_):
-        """fused pass: route the entries of the `routed` parent slots to their children and build the children's
-        histograms (returns the zero-initialised, now filled, histogram buffer of the next level)."""
+    def plan_route(routed, lens_, total_out):
+        """enqueue the chunk table of a fused routing pass; the chunk count lands in the device scalar `total_out`."""
         nch = torch.where(routed, (lens_ + (route_ch - 1)) // route_ch, torch.zeros_like(lens_)).to(torch.int32).contiguous()
-        roff, rch = chunk_table(nch)
+        roff = torch.empty(nch.shape[0] + 1, dtype=torch.int64, device=dev)
+        call("b200flow_exclusive_scan_i32_to_i64", ptr(nch), nch.shape[0], ptr(roff), ptr(total_out))
+        if PROFILE is not None:
+            PROFILE.setdefault("_route_entries", []).append(torch.where(routed, lens_, torch.zeros_like(lens_)).sum())
+        return roff
+
+    def run_route(roff, rch, n_parents, split_, child_slot_, cursors_, next_subset_, n_next_):
+        """fused pass: route the entries of the planned parent slots to their children and build the children's
+        histograms (returns the zero-initialised, now filled, histogram buffer of the next level)."""
         hist_next = torch.zeros(n_next_ * hsz, dtype=torch.int32, device=dev)
         scratch = torch.empty(max(rch, 1) * 4, dtype=torch.int32, device=dev)
-        _timed("route_hist_level", "b200flow_route_hist_level", ptr(tp), stride, F, ptr(ent), ptr(ent2), lens_.shape[0],
+        _timed("route_hist_level", "b200flow_route_hist_level", ptr(tp), stride, F, ptr(ent), ptr(ent2), n_parents,
                ptr(seg_begin), ptr(seg_end), ptr(roff), rch, route_ch, ptr(split_), ptr(child_slot_), ptr(cursors_), ptr(scratch),
                ptr(next_subset_), m, n_bins, C, ptr(hist_next))
         stats["hist_launches"] += 1
-        if PROFILE is not None:
-            PROFILE.setdefault("_route_entries", []).append(torch.where(routed, lens_, torch.zeros_like(lens_)).sum())
         return hist_next
 
     subset = level_subsets(n_slots, slot_tree, slot_nid)
@@ -376,8 +381,8 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         child0 = torch.stack([torch.arange(T, dtype=torch.int32, device=dev),
                               torch.full((T,), -1, dtype=torch.int32, device=dev)], 1).contiguous().view(-1)
         cursors0 = torch.zeros(2 * T, dtype=torch.int32, device=dev)
-        hist_ready = route_and_hist(torch.ones(T, dtype=torch.bool, device=dev), seg_end - seg_begin, pseudo_t, child0,
-                                    cursors0, subset, T)
+        roff0 = plan_route(torch.ones(T, dtype=torch.bool, device=dev), seg_end - seg_begin, total)
+        hist_ready = run_route(roff0, int(total.item()), T, pseudo_t, child0, cursors0, subset, T)
         ent, ent2 = ent2, ent          # the pass copied every entry into the other buffer, same segments
     while n_slots > 0:
         grow_pool(pool_size + 2 * n_slots)
@@ -419,7 +424,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         hist_ready = None
         # grow the pool by this level's children and emit the next level's slots
         nblk = (n_slots + 255) // 256
-        counters = torch.zeros(4 + nblk + 1, dtype=torch.int64, device=dev)
+        counters = torch.zeros(8 + nblk + 1, dtype=torch.int64, device=dev)   # [pool, n_next, overflow, pool_before, route chunks, ...]
         counters[0] = pool_size
         next_tree = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_nid = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
@@ -430,7 +435,12 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                ptr(left_counts), ptr(right_counts), C, ptr(nodes), ptr(node_mask), ptr(pool_counts), ptr(node_tree),
                cap_nodes, ptr(next_tree), ptr(next_nid), ptr(next_node), ptr(next_parent), ptr(child_slot), ptr(counters))
         node_gain[slot_node.long()] = split.view(torch.float64)[:, 2]
-        cnt = counters[:3].cpu()
+        roff = None
+        if fused:                                       # plan the routing pass before the level's only host sync
+            flags = split.view(torch.int32)[:, 3]
+            routed = ((flags & 1) == 0) & ((flags & 6) != 6)          # split parents with at least one non-leaf child
+            roff = plan_route(routed, lens, counters[4:5])
+        cnt = counters[:5].cpu()
         if int(cnt[2]) != 0:
             raise B200FlowError("node pool overflow (capacity %d)" % cap_nodes)
         pool_size, n_next = int(cnt[0]), int(cnt[1])
@@ -442,9 +452,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
         if fused and n_next * hsz * 4 <= HIST_BUDGET_BYTES:
             # route every entry to its child AND build the children's histograms in the same pass
-            flags = split.view(torch.int32)[:, 3]
-            routed = ((flags & 1) == 0) & ((flags & 6) != 6)          # split parents with at least one non-leaf child
-            hist_ready = route_and_hist(routed, lens, split, child_slot, cursors, next_subset, n_next)
+            hist_ready = run_route(roff, int(cnt[4]), n_slots, split, child_slot, cursors, next_subset, n_next)
         else:
             if chunk_off is None:
                 nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()

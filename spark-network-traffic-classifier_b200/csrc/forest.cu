@@ -748,10 +748,10 @@ extern "C" int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, co
     B2F_REQUIRE(slot_tree && slot_nid && slot_node && split && node_counts && left_counts && right_counts && nodes && pool_counts &&
                     node_tree && next_tree && next_nid && next_node && next_parent && counters, "grow_level: null pointer");
     if (n_slots <= 0) return B200FLOW_OK;
-    // counters: int64[4] {pool size, n_next, overflow flag, pool size before the level} followed by the
-    // int32 scratch for the per-block counts (2 * ceil(n_slots/256) ints), all caller-owned.
+    // counters: int64[8] header {pool size, n_next, overflow flag, pool size before the level, 4 free for the caller}
+    // followed by the int32 scratch for the per-block counts (2 * ceil(n_slots/256) ints), all caller-owned.
     const int nb = (n_slots + kGrowBlock - 1) / kGrowBlock;
-    int32_t* blk = (int32_t*)(counters + 4);
+    int32_t* blk = (int32_t*)(counters + 8);
     grow_count_kernel<<<nb, kGrowBlock, 0, (cudaStream_t)stream>>>(n_slots, split, blk);
     grow_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nb, blk, counters, pool_capacity);
     grow_write_kernel<<<nb, kGrowBlock, 0, (cudaStream_t)stream>>>(n_slots, slot_tree, slot_nid, slot_node, split, node_counts, left_counts,
