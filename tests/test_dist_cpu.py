@@ -1,0 +1,63 @@
+"""Host-side logic of the row-sharded (multi-GPU) path, exercised with 2 CPU processes over gloo:
+block partition, global row offsets, integer all-reduce of per-shard histograms == unsharded histogram,
+and shard-independent RNG streams (bagging weights / randomSplit ids are slices of the global stream)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from b200flow import dist as bdist
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert bdist.group() is not None
+        n, F, C, NB, m = 10007, 12, 3, 16, 4
+        rng = np.random.default_rng(0)                      # same global data in every rank
+        tp = rng.integers(0, NB, size=(n, 16), dtype=np.uint8); tp[:, F] = rng.integers(0, C, n)
+        lo, hi = bdist.shard_bounds(n, rank, world)
+        off, tot = bdist.global_offset(hi - lo, torch.device("cpu"))
+        assert (off, tot) == (lo, n)
+        cdf = oracle.poisson_cdf_table(1.0)
+        w_local = oracle.bag_weights(99, 3, hi - lo, cdf, row_offset=off)          # counter RNG keyed by GLOBAL row
+        w_full = oracle.bag_weights(99, 3, n, cdf)
+        assert np.array_equal(w_local, w_full[:, lo:hi])
+        sid = oracle.random_split(2019, hi - lo, [0.75, 1.0], row_offset=off)
+        assert np.array_equal(sid, oracle.random_split(2019, n, [0.75, 1.0])[lo:hi])
+        subset = oracle.feature_subset(5, 1, 7, F, m)
+        rows = np.nonzero(w_local[1])[0].astype(np.int32)
+        h = oracle.hist_node(tp[lo:hi], F, rows, w_local[1][rows], subset, NB, C)
+        ht = torch.from_numpy(h.astype(np.int32))
+        bdist.all_reduce_sum_(ht)                                                    # R7r: the per-level collective
+        rows_f = np.nonzero(w_full[1])[0].astype(np.int32)
+        want = oracle.hist_node(tp, F, rows_f, w_full[1][rows_f], subset, NB, C)
+        assert np.array_equal(ht.numpy().astype(np.int64), want)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 1000, 4898431):
+        for world in (1, 2, 3, 8):
+            b = [bdist.shard_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+    assert bdist.group() is None and bdist.global_offset(5, torch.device("cpu")) == (0, 5)

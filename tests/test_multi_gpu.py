@@ -1,0 +1,65 @@
+"""Real multi-GPU check (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`):
+rows sharded over 2 ranks + NCCL all-reduce of the level histograms must reproduce the 1-GPU forest byte for byte."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from b200flow import dist as bdist, encode as enc, forest as fr, synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dev = torch.device("cuda", rank)
+        n = 60000
+        rec, dicts = synth.make_kdd(n, 5, seed=17, device=dev)              # identical global data in both ranks
+        schema = synth.kdd_schema()
+        lo, hi = bdist.shard_bounds(n, rank, world)
+        shard = rec[lo:hi].contiguous()
+        luts, ordered = {}, {}
+        for c in synth.KDD_CATEGORICAL + ["label"]:
+            cnt = bdist.all_reduce_sum_(enc.category_counts(shard, schema, c, len(dicts[c]))).cpu().numpy()
+            ordered[c], luts[c] = enc.string_index_order(cnt, dicts[c])
+        plan = enc.EncodePlan(schema)
+        for c in synth.KDD_COLUMNS:
+            if c not in synth.KDD_CATEGORICAL and c != "label":
+                plan.add_numeric(c)
+        for c in synth.KDD_CATEGORICAL:
+            plan.add_index(c, luts[c])
+        plan.set_label("label", luts["label"])
+        x, y, _ = plan.run(shard, torch.float64)
+        arity = [0] * 38 + [len(ordered[c]) for c in synth.KDD_CATEGORICAL]
+        p = fr.ForestParams(num_trees=8, max_bins=70, max_depth=10, seed=2019)
+        off, _ = bdist.global_offset(hi - lo, dev)
+        model = fr.fit_forest(x, y, len(ordered["label"]), arity, p, row_offset=off, group=bdist.group())
+        ex = model.export()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "sharded.npz"), **ex)
+            xf, yf, _ = plan.run(rec, torch.float64)
+            single = fr.fit_forest(xf, yf, len(ordered["label"]), arity, p).export()
+            np.savez(os.path.join(out_dir, "single.npz"), **single)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_forest_is_byte_identical_to_one_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "sharded.npz"), np.load(tmp_path / "single.npz")
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k
+    assert len(a["nid"]) > 500
