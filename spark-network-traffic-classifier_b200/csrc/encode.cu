@@ -299,9 +299,9 @@ using namespace b200flow;
 
 extern "C" int b200flow_category_counts(const void* records, int64_t n_rows, int32_t row_bytes, int32_t src_off,
                                         int32_t K, int64_t* counts, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(records && counts && K > 0 && row_bytes >= 4 && src_off >= 0 && src_off + 4 <= row_bytes && (src_off & 3) == 0 &&
                     (row_bytes & 3) == 0, "category_counts: bad arguments");
-    if (n_rows <= 0) return B200FLOW_OK;
     int use_smem = K <= 8192;
     int grid = grid_for(n_rows, 256 * 8, kNumSMs * 8);
     category_counts_kernel<<<grid, 256, use_smem ? K * 4 : 0, (cudaStream_t)stream>>>(
@@ -313,12 +313,12 @@ extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_
                                int32_t n_out, const int32_t* lut, int32_t lut_total, int32_t label_off,
                                int32_t label_lut_off, int32_t label_lut_len, int32_t check_nan, void* out,
                                int32_t out_dtype, int32_t* label_out, uint8_t* valid_out, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(records && plan && out, "encode: null pointer");
     B2F_REQUIRE(n_out > 0 && n_out <= 4096 && row_bytes >= 4 && (row_bytes & 3) == 0, "encode: bad n_out/row_bytes");
     B2F_REQUIRE(out_dtype == B200FLOW_F32 || out_dtype == B200FLOW_F64, "encode: bad out_dtype");
     B2F_REQUIRE(((uintptr_t)records & 15) == 0 && ((uintptr_t)out & 15) == 0, "encode: records/out must be 16-byte aligned");
     B2F_REQUIRE(label_off < 0 || (label_off + 4 <= row_bytes && (label_off & 3) == 0 && lut), "encode: bad label_off");
-    if (n_rows <= 0) return B200FLOW_OK;
     const int osz = out_dtype == B200FLOW_F32 ? 4 : 8;
     EncodeArgs a;
     a.records = (const uint8_t*)records; a.n_rows = n_rows; a.row_bytes = row_bytes; a.plan = plan; a.n_out = n_out;
@@ -363,9 +363,9 @@ extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_
 
 extern "C" int b200flow_column_moments(const void* x, int32_t dtype, int64_t n_rows, int32_t D, int64_t ld,
                                        const double* shift, double* sum, double* sumsq, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(x && sum && sumsq && D > 0 && ld >= D, "column_moments: bad arguments");
     B2F_REQUIRE(dtype == B200FLOW_F32 || dtype == B200FLOW_F64, "column_moments: bad dtype");
-    if (n_rows <= 0) return B200FLOW_OK;
     int grid = grid_for(n_rows, 256, kNumSMs * 4);
     size_t smem = 2 * 256 * sizeof(double);
     if (dtype == B200FLOW_F32)

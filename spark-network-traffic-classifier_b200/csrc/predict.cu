@@ -139,10 +139,10 @@ using namespace b200flow;
 extern "C" int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_rows, const b200flow_node* nodes,
                                 const uint64_t* node_mask, const double* leaf_prob, const uint32_t* pool_counts, int32_t T,
                                 int32_t C, int32_t dt_mode, double* raw, double* prob, double* pred, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(tp && nodes && pred && T > 0 && C > 0 && (tp_stride & 15) == 0, "predict: bad arguments");
     B2F_REQUIRE(dt_mode ? pool_counts != nullptr : leaf_prob != nullptr, "predict: missing leaf payload");
     B2F_REQUIRE(((uintptr_t)tp & 15) == 0, "predict: tp must be 16-byte aligned");
-    if (n_rows <= 0) return B200FLOW_OK;
     int bd = 128;
     size_t per_thread = (size_t)tp_stride + (size_t)C * 8;
     while (bd > 32 && per_thread * bd > 96 * 1024) bd >>= 1;
@@ -157,8 +157,8 @@ extern "C" int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_
 }
 
 extern "C" int b200flow_confusion(const double* pred, const double* label, int64_t n_rows, int32_t C, int64_t* cm, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(pred && label && cm && C > 0 && C <= 1024, "confusion: bad arguments");
-    if (n_rows <= 0) return B200FLOW_OK;
     int use_smem = (size_t)C * C * 4 <= 64 * 1024;
     size_t smem = use_smem ? (size_t)C * C * 4 : 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(confusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -169,8 +169,8 @@ extern "C" int b200flow_confusion(const double* pred, const double* label, int64
 
 extern "C" int b200flow_random_split(uint64_t seed, int64_t row_offset, int64_t n_rows, const double* cum_bounds_host,
                                      int32_t n_splits, uint8_t* split_id, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(cum_bounds_host && split_id && n_splits >= 1 && n_splits <= 8, "random_split: bad arguments");
-    if (n_rows <= 0) return B200FLOW_OK;
     SplitBounds b; b.n = n_splits;
     for (int i = 0; i < 8; ++i) b.cum[i] = i < n_splits ? cum_bounds_host[i] : 2.0;
     int grid = grid_for(n_rows, 256 * 4, kNumSMs * 8);

@@ -219,8 +219,8 @@ extern "C" int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, 
 extern "C" int b200flow_sample_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, int64_t ld, uint64_t seed,
                                     uint64_t keep_threshold, int64_t row_offset, double* sample, int64_t cap,
                                     int32_t* n_sampled, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(x && sample && n_sampled && F > 0 && ld >= F && cap > 0, "sample_rows: bad arguments");
-    if (n_rows <= 0) return B200FLOW_OK;
     int grid = grid_for(n_rows, 256 * 4, kNumSMs * 8);
     if (dtype == B200FLOW_F32)
         sample_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, n_rows, F, ld, seed, keep_threshold, row_offset, sample, cap, n_sampled);
@@ -243,11 +243,11 @@ extern "C" int b200flow_find_splits(double* sample, int64_t cap, int32_t n_s, in
 extern "C" int b200flow_bin_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, int64_t ld,
                                  const double* thresholds, const int32_t* n_thr, const int32_t* arity, int32_t max_bins,
                                  const int32_t* labels, uint8_t* tp, int32_t tp_stride, int32_t* bad_rows, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(x && thresholds && n_thr && arity && tp && bad_rows, "bin_rows: null pointer");
     B2F_REQUIRE(F > 0 && F < 65536 && ld >= F && tp_stride >= F + 1 && (tp_stride & 15) == 0 && max_bins >= 2 && max_bins <= 256,
                 "bin_rows: bad shape (F=%d stride=%d max_bins=%d)", F, tp_stride, max_bins);
     B2F_REQUIRE(((uintptr_t)tp & 15) == 0, "bin_rows: tp must be 16-byte aligned");
-    if (n_rows <= 0) return B200FLOW_OK;
     size_t thr_bytes = (size_t)F * (max_bins - 1) * 8;
     int thr_in_smem = thr_bytes <= 96 * 1024;
     int R = 4096 / tp_stride; if (R < 8) R = 8; if (R > 128) R = 128;
