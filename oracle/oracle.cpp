@@ -397,16 +397,17 @@ void orc_bin_rows(const double* x, int64_t n, int32_t F, const double* threshold
     if (bad_rows) *bad_rows = bad;
 }
 
-// R6 BaggedPoint (A.4): w[t][i] = #{k : cdf[k] != 2^32-1 and r >= cdf[k]}, r = philox(seed,'BAGG', global row, tree).x
+// R6 BaggedPoint (A.4): w[t][i] = #{k : cdf[k] != 2^32-1 and r >= cdf[k]}, r = word tree%4 of philox(seed,'BAGG', global row, tree/4)
 void orc_bag_weights(uint64_t seed, int32_t T, int64_t row_offset, int64_t n, const uint32_t* cdf, uint8_t* w) {
 #pragma omp parallel for schedule(static)
     for (int t = 0; t < T; ++t)
         for (int64_t i = 0; i < n; ++i) {
             if (!cdf) { w[(size_t)t * n + i] = 1; continue; }
             uint64_t g = (uint64_t)(row_offset + i);
-            U4 r = philox_keyed(seed, PURPOSE_BAG, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)t, 0);
+            U4 r4 = philox_keyed(seed, PURPOSE_BAG, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(t >> 2), 0);   // one call serves 4 trees
+            uint32_t r = (t & 3) == 0 ? r4.x : (t & 3) == 1 ? r4.y : (t & 3) == 2 ? r4.z : r4.w;
             int k = 0;
-            for (int j = 0; j < 32; ++j) k += (cdf[j] != 0xFFFFFFFFu && r.x >= cdf[j]) ? 1 : 0;   // saturated thresholds are unreachable
+            for (int j = 0; j < 32; ++j) k += (cdf[j] != 0xFFFFFFFFu && r >= cdf[j]) ? 1 : 0;   // saturated thresholds are unreachable
             w[(size_t)t * n + i] = (uint8_t)k;
         }
 }

@@ -21,7 +21,7 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in mult
 // ------------------------------------------------------------------ Philox4x32-10
 // Counter-based RNG: key = (lo32(seed) ^ purpose, hi32(seed)).
 constexpr uint32_t PURPOSE_SAMPLE = 0x53414D50u;  // findSplits row sample      ctr = (row_lo,row_hi,0,0)
-constexpr uint32_t PURPOSE_BAG    = 0x42414747u;  // Poisson bagging            ctr = (row_lo,row_hi,tree,0)
+constexpr uint32_t PURPOSE_BAG    = 0x42414747u;  // Poisson bagging            ctr = (row_lo,row_hi,tree/4,0), word tree%4
 constexpr uint32_t PURPOSE_FEAT   = 0x46454154u;  // per-node feature subset    ctr = (tree,nid,draw/4,0)
 constexpr uint32_t PURPOSE_RSPLIT = 0x5253504Cu;  // DataFrame.randomSplit      ctr = (row_lo,row_hi,0,0)
 
@@ -41,13 +41,15 @@ __device__ __forceinline__ uint4 philox_keyed(uint64_t seed, uint32_t purpose, u
     return philox4x32_10((uint32_t)seed ^ purpose, (uint32_t)(seed >> 32), make_uint4(c0, c1, c2, c3));
 }
 
-// Poisson weight by inverse CDF over 32 integer thresholds (NULL table = no bagging)
-__device__ __forceinline__ uint32_t bag_weight(uint64_t seed, int tree, uint64_t grow, const uint32_t* cdf_sh) {
-    uint4 r = philox_keyed(seed, PURPOSE_BAG, (uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)tree, 0u);
+// Poisson weights by inverse CDF over 32 increasing integer thresholds: w = #{k : cdf[k] != 2^32-1 and r >= cdf[k]}.
+// One Philox call serves FOUR trees: counter = (row_lo, row_hi, tree >> 2, 0), word = tree & 3.
+__device__ __forceinline__ uint32_t poisson_weight(uint32_t r, const uint32_t* cdf_sh) {
     uint32_t k = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) k += (cdf_sh[j] != 0xFFFFFFFFu && r.x >= cdf_sh[j]) ? 1u : 0u;   // saturated = unreachable
+    while (k < 32 && cdf_sh[k] != 0xFFFFFFFFu && r >= cdf_sh[k]) ++k;      // thresholds increase: first failure ends the count
     return k;
+}
+__device__ __forceinline__ uint4 bag_draw4(uint64_t seed, int tree_quad, uint64_t grow) {
+    return philox_keyed(seed, PURPOSE_BAG, (uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)tree_quad, 0u);
 }
 
 // bagged entry = row index (27 bits) | bag weight (5 bits): one 32-bit word per (tree, row) pair

@@ -161,49 +161,74 @@ __global__ void __launch_bounds__(256) bin_rows_kernel(const T* __restrict__ x, 
 // ------------------------------------------------------------------ R6 bagging
 constexpr int kBagBlockRows = 1024;
 
-__global__ void __launch_bounds__(256) bag_count_kernel(uint64_t seed, int64_t row_offset, int64_t n,
+// grid = (row blocks of 1024, tree quads).  A thread owns 4 consecutive rows; one Philox call per row yields the weights
+// of the quad's 4 trees.
+__global__ void __launch_bounds__(256) bag_count_kernel(uint64_t seed, int T, int64_t row_offset, int64_t n,
                                                         const uint32_t* __restrict__ cdf, int32_t* blk_cnt, int64_t n_blocks) {
     __shared__ uint32_t cdf_sh[32];
-    __shared__ int cnt_sh;
-    const int t = blockIdx.y;
+    __shared__ int cnt_sh[4];
+    const int tq = blockIdx.y;
     if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
-    if (threadIdx.x == 0) cnt_sh = 0;
+    if (threadIdx.x < 4) cnt_sh[threadIdx.x] = 0;
     __syncthreads();
     const int64_t rb = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
-    int c = 0;
+    int c[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        int64_t i = rb + k;
-        if (i < n) c += (cdf ? bag_weight(seed, t, (uint64_t)(row_offset + i), cdf_sh) : 1u) > 0 ? 1 : 0;
+        const int64_t i = rb + k;
+        if (i < n) {
+            if (cdf) {
+                const uint4 r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
+                c[0] += poisson_weight(r.x, cdf_sh) > 0; c[1] += poisson_weight(r.y, cdf_sh) > 0;
+                c[2] += poisson_weight(r.z, cdf_sh) > 0; c[3] += poisson_weight(r.w, cdf_sh) > 0;
+            } else { c[0]++; c[1]++; c[2]++; c[3]++; }
+        }
     }
-    c = warp_sum(c);
-    if (lane_id() == 0 && c) atomicAdd(&cnt_sh, c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int v = warp_sum(c[q]);
+        if (lane_id() == 0 && v) atomicAdd(&cnt_sh[q], v);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) blk_cnt[(int64_t)t * n_blocks + blockIdx.x] = cnt_sh;
+    if (threadIdx.x < 4 && tq * 4 + threadIdx.x < T) blk_cnt[(int64_t)(tq * 4 + threadIdx.x) * n_blocks + blockIdx.x] = cnt_sh[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(256) bag_fill_kernel(uint64_t seed, int64_t row_offset, int64_t n,
+__global__ void __launch_bounds__(256) bag_fill_kernel(uint64_t seed, int T, int64_t row_offset, int64_t n,
                                                        const uint32_t* __restrict__ cdf, const int64_t* __restrict__ blk_off,
                                                        int64_t n_blocks, uint32_t* ent) {
     __shared__ uint32_t cdf_sh[32];
     __shared__ int sh[33];
-    const int t = blockIdx.y;
+    const int tq = blockIdx.y;
     if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
     __syncthreads();
     const int64_t rb = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
-    uint32_t w[4]; int c = 0;
+    uint32_t w[4][4];                                   // [tree in quad][row]
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        int64_t i = rb + k;
-        w[k] = (i < n) ? (cdf ? bag_weight(seed, t, (uint64_t)(row_offset + i), cdf_sh) : 1u) : 0u;
-        c += w[k] > 0 ? 1 : 0;
+        const int64_t i = rb + k;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        const bool live = i < n;
+        if (live && cdf) r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
+        w[0][k] = live ? (cdf ? poisson_weight(r.x, cdf_sh) : 1u) : 0u;
+        w[1][k] = live ? (cdf ? poisson_weight(r.y, cdf_sh) : 1u) : 0u;
+        w[2][k] = live ? (cdf ? poisson_weight(r.z, cdf_sh) : 1u) : 0u;
+        w[3][k] = live ? (cdf ? poisson_weight(r.w, cdf_sh) : 1u) : 0u;
     }
-    int tot;
-    int ex = block_exclusive_scan(c, sh, &tot);
-    int64_t pos = blk_off[(int64_t)t * n_blocks + blockIdx.x] + ex;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (w[k] > 0) { ent[pos] = ent_pack((uint32_t)(rb + k), min(w[k], 31u)); ++pos; }
+    for (int q = 0; q < 4; ++q) {
+        const int t = tq * 4 + q;                       // uniform per block
+        if (t >= T) break;
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c += w[q][k] > 0 ? 1 : 0;
+        int tot;
+        const int ex = block_exclusive_scan(c, sh, &tot);
+        int64_t pos = blk_off[(int64_t)t * n_blocks + blockIdx.x] + ex;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (w[q][k] > 0) { ent[pos] = ent_pack((uint32_t)(rb + k), min(w[q][k], 31u)); ++pos; }
+        __syncthreads();                                // sh reused by the next tree's scan
+    }
 }
 
 }  // namespace b200flow
@@ -272,7 +297,7 @@ extern "C" int b200flow_bag_count(uint64_t seed, int32_t T, int64_t row_offset, 
     B2F_REQUIRE(blk_cnt && T > 0 && T <= 65535 && n_rows >= 0, "bag_count: bad arguments");
     if (n_rows == 0) return B200FLOW_OK;
     int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
-    bag_count_kernel<<<dim3((unsigned)nb, (unsigned)T), 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n_rows, poisson_cdf, blk_cnt, nb);
+    bag_count_kernel<<<dim3((unsigned)nb, (unsigned)((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, blk_cnt, nb);
     return check_launch("bag_count");
 }
 
@@ -282,6 +307,6 @@ extern "C" int b200flow_bag_fill(uint64_t seed, int32_t T, int64_t row_offset, i
     B2F_REQUIRE(n_rows <= (int64_t)kEntRowMask + 1, "bag_fill: at most 2^27 rows per GPU (row index is packed into 27 bits)");
     if (n_rows == 0) return B200FLOW_OK;
     int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
-    bag_fill_kernel<<<dim3((unsigned)nb, (unsigned)T), 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n_rows, poisson_cdf, blk_off, nb, ent);
+    bag_fill_kernel<<<dim3((unsigned)nb, (unsigned)((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, blk_off, nb, ent);
     return check_launch("bag_fill");
 }
