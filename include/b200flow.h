@@ -123,18 +123,28 @@ int b200flow_bin_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, i
                       int32_t max_bins, const int32_t* labels,
                       uint8_t* tp, int32_t tp_stride, int32_t* bad_rows, void* stream);
 
-/* R6  BaggedPoint.convertToBaggedRDD, pass 1: per (tree, block of 1024 rows) number of
- * rows with Poisson weight > 0.  poisson_cdf: 32 uint32 thresholds, weight = #{k: cdf[k] != 2^32-1 && r >= cdf[k]};
- * NULL = no bagging (weight 1 for every row, numTrees==1).  blk_cnt[T][n_blocks] int32. */
-int b200flow_bag_count(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows,
-                       const uint32_t* poisson_cdf, int32_t* blk_cnt, void* stream);
+/* Row de-duplication (flow records repeat massively: KDD99 has 4.9 M rows but ~1.07 M distinct ones).  Rows whose TreePoint
+ * records (first key_bytes bytes: bins + label) are identical are interchangeable for the trees: uid[row] = index of the
+ * row's unique record (numbered in order of each group's first row), tp_unique[U][tp_stride] = the unique records,
+ * *n_unique = U (device scalar).  Scratch (caller-owned): table/minrow int32[table_cap] (power of two >= 2*n_rows),
+ * slot_of/rep/flag int32[n_rows], pos int64[n_rows+1]. */
+int b200flow_dedup_rows(const uint8_t* tp, int64_t n_rows, int32_t tp_stride, int32_t key_bytes,
+                        int32_t* table, int32_t* minrow, int64_t table_cap, int32_t* slot_of, int32_t* rep,
+                        int32_t* flag, int64_t* pos, int64_t* n_unique, int32_t* uid, uint8_t* tp_unique, void* stream);
 
-/* R6 pass 2: given blk_off = exclusive scan of blk_cnt (int64, tree-major), write the
- * bagged entries of every tree in row order.  One entry = one uint32: local row index in the
- * low 27 bits (=> at most 2^27 rows per GPU), bag weight in the high 5 bits. */
-int b200flow_bag_fill(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows,
-                      const uint32_t* poisson_cdf, const int64_t* blk_off,
-                      uint32_t* ent, void* stream);
+/* R6  BaggedPoint.convertToBaggedRDD: W[tree][uid[row]] += Poisson weight of (tree, global row).  poisson_cdf: 32 increasing
+ * uint32 thresholds, weight = #{k: cdf[k] != 2^32-1 && r >= cdf[k]} with r = word tree%4 of Philox(seed,'BAGG', row, tree/4);
+ * NULL = no bagging (weight 1 per row, numTrees==1).  uid NULL = identity.  W uint32[T][n_unique], caller zeroes. */
+int b200flow_bag_weights(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows,
+                         const uint32_t* poisson_cdf, const int32_t* uid, int64_t n_unique, uint32_t* W, void* stream);
+
+/* entries of every tree = its non-zero (unique record, summed weight) pairs in unique-id order.  Pass 1: non-zeros per
+ * (tree, block of 1024 uniques) -> blk_cnt[T][n_blocks]. */
+int b200flow_bag_count(const uint32_t* W, int32_t T, int64_t n_unique, int32_t* blk_cnt, void* stream);
+
+/* pass 2: given blk_off = exclusive scan of blk_cnt (int64, tree-major) write the entries; one entry = 8 bytes
+ * {uint32 unique record index, uint32 weight}. */
+int b200flow_bag_fill(const uint32_t* W, int32_t T, int64_t n_unique, const int64_t* blk_off, void* ent, void* stream);
 
 /* exclusive prefix sum utilities used by the trainer (single launch, any n) */
 int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* out,
@@ -144,7 +154,7 @@ int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* ou
  * One LEVEL of every tree is processed at once.  An active node is a "slot":
  *   slot_tree[s], slot_nid[s] (MLlib node id: root 1, children 2i/2i+1),
  *   slot_node[s]  index of the node in the forest node pool,
- *   seg_begin/seg_end[s]  its bagged entries inside ent (packed row|weight words).  */
+ *   seg_begin/seg_end[s]  its bagged entries inside ent (8-byte {record index, weight} pairs).  */
 
 /* per-node feature subsets (RandomForest.selectNodesToSplit): m of F features by a
  * partial Fisher-Yates keyed by (seed, tree, nid), sorted ascending -> subset[s*m..].
@@ -158,7 +168,7 @@ int b200flow_feature_subsets(uint64_t seed, int32_t n_slots, const int32_t* slot
  * the caller; layout stride = m * n_bins * C.  chunk_off = exclusive scan over slots of
  * ceil(len/chunk_rows) (int64[n_slots+1]); the grid is one CTA per chunk. */
 int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
-                        const uint32_t* ent,
+                        const void* ent,
                         int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
                         const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
                         const uint16_t* subset, int32_t m, int32_t n_bins, int32_t C,
@@ -217,7 +227,7 @@ int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, const uint32_
  * cursors[s*2+{0,1}] (int32, caller zeroes) end as (#left, #right).  Entries of children
  * that are leaves are dropped. */
 int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
-                             const uint32_t* ent, uint32_t* ent_out,
+                             const void* ent, void* ent_out,
                              int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
                              const b200flow_split* split, int32_t* cursors, void* stream);
@@ -232,7 +242,7 @@ int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
  * they do not, use partition_level followed by hist_level. */
 int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows);
 int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
-                              const uint32_t* ent, uint32_t* ent_out,
+                              const void* ent, void* ent_out,
                               int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
                               const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
                               const b200flow_split* split, const int32_t* child_slot, int32_t* cursors,

@@ -37,8 +37,10 @@ _SIGNATURES = {
     "b200flow_sample_rows": [_P, _I32, _I64, _I32, _I64, _U64, _U64, _I64, _P, _I64, _P, _P],
     "b200flow_find_splits": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P],
     "b200flow_bin_rows": [_P, _I32, _I64, _I32, _I64, _P, _P, _P, _I32, _P, _P, _I32, _P, _P],
-    "b200flow_bag_count": [_U64, _I32, _I64, _I64, _P, _P, _P],
-    "b200flow_bag_fill": [_U64, _I32, _I64, _I64, _P, _P, _P, _P],
+    "b200flow_dedup_rows": [_P, _I64, _I32, _I32, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b200flow_bag_weights": [_U64, _I32, _I64, _I64, _P, _P, _I64, _P, _P],
+    "b200flow_bag_count": [_P, _I32, _I64, _P, _P],
+    "b200flow_bag_fill": [_P, _I32, _I64, _P, _P, _P],
     "b200flow_exclusive_scan_i32_to_i64": [_P, _I64, _P, _P, _P],
     "b200flow_feature_subsets": [_U64, _I32, _P, _P, _I32, _I32, _P, _P],
     "b200flow_hist_level": [_P, _I32, _I32, _P, _I32, _P, _P, _P, _I64, _I32, _P, _I32, _I32, _I32, _P, _P],
@@ -58,7 +60,7 @@ EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version",
 
 _lib = None
 launches = 0   # kernels of OURS launched so far (counted per C-ABI call); bench.py reads the delta over the timed region
-_KERNELS_PER_CALL = {"b200flow_grow_level": 3, "b200flow_compact_rows": 3, "b200flow_route_hist_level": 2}
+_KERNELS_PER_CALL = {"b200flow_grow_level": 3, "b200flow_compact_rows": 3, "b200flow_route_hist_level": 2, "b200flow_dedup_rows": 5}
 
 
 def load():

@@ -22,6 +22,7 @@ CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_l
 import os as _os
 ROUTE_CHUNK_ROWS = int(_os.environ.get("B200FLOW_ROUTE_CHUNK", "512"))   # entries per CTA in the fused route_hist_level kernel
 FUSED = True                       # use route_hist_level (partition + next-level histogram in one pass) when it fits
+DEDUP = True                       # run the level loop on unique binned records (flow records repeat massively)
 PROFILE = None                     # set to a dict to collect per-kernel CUDA-event timings (bench.py)
 
 
@@ -275,23 +276,42 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     n_bins = int(head[1])
     feat_kind = _i32(kind, dev)
 
-    # ---- R6 bagging: count, scan, fill -> entries of every tree in row order
+    # ---- de-duplicate the binned rows: the level loop runs on UNIQUE TreePoint records carrying summed bag weights
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    if n > 0 and DEDUP:
+        cap_tab = 1
+        while cap_tab < 2 * n:
+            cap_tab <<= 1
+        table = torch.empty(cap_tab, dtype=torch.int32, device=dev); minrow = torch.empty(cap_tab, dtype=torch.int32, device=dev)
+        slot_of = torch.empty(n, dtype=torch.int32, device=dev); rep = torch.empty(n, dtype=torch.int32, device=dev)
+        flag = torch.empty(n, dtype=torch.int32, device=dev); pos = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        uid = torch.empty(n, dtype=torch.int32, device=dev)
+        tpu = torch.empty_like(tp)
+        _timed("dedup_rows", "b200flow_dedup_rows", ptr(tp), n, stride, F + 1, ptr(table), ptr(minrow), cap_tab, ptr(slot_of), ptr(rep),
+               ptr(flag), ptr(pos), ptr(total), ptr(uid), ptr(tpu))
+        U = int(total.item())
+        tp = tpu[:U]
+        del table, minrow, slot_of, rep, flag, pos, tpu
+    else:
+        uid, U = None, n
+    # ---- R6 bagging: W[tree][unique] = summed Poisson weights; entries = non-zero (unique, weight) pairs per tree
     bagging = p.bootstrap and T > 1
     cdf = torch.from_numpy(poisson_cdf_table(p.subsampling_rate).view(np.int32).copy()).to(dev) if bagging else None
-    nb = (n + 1023) // 1024
+    nb = (U + 1023) // 1024
+    W = torch.zeros(max(T * U, 1), dtype=torch.int32, device=dev)
+    if n > 0:
+        _timed("bag_weights", "b200flow_bag_weights", seed, T, int(row_offset), n, ptr(cdf), ptr(uid), U, ptr(W))
     blk_cnt = torch.zeros(max(T * nb, 1), dtype=torch.int32, device=dev)
     blk_off = torch.zeros(T * nb + 1, dtype=torch.int64, device=dev)
-    total = torch.zeros(1, dtype=torch.int64, device=dev)
-    if n > 0:
-        call("b200flow_bag_count", seed, T, int(row_offset), n, ptr(cdf), ptr(blk_cnt))
+    if U > 0:
+        call("b200flow_bag_count", ptr(W), T, U, ptr(blk_cnt))
     call("b200flow_exclusive_scan_i32_to_i64", ptr(blk_cnt), T * nb, ptr(blk_off), ptr(total))
     E = int(total.item())
-    if n > (1 << 27):
-        raise B200FlowError("at most 2^27 rows per GPU (bagged entries pack the row index into 27 bits); shard the rows")
-    ent = torch.empty(max(E, 1), dtype=torch.int32, device=dev)          # packed: row | weight << 27
+    ent = torch.empty((max(E, 1), 2), dtype=torch.int32, device=dev)     # {unique record index, weight}
     ent2 = torch.empty_like(ent)
-    if n > 0:
-        call("b200flow_bag_fill", seed, T, int(row_offset), n, ptr(cdf), ptr(blk_off), ptr(ent))
+    if U > 0:
+        call("b200flow_bag_fill", ptr(W), T, U, ptr(blk_off), ptr(ent))
+    del W, uid
 
     # ---- node pool
     cap_nodes = max(4096, 4 * T)
@@ -334,7 +354,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     level = 0
     per_slot_hist = m * n_bins * C * 4
     group_slots = max(1, HIST_BUDGET_BYTES // per_slot_hist)
-    stats = dict(levels=0, slots=0, entries=E, hist_launches=0)
+    stats = dict(levels=0, slots=0, entries=E, hist_launches=0, rows=n, unique_rows=U)
 
     route_ch = ROUTE_CHUNK_ROWS
     while route_ch > 128 and not _lib.load().b200flow_route_hist_fits(F, m, n_bins, C, route_ch):

@@ -52,11 +52,8 @@ __device__ __forceinline__ uint4 bag_draw4(uint64_t seed, int tree_quad, uint64_
     return philox_keyed(seed, PURPOSE_BAG, (uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)tree_quad, 0u);
 }
 
-// bagged entry = row index (27 bits) | bag weight (5 bits): one 32-bit word per (tree, row) pair
-constexpr uint32_t kEntRowMask = (1u << 27) - 1u;
-__device__ __forceinline__ uint32_t ent_pack(uint32_t row, uint32_t w) { return row | (w << 27); }
-__device__ __forceinline__ int ent_row_of(uint32_t e) { return (int)(e & kEntRowMask); }
-__device__ __forceinline__ uint32_t ent_weight_of(uint32_t e) { return e >> 27; }
+// bagged entry = (index of a UNIQUE TreePoint record, summed bag weight of the rows that share it): 8 bytes
+typedef uint2 b2f_entry;      // .x = record index, .y = weight
 
 // ------------------------------------------------------------------ warp / block helpers
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -61,7 +61,7 @@ __device__ __forceinline__ int find_slot(const int64_t* __restrict__ chunk_off, 
 
 // ------------------------------------------------------------------ R7 histogram build (HOT LOOP A)
 __global__ void __launch_bounds__(256) hist_level_kernel(const uint8_t* __restrict__ tp, int stride, int F,
-                                                         const uint32_t* __restrict__ ent, int n_slots, const int64_t* __restrict__ seg_begin,
+                                                         const b2f_entry* __restrict__ ent, int n_slots, const int64_t* __restrict__ seg_begin,
                                                          const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off,
                                                          int chunk_rows, const uint16_t* __restrict__ subset, int m, int n_bins,
                                                          int C, int m_pass, uint32_t* hist) {
@@ -82,9 +82,9 @@ __global__ void __launch_bounds__(256) hist_level_kernel(const uint8_t* __restri
         for (int i = threadIdx.x; i < hsz; i += blockDim.x) sh_hist[i] = 0;
         __syncthreads();
         for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
-            const uint32_t en = ent[i];
-            const uint32_t w = ent_weight_of(en);
-            const uint8_t* rec = tp + (int64_t)ent_row_of(en) * stride;
+            const b2f_entry en = ent[i];
+            const uint32_t w = en.y;
+            const uint8_t* rec = tp + (int64_t)en.x * stride;
             const int lab = rec[F];
             for (int j = 0; j < mp; ++j) {
                 const int bin = rec[sh_feat[j0 + j]];
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kGrowBlock) grow_write_kernel(
 constexpr int kPartPerThread = 8;      // chunk_rows <= 256 * 8
 
 __global__ void __launch_bounds__(256) partition_level_kernel(
-    const uint8_t* __restrict__ tp, int stride, const uint32_t* __restrict__ ent, uint32_t* ent_out, int n_slots,
+    const uint8_t* __restrict__ tp, int stride, const b2f_entry* __restrict__ ent, b2f_entry* ent_out, int n_slots,
     const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end, const int64_t* __restrict__ chunk_off,
     int chunk_rows, const b200flow_split* __restrict__ split, int32_t* cursors) {
     const int64_t c = blockIdx.x;
@@ -382,15 +382,15 @@ __global__ void __launch_bounds__(256) partition_level_kernel(
     const int64_t b = sb + (c - chunk_off[s]) * chunk_rows;
     const int64_t e = min(se, b + chunk_rows);
     const int lane = lane_id();
-    uint32_t ents[kPartPerThread]; uint32_t dec = 0;   // dec: 2 bits per entry (1 = left kept, 2 = right kept)
+    b2f_entry ents[kPartPerThread]; uint32_t dec = 0;  // dec: 2 bits per entry (1 = left kept, 2 = right kept)
     int nL = 0, nR = 0;
 #pragma unroll
     for (int k = 0; k < kPartPerThread; ++k) {
         const int64_t i = b + threadIdx.x + (int64_t)k * blockDim.x;
-        int d = 0; ents[k] = 0;
+        int d = 0; ents[k] = make_uint2(0u, 0u);
         if (i < e) {
             ents[k] = ent[i];
-            const int bin = tp[(int64_t)ent_row_of(ents[k]) * stride + sp.feat];
+            const int bin = tp[(int64_t)ents[k].x * stride + sp.feat];
             const bool left = sp.kind == 0 ? (bin <= sp.bin_thr) : ((sp.mask[bin >> 6] >> (bin & 63)) & 1ull);
             d = left ? (keepL ? 1 : 0) : (keepR ? 2 : 0);
         }
@@ -439,19 +439,9 @@ __global__ void route_chunks_kernel(const int64_t* __restrict__ chunk_off, int n
     out[c] = rc;
 }
 
-// Σ of the (small integer) bag weights over the lanes of `g`, for every lane of `active` at once, from three ballots.
-// Lanes with w > 3 (3 % of bagged rows) are not merged: they add their own weight.
-__device__ __forceinline__ uint32_t group_weight(uint32_t g, uint32_t w, uint32_t active, bool* leader) {
-    const uint32_t b1 = __ballot_sync(active, w == 1), b2 = __ballot_sync(active, w == 2), b3 = __ballot_sync(active, w == 3);
-    const uint32_t gg = g & (b1 | b2 | b3);
-    if (w > 3) { *leader = true; return w; }
-    *leader = (int)(__ffs(gg) - 1) == lane_id();
-    return __popc(gg & b1) + 2 * __popc(gg & b2) + 3 * __popc(gg & b3);
-}
-
 struct RouteArgs {
     const uint8_t* tp; int stride; int F;
-    const uint32_t* ent; uint32_t* ent_out;
+    const b2f_entry* ent; b2f_entry* ent_out;
     const RouteChunk* chunks; int64_t n_chunks; int CH;
     const int64_t* seg_begin; const int64_t* seg_end;
     const b200flow_split* split; const int32_t* child_slot; int32_t* cursors;
@@ -496,34 +486,34 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     };
     auto desc_at = [&](int64_t c) { return c < c1 ? __ldg((const int4*)(a.chunks + c)) : make_int4(-1, 0, 0, 0); };
     auto count_of = [&](const int4& d) { return min(kSub, d.y - wid * kSub); };
-    auto entries_of = [&](const int4& d, uint32_t* x0, uint32_t* x1) {
+    auto entries_of = [&](const int4& d, b2f_entry* x0, b2f_entry* x1) {
         const int cn = count_of(d);
-        const uint32_t* ep = a.ent + (((long long)(uint32_t)d.z) | ((long long)d.w << 32)) + wid * kSub;
-        *x0 = lane < cn ? __ldg(ep + lane) : 0u;
-        *x1 = lane + 32 < cn ? __ldg(ep + 32 + lane) : 0u;
+        const b2f_entry* ep = a.ent + (((long long)(uint32_t)d.z) | ((long long)d.w << 32)) + wid * kSub;
+        *x0 = lane < cn ? __ldg(ep + lane) : make_uint2(0u, 0u);
+        *x1 = lane + 32 < cn ? __ldg(ep + 32 + lane) : make_uint2(0u, 0u);
     };
-    auto issue_gather = [&](const int4& d, uint32_t x0, uint32_t x1, uint32_t* tile) {
+    auto issue_gather = [&](const int4& d, const b2f_entry& x0, const b2f_entry& x1, uint32_t* tile) {
         const int cn = count_of(d);
         if (lane < cn) {
-            const uint8_t* src = a.tp + (int64_t)ent_row_of(x0) * a.stride;
+            const uint8_t* src = a.tp + (int64_t)x0.x * a.stride;
             for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + lane) * 4, src + q * 16);
         }
         if (lane + 32 < cn) {
-            const uint8_t* src = a.tp + (int64_t)ent_row_of(x1) * a.stride;
+            const uint8_t* src = a.tp + (int64_t)x1.x * a.stride;
             for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + 32 + lane) * 4, src + q * 16);
         }
         cp_async_commit();
     };
     // pending write of the previous step (registers only)
     bool pending = false;
-    uint32_t p_e0 = 0, p_e1 = 0, p_dec = 0; int p_bl = 0, p_br = 0; int64_t p_sb = 0, p_se = 0;
+    b2f_entry p_e0 = make_uint2(0u, 0u), p_e1 = p_e0; uint32_t p_dec = 0; int p_bl = 0, p_br = 0; int64_t p_sb = 0, p_se = 0;
     const uint32_t lt = (1u << lane) - 1u;
     auto write_pending = [&]() {
         int baseL = __shfl_sync(0xffffffffu, p_bl, 0), baseR = __shfl_sync(0xffffffffu, p_br, 0);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int d = (p_dec >> (2 * k)) & 3;
-            const uint32_t e = k ? p_e1 : p_e0;
+            const b2f_entry e = k ? p_e1 : p_e0;
             const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
             if (d == 1) a.ent_out[p_sb + baseL + __popc(mL & lt)] = e;
             else if (d == 2) a.ent_out[p_se - 1 - (baseR + __popc(mR & lt))] = e;
@@ -533,7 +523,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     };
 
     int4 d0 = desc_at(c0), d1 = desc_at(c0 + 1), d2 = desc_at(c0 + 2);
-    uint32_t e0, e1, f0, f1, g0 = 0, g1 = 0;                 // entries of steps t, t+1, t+2
+    b2f_entry e0, e1, f0, f1, g0 = make_uint2(0u, 0u), g1 = g0;   // entries of steps t, t+1, t+2
     entries_of(d0, &e0, &e1);
     entries_of(d1, &f0, &f1);
     if (NBUF == 2) issue_gather(d0, e0, e1, tiles);
@@ -591,7 +581,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                     const int* fpos = sh_fpos + side * m;
                     uint32_t* hist = sh_hist + side * hsz;
                     const uint32_t lab = (tile[lab_pos + i * 4] >> lab_sh) & 0xffu;
-                    const uint32_t w = ent_weight_of(k ? e1 : e0);
+                    const uint32_t w = k ? e1.y : e0.y;
                     if (M > 0 && FULLKEY) {
                         // whole-key merge: lanes with identical (child, all M bins, label) are combined
                         constexpr int NW = (M + 1 + 3) / 4;
@@ -607,9 +597,8 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                         uint32_t g = active;
 #pragma unroll
                         for (int q = 0; q < NW; ++q) g &= __match_any_sync(active, keys[q]);
-                        bool leader;
-                        const uint32_t sum = group_weight(g, w, active, &leader);
-                        if (leader) {
+                        const uint32_t sum = __reduce_add_sync(g, w);        // weights are sums over duplicate rows: any size
+                        if ((int)(__ffs(g) - 1) == lane) {
 #pragma unroll
                             for (int j = 0; j < M; ++j)
                                 atomicAdd(&hist[j * nbC + ((keys[j >> 2] >> (8 * (j & 3))) & 0xff) * a.C + lab], sum);
@@ -617,17 +606,14 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                     } else if (M > 0) {
                         // per-feature merge: lanes that hit the same (child, feature, bin, label) counter are combined with
                         // match.any; the group's bag-weight sum comes from three ballots shared by all features
-                        const uint32_t b1 = __ballot_sync(active, w == 1), b2 = __ballot_sync(active, w == 2), b3 = __ballot_sync(active, w == 3);
-                        const uint32_t small = b1 | b2 | b3;
                         const uint32_t tag = (lab << 8) | ((uint32_t)side << 16);
 #pragma unroll
                         for (int j = 0; j < M; ++j) {
                             const int fp = fpos[j];
                             const uint32_t bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu;
-                            const uint32_t gg = __match_any_sync(active, bin | tag) & small;
-                            uint32_t* addr = &hist[j * nbC + bin * a.C + lab];
-                            if (w > 3) atomicAdd(addr, w);
-                            else if ((int)(__ffs(gg) - 1) == lane) atomicAdd(addr, (uint32_t)(__popc(gg & b1) + 2 * __popc(gg & b2) + 3 * __popc(gg & b3)));
+                            const uint32_t gg = __match_any_sync(active, bin | tag);
+                            const uint32_t sum = __reduce_add_sync(gg, w);
+                            if ((int)(__ffs(gg) - 1) == lane) atomicAdd(&hist[j * nbC + bin * a.C + lab], sum);
                         }
                     } else {
                         for (int j = 0; j < m; ++j) {
@@ -698,7 +684,7 @@ extern "C" int b200flow_feature_subsets(uint64_t seed, int32_t n_slots, const in
     return check_launch("feature_subsets");
 }
 
-extern "C" int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const uint32_t* ent,
+extern "C" int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const void* ent,
                                    int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end, const int64_t* chunk_off,
                                    int64_t n_chunks, int32_t chunk_rows, const uint16_t* subset, int32_t m, int32_t n_bins,
                                    int32_t C, uint32_t* hist, void* stream) {
@@ -714,7 +700,7 @@ extern "C" int b200flow_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t
     B2F_REQUIRE(n_chunks < ((int64_t)1 << 31), "hist_level: too many chunks");
     cudaError_t e = cudaFuncSetAttribute(hist_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
-    hist_level_kernel<<<(unsigned)n_chunks, 256, smem, (cudaStream_t)stream>>>(tp, tp_stride, F, ent, n_slots, seg_begin,
+    hist_level_kernel<<<(unsigned)n_chunks, 256, smem, (cudaStream_t)stream>>>(tp, tp_stride, F, (const b2f_entry*)ent, n_slots, seg_begin,
                                                                              seg_end, chunk_off, chunk_rows, subset, m, n_bins, C, m_pass, hist);
     return check_launch("hist_level");
 }
@@ -760,13 +746,13 @@ extern "C" int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, co
     return check_launch("grow_level");
 }
 
-extern "C" int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride, const uint32_t* ent, uint32_t* ent_out, int32_t n_slots,
+extern "C" int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride, const void* ent, void* ent_out, int32_t n_slots,
                                         const int64_t* seg_begin, const int64_t* seg_end, const int64_t* chunk_off, int64_t n_chunks,
                                         int32_t chunk_rows, const b200flow_split* split, int32_t* cursors, void* stream) {
     B2F_REQUIRE(tp && ent && ent_out && seg_begin && seg_end && chunk_off && split && cursors, "partition_level: null pointer");
     B2F_REQUIRE(chunk_rows > 0 && chunk_rows <= 256 * kPartPerThread, "partition_level: chunk_rows must be <= %d", 256 * kPartPerThread);
     if (n_slots <= 0 || n_chunks <= 0) return B200FLOW_OK;
-    partition_level_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(tp, tp_stride, ent, ent_out, n_slots, seg_begin, seg_end,
+    partition_level_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(tp, tp_stride, (const b2f_entry*)ent, (b2f_entry*)ent_out, n_slots, seg_begin, seg_end,
                                                                                chunk_off, chunk_rows, split, cursors);
     return check_launch("partition_level");
 }
@@ -791,7 +777,7 @@ extern "C" int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, in
     return route_hist_smem(F, m, n_bins, C, chunk_rows) <= 110 * 1024 ? 1 : 0;    // >= 2 CTAs per SM
 }
 
-extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const uint32_t* ent, uint32_t* ent_out,
+extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const void* ent, void* ent_out,
                                          int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end, const int64_t* chunk_off,
                                          int64_t n_chunks, int32_t chunk_rows, const b200flow_split* split, const int32_t* child_slot,
                                          int32_t* cursors, void* chunk_scratch, const uint16_t* subset_next, int32_t m, int32_t n_bins,
@@ -807,7 +793,7 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     route_chunks_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chunk_off, n_slots, n_chunks, seg_begin, seg_end,
                                                                                             chunk_rows, chunks);
     RouteArgs a;
-    a.tp = tp; a.stride = tp_stride; a.F = F; a.ent = ent; a.ent_out = ent_out; a.chunks = chunks; a.n_chunks = n_chunks; a.CH = chunk_rows;
+    a.tp = tp; a.stride = tp_stride; a.F = F; a.ent = (const b2f_entry*)ent; a.ent_out = (b2f_entry*)ent_out; a.chunks = chunks; a.n_chunks = n_chunks; a.CH = chunk_rows;
     a.seg_begin = seg_begin; a.seg_end = seg_end; a.split = split; a.child_slot = child_slot; a.cursors = cursors;
     a.subset_next = subset_next; a.m = m; a.n_bins = n_bins; a.C = C; a.hist_next = hist_next;
     int per_sm = (int)((227 * 1024) / (smem + 1024));

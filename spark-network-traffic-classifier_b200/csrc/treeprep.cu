@@ -158,77 +158,120 @@ __global__ void __launch_bounds__(256) bin_rows_kernel(const T* __restrict__ x, 
     }
 }
 
+// ------------------------------------------------------------------ row de-duplication
+// Flow records repeat massively (KDD99: 4.9 M rows, ~1.07 M distinct; the smurf/neptune floods are literally the same
+// record).  After binning, rows with identical TreePoint records (bins + label) are interchangeable for the trees, so the
+// level loop runs on UNIQUE records carrying the summed bag weight of their duplicates — same integer histograms, same
+// forest, several times fewer entries.  Open-addressing hash table keyed by the record bytes; the representative of a
+// group is its smallest row index (deterministic), unique ids are assigned in representative-row order.
+__device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v) {
+    h ^= v * 0x9E3779B97F4A7C15ull; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    return h;
+}
+__device__ __forceinline__ bool records_equal(const uint4* a, const uint4* b, int nq) {
+    bool eq = true;
+    for (int q = 0; q < nq; ++q) { const uint4 x = __ldg(a + q), y = __ldg(b + q); eq = eq && x.x == y.x && x.y == y.y && x.z == y.z && x.w == y.w; }
+    return eq;
+}
+
+__global__ void __launch_bounds__(256) dedup_insert_kernel(const uint8_t* __restrict__ tp, int64_t n, int stride, int nq,
+                                                           int32_t* table, uint32_t cap_mask, int32_t* slot_of) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* rec = (const uint4*)(tp + i * stride);
+    uint64_t h = 0x243F6A8885A308D3ull;
+    for (int q = 0; q < nq; ++q) { const uint4 v = __ldg(rec + q); h = mix64(h, ((uint64_t)v.y << 32) | v.x); h = mix64(h, ((uint64_t)v.w << 32) | v.z); }
+    uint32_t slot = (uint32_t)(h ^ (h >> 32)) & cap_mask;
+    while (true) {
+        int cur = table[slot];
+        if (cur < 0) { cur = atomicCAS(&table[slot], -1, (int)i); if (cur < 0) { slot_of[i] = (int)slot; return; } }
+        if (records_equal(rec, (const uint4*)(tp + (int64_t)cur * stride), nq)) { slot_of[i] = (int)slot; return; }
+        slot = (slot + 1) & cap_mask;
+    }
+}
+__global__ void __launch_bounds__(256) dedup_min_kernel(int64_t n, const int32_t* __restrict__ slot_of, int32_t* minrow) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicMin(&minrow[slot_of[i]], (int)i);
+}
+__global__ void __launch_bounds__(256) dedup_flag_kernel(int64_t n, const int32_t* __restrict__ slot_of, const int32_t* __restrict__ minrow,
+                                                         int32_t* rep, int32_t* flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int r = minrow[slot_of[i]]; rep[i] = r; flag[i] = r == (int)i ? 1 : 0; }
+}
+__global__ void __launch_bounds__(256) dedup_emit_kernel(const uint8_t* __restrict__ tp, int64_t n, int stride, const int32_t* __restrict__ rep,
+                                                         const int64_t* __restrict__ pos, int32_t* uid, uint8_t* tpu) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = rep[i];
+    const int64_t u = pos[r];
+    uid[i] = (int32_t)u;
+    if (r == (int)i) {
+        const uint4* src = (const uint4*)(tp + i * stride); uint4* dst = (uint4*)(tpu + u * stride);
+        for (int q = 0; q < stride / 16; ++q) dst[q] = __ldg(src + q);
+    }
+}
+
 // ------------------------------------------------------------------ R6 bagging
 constexpr int kBagBlockRows = 1024;
 
-// grid = (row blocks of 1024, tree quads).  A thread owns 4 consecutive rows; one Philox call per row yields the weights
-// of the quad's 4 trees.
-__global__ void __launch_bounds__(256) bag_count_kernel(uint64_t seed, int T, int64_t row_offset, int64_t n,
-                                                        const uint32_t* __restrict__ cdf, int32_t* blk_cnt, int64_t n_blocks) {
+// W[tree][uid[row]] += Poisson weight of (tree, row).  grid = (row blocks of 1024, tree quads); a thread owns 4 consecutive
+// rows; one Philox call per row yields the weights of the quad's 4 trees.  Rows of one duplicate group are adjacent lanes
+// only by chance, so the adds are global REDs (the hot groups serialise in L2; measured in profiles/).
+__global__ void __launch_bounds__(256) bag_weights_kernel(uint64_t seed, int T, int64_t row_offset, int64_t n,
+                                                          const uint32_t* __restrict__ cdf, const int32_t* __restrict__ uid, int64_t U,
+                                                          uint32_t* W) {
     __shared__ uint32_t cdf_sh[32];
-    __shared__ int cnt_sh[4];
     const int tq = blockIdx.y;
     if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
-    if (threadIdx.x < 4) cnt_sh[threadIdx.x] = 0;
     __syncthreads();
     const int64_t rb = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
-    int c[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int64_t i = rb + k;
-        if (i < n) {
-            if (cdf) {
-                const uint4 r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
-                c[0] += poisson_weight(r.x, cdf_sh) > 0; c[1] += poisson_weight(r.y, cdf_sh) > 0;
-                c[2] += poisson_weight(r.z, cdf_sh) > 0; c[3] += poisson_weight(r.w, cdf_sh) > 0;
-            } else { c[0]++; c[1]++; c[2]++; c[3]++; }
+        if (i >= n) break;
+        const int64_t u = uid ? uid[i] : i;
+        uint32_t w[4] = {1u, 1u, 1u, 1u};
+        if (cdf) {
+            const uint4 r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
+            w[0] = poisson_weight(r.x, cdf_sh); w[1] = poisson_weight(r.y, cdf_sh);
+            w[2] = poisson_weight(r.z, cdf_sh); w[3] = poisson_weight(r.w, cdf_sh);
         }
-    }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int v = warp_sum(c[q]);
-        if (lane_id() == 0 && v) atomicAdd(&cnt_sh[q], v);
+        for (int q = 0; q < 4; ++q)
+            if (tq * 4 + q < T && w[q]) atomicAdd(&W[(int64_t)(tq * 4 + q) * U + u], w[q]);
     }
-    __syncthreads();
-    if (threadIdx.x < 4 && tq * 4 + threadIdx.x < T) blk_cnt[(int64_t)(tq * 4 + threadIdx.x) * n_blocks + blockIdx.x] = cnt_sh[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(256) bag_fill_kernel(uint64_t seed, int T, int64_t row_offset, int64_t n,
-                                                       const uint32_t* __restrict__ cdf, const int64_t* __restrict__ blk_off,
-                                                       int64_t n_blocks, uint32_t* ent) {
-    __shared__ uint32_t cdf_sh[32];
-    __shared__ int sh[33];
-    const int tq = blockIdx.y;
-    if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
+// entries of every tree = its non-zero (unique record, weight) pairs, in unique-id order: count per block, scan, fill
+__global__ void __launch_bounds__(256) bag_count_kernel(const uint32_t* __restrict__ W, int64_t U, int32_t* blk_cnt, int64_t n_blocks) {
+    __shared__ int cnt_sh;
+    const int t = blockIdx.y;
+    if (threadIdx.x == 0) cnt_sh = 0;
     __syncthreads();
-    const int64_t rb = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
-    uint32_t w[4][4];                                   // [tree in quad][row]
+    const int64_t ub = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
+    int c = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int64_t i = rb + k;
-        uint4 r = make_uint4(0, 0, 0, 0);
-        const bool live = i < n;
-        if (live && cdf) r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
-        w[0][k] = live ? (cdf ? poisson_weight(r.x, cdf_sh) : 1u) : 0u;
-        w[1][k] = live ? (cdf ? poisson_weight(r.y, cdf_sh) : 1u) : 0u;
-        w[2][k] = live ? (cdf ? poisson_weight(r.z, cdf_sh) : 1u) : 0u;
-        w[3][k] = live ? (cdf ? poisson_weight(r.w, cdf_sh) : 1u) : 0u;
-    }
+    for (int k = 0; k < 4; ++k) if (ub + k < U && W[(int64_t)t * U + ub + k]) ++c;
+    c = warp_sum(c);
+    if (lane_id() == 0 && c) atomicAdd(&cnt_sh, c);
+    __syncthreads();
+    if (threadIdx.x == 0) blk_cnt[(int64_t)t * n_blocks + blockIdx.x] = cnt_sh;
+}
+
+__global__ void __launch_bounds__(256) bag_fill_kernel(const uint32_t* __restrict__ W, int64_t U, const int64_t* __restrict__ blk_off,
+                                                       int64_t n_blocks, b2f_entry* ent) {
+    __shared__ int sh[33];
+    const int t = blockIdx.y;
+    const int64_t ub = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
+    uint32_t w[4]; int c = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int t = tq * 4 + q;                       // uniform per block
-        if (t >= T) break;
-        int c = 0;
+    for (int k = 0; k < 4; ++k) { w[k] = (ub + k < U) ? W[(int64_t)t * U + ub + k] : 0u; c += w[k] ? 1 : 0; }
+    int tot;
+    const int ex = block_exclusive_scan(c, sh, &tot);
+    int64_t pos = blk_off[(int64_t)t * n_blocks + blockIdx.x] + ex;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) c += w[q][k] > 0 ? 1 : 0;
-        int tot;
-        const int ex = block_exclusive_scan(c, sh, &tot);
-        int64_t pos = blk_off[(int64_t)t * n_blocks + blockIdx.x] + ex;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (w[q][k] > 0) { ent[pos] = ent_pack((uint32_t)(rb + k), min(w[q][k], 31u)); ++pos; }
-        __syncthreads();                                // sh reused by the next tree's scan
-    }
+    for (int k = 0; k < 4; ++k)
+        if (w[k]) { ent[pos] = make_uint2((uint32_t)(ub + k), w[k]); ++pos; }
 }
 
 }  // namespace b200flow
@@ -292,21 +335,51 @@ extern "C" int b200flow_bin_rows(const void* x, int32_t dtype, int64_t n_rows, i
     return check_launch("bin_rows");
 }
 
-extern "C" int b200flow_bag_count(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows, const uint32_t* poisson_cdf,
-                                  int32_t* blk_cnt, void* stream) {
-    B2F_REQUIRE(blk_cnt && T > 0 && T <= 65535 && n_rows >= 0, "bag_count: bad arguments");
-    if (n_rows == 0) return B200FLOW_OK;
-    int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
-    bag_count_kernel<<<dim3((unsigned)nb, (unsigned)((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, blk_cnt, nb);
+extern "C" int b200flow_dedup_rows(const uint8_t* tp, int64_t n_rows, int32_t tp_stride, int32_t key_bytes, int32_t* table,
+                                   int32_t* minrow, int64_t table_cap, int32_t* slot_of, int32_t* rep, int32_t* flag, int64_t* pos,
+                                   int64_t* n_unique, int32_t* uid, uint8_t* tp_unique, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(tp && table && minrow && slot_of && rep && flag && pos && n_unique && uid && tp_unique, "dedup_rows: null pointer");
+    B2F_REQUIRE((tp_stride & 15) == 0 && key_bytes > 0 && key_bytes <= tp_stride && ((uintptr_t)tp & 15) == 0 && ((uintptr_t)tp_unique & 15) == 0,
+                "dedup_rows: bad stride/alignment");
+    B2F_REQUIRE(table_cap >= 2 * n_rows && (table_cap & (table_cap - 1)) == 0 && table_cap <= ((int64_t)1 << 31), "dedup_rows: table_cap must be a power of two >= 2*n_rows");
+    B2F_REQUIRE(n_rows < ((int64_t)1 << 31), "dedup_rows: too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(table, 0xFF, (size_t)table_cap * 4, st);            // -1 = empty
+    cudaMemsetAsync(minrow, 0x7F, (size_t)table_cap * 4, st);           // 0x7F7F7F7F > any row index
+    const unsigned grid = (unsigned)((n_rows + 255) / 256);
+    const int nq = (key_bytes + 15) / 16;                               // pad bytes of a TreePoint are zero: whole quads compare equal
+    dedup_insert_kernel<<<grid, 256, 0, st>>>(tp, n_rows, tp_stride, nq, table, (uint32_t)(table_cap - 1), slot_of);
+    dedup_min_kernel<<<grid, 256, 0, st>>>(n_rows, slot_of, minrow);
+    dedup_flag_kernel<<<grid, 256, 0, st>>>(n_rows, slot_of, minrow, rep, flag);
+    int rc = b200flow_exclusive_scan_i32_to_i64(flag, n_rows, pos, n_unique, stream);
+    if (rc) return rc;
+    dedup_emit_kernel<<<grid, 256, 0, st>>>(tp, n_rows, tp_stride, rep, pos, uid, tp_unique);
+    return check_launch("dedup_rows");
+}
+
+extern "C" int b200flow_bag_weights(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows, const uint32_t* poisson_cdf,
+                                    const int32_t* uid, int64_t n_unique, uint32_t* W, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(W && T > 0 && T <= 65535 * 4 && n_unique > 0, "bag_weights: bad arguments");
+    const int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
+    bag_weights_kernel<<<dim3((unsigned)nb, (unsigned)((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, uid,
+                                                                                                   n_unique, W);
+    return check_launch("bag_weights");
+}
+
+extern "C" int b200flow_bag_count(const uint32_t* W, int32_t T, int64_t n_unique, int32_t* blk_cnt, void* stream) {
+    B2F_REQUIRE(W && blk_cnt && T > 0 && T <= 65535 && n_unique >= 0, "bag_count: bad arguments");
+    if (n_unique == 0) return B200FLOW_OK;
+    const int64_t nb = (n_unique + kBagBlockRows - 1) / kBagBlockRows;
+    bag_count_kernel<<<dim3((unsigned)nb, (unsigned)T), 256, 0, (cudaStream_t)stream>>>(W, n_unique, blk_cnt, nb);
     return check_launch("bag_count");
 }
 
-extern "C" int b200flow_bag_fill(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows, const uint32_t* poisson_cdf,
-                                 const int64_t* blk_off, uint32_t* ent, void* stream) {
-    B2F_REQUIRE(blk_off && ent && T > 0 && T <= 65535 && n_rows >= 0, "bag_fill: bad arguments");
-    B2F_REQUIRE(n_rows <= (int64_t)kEntRowMask + 1, "bag_fill: at most 2^27 rows per GPU (row index is packed into 27 bits)");
-    if (n_rows == 0) return B200FLOW_OK;
-    int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
-    bag_fill_kernel<<<dim3((unsigned)nb, (unsigned)((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, blk_off, nb, ent);
+extern "C" int b200flow_bag_fill(const uint32_t* W, int32_t T, int64_t n_unique, const int64_t* blk_off, void* ent, void* stream) {
+    B2F_REQUIRE(W && blk_off && ent && T > 0 && T <= 65535 && n_unique >= 0 && ((uintptr_t)ent & 7) == 0, "bag_fill: bad arguments");
+    if (n_unique == 0) return B200FLOW_OK;
+    const int64_t nb = (n_unique + kBagBlockRows - 1) / kBagBlockRows;
+    bag_fill_kernel<<<dim3((unsigned)nb, (unsigned)T), 256, 0, (cudaStream_t)stream>>>(W, n_unique, blk_off, nb, (b2f_entry*)ent);
     return check_launch("bag_fill");
 }

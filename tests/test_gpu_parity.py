@@ -132,27 +132,64 @@ def test_find_splits_and_binning_exact():
     assert np.array_equal(tp32.cpu().numpy()[:, :F + 1], tp_o32[:, :F + 1])
 
 
-def test_bagging_entries_match_oracle_weights():
+def test_bagging_weights_and_entries_match_oracle():
     n, T, seed = 5000, 7, 1234
     cdf = fr.poisson_cdf_table(1.0)
     assert np.array_equal(cdf, oracle.poisson_cdf_table(1.0))
     w = oracle.bag_weights(seed, T, n, cdf, row_offset=17)
-    nb = (n + 1023) // 1024
     cdf_t = torch.from_numpy(cdf.view(np.int32).copy()).to(DEV)
+    W = torch.zeros(T * n, dtype=torch.int32, device=DEV)
+    _lib.call("b200flow_bag_weights", seed, T, 17, n, _lib.ptr(cdf_t), None, n, _lib.ptr(W))       # identity uid
+    assert np.array_equal(W.cpu().numpy().reshape(T, n), w.astype(np.int32))
+    # duplicate groups: weights of the rows of a group are summed into its unique record
+    uid = torch.randint(0, 37, (n,), dtype=torch.int32, device=DEV)
+    W2 = torch.zeros(T * 37, dtype=torch.int32, device=DEV)
+    _lib.call("b200flow_bag_weights", seed, T, 17, n, _lib.ptr(cdf_t), _lib.ptr(uid), 37, _lib.ptr(W2))
+    want = np.zeros((T, 37), np.int64)
+    for t in range(T):
+        np.add.at(want[t], uid.cpu().numpy(), w[t])
+    assert np.array_equal(W2.cpu().numpy().reshape(T, 37), want)
+    # entries = non-zero (unique, weight) pairs per tree, in unique-id order
+    nb = (n + 1023) // 1024
     blk = torch.zeros(T * nb, dtype=torch.int32, device=DEV)
-    _lib.call("b200flow_bag_count", seed, T, 17, n, _lib.ptr(cdf_t), _lib.ptr(blk))
+    _lib.call("b200flow_bag_count", _lib.ptr(W), T, n, _lib.ptr(blk))
     off = torch.zeros(T * nb + 1, dtype=torch.int64, device=DEV); tot = torch.zeros(1, dtype=torch.int64, device=DEV)
     _lib.call("b200flow_exclusive_scan_i32_to_i64", _lib.ptr(blk), T * nb, _lib.ptr(off), _lib.ptr(tot))
     E = int(tot.item())
     assert E == int((w > 0).sum())
-    ent = torch.empty(E, dtype=torch.int32, device=DEV)
-    _lib.call("b200flow_bag_fill", seed, T, 17, n, _lib.ptr(cdf_t), _lib.ptr(off), _lib.ptr(ent))
-    ent = ent.cpu().numpy().view(np.uint32)
-    rows, wt, off = (ent & ((1 << 27) - 1)).astype(np.int64), (ent >> 27).astype(np.uint8), off.cpu().numpy()
+    ent = torch.empty((E, 2), dtype=torch.int32, device=DEV)
+    _lib.call("b200flow_bag_fill", _lib.ptr(W), T, n, _lib.ptr(off), _lib.ptr(ent))
+    ent, off = ent.cpu().numpy(), off.cpu().numpy()
     for t in range(T):
         b, e = off[t * nb], off[(t + 1) * nb]
         idx = np.nonzero(w[t])[0]
-        assert np.array_equal(rows[b:e], idx) and np.array_equal(wt[b:e], w[t][idx])
+        assert np.array_equal(ent[b:e, 0], idx) and np.array_equal(ent[b:e, 1], w[t][idx])
+
+
+def test_dedup_rows_groups_identical_records():
+    n, F = 50000, 41
+    stride = fr.tp_stride(F)
+    g = torch.Generator(device=DEV); g.manual_seed(3)
+    base = torch.randint(0, 70, (900, stride), dtype=torch.uint8, device=DEV, generator=g)
+    base[:, F + 1:] = 0
+    pick = torch.randint(0, 900, (n,), device=DEV, generator=g)
+    pick[:20000] = 5                                                                   # one huge duplicate group
+    tp = base[pick].contiguous()
+    cap = 1 << 17
+    table = torch.empty(cap, dtype=torch.int32, device=DEV); minrow = torch.empty(cap, dtype=torch.int32, device=DEV)
+    slot_of = torch.empty(n, dtype=torch.int32, device=DEV); rep = torch.empty(n, dtype=torch.int32, device=DEV)
+    flag = torch.empty(n, dtype=torch.int32, device=DEV); pos = torch.empty(n + 1, dtype=torch.int64, device=DEV)
+    uid = torch.empty(n, dtype=torch.int32, device=DEV); tpu = torch.empty_like(tp); tot = torch.zeros(1, dtype=torch.int64, device=DEV)
+    _lib.call("b200flow_dedup_rows", _lib.ptr(tp), n, stride, F + 1, _lib.ptr(table), _lib.ptr(minrow), cap, _lib.ptr(slot_of),
+              _lib.ptr(rep), _lib.ptr(flag), _lib.ptr(pos), _lib.ptr(tot), _lib.ptr(uid), _lib.ptr(tpu))
+    U = int(tot.item())
+    tp_n, uid_n, tpu_n = tp.cpu().numpy(), uid.cpu().numpy(), tpu.cpu().numpy()[:U]
+    uniq, first, inv = np.unique(tp_n, axis=0, return_index=True, return_inverse=True)
+    assert U == len(uniq)
+    assert np.array_equal(tpu_n[uid_n], tp_n)                                          # every row maps to its own record
+    order = np.argsort(first)                                                          # ids follow each group's first row
+    rank = np.empty(len(uniq), np.int64); rank[order] = np.arange(len(uniq))
+    assert np.array_equal(uid_n, rank[inv.reshape(-1)])
 
 
 def test_scan_large():
@@ -193,7 +230,7 @@ def test_hist_level_direct():
     _lib.call("b200flow_exclusive_scan_i32_to_i64", _lib.ptr(nch), S, _lib.ptr(coff), _lib.ptr(tot))
     sub = torch.stack([torch.sort(torch.randperm(F, device=DEV, generator=g)[:m])[0] for _ in range(S)]).to(torch.int16)
     hist = torch.zeros(S * m * NB * C, dtype=torch.int32, device=DEV)
-    packed = (ent.to(torch.int64) | (w.to(torch.int64) << 27)).to(torch.int32)
+    packed = torch.stack([ent, w.to(torch.int32)], 1).contiguous()                     # {record index, weight} pairs
     _lib.call("b200flow_hist_level", _lib.ptr(tp), stride, F, _lib.ptr(packed), S, _lib.ptr(seg_b), _lib.ptr(seg_e),
               _lib.ptr(coff), int(tot.item()), 2048, _lib.ptr(sub), m, NB, C, _lib.ptr(hist))
     hist = hist.cpu().numpy().reshape(S, m, NB, C)
@@ -289,6 +326,18 @@ def test_unfused_level_loop_equals_fused(monkeypatch):
     b = fr.fit_forest(x, y, C, arity, p).export()
     assert forests_equal(a, b) == []
     assert np.array_equal(a["gain"], b["gain"])
+
+
+def test_dedup_does_not_change_the_forest(monkeypatch):
+    # the level loop on unique records + summed weights must give the forest of the row-by-row loop
+    x, y, arity, C = _features(50000, 5, 71)
+    p = fr.ForestParams(num_trees=6, max_bins=70, max_depth=10, seed=29)
+    m1 = fr.fit_forest(x, y, C, arity, p)
+    assert m1.train_stats["unique_rows"] < 0.8 * m1.train_stats["rows"]                # the synthetic flows do repeat
+    monkeypatch.setattr(fr, "DEDUP", False)
+    m2 = fr.fit_forest(x, y, C, arity, p)
+    assert m2.train_stats["unique_rows"] == m2.train_stats["rows"]
+    assert forests_equal(m1.export(), m2.export()) == [] and np.array_equal(m1.export()["gain"], m2.export()["gain"])
 
 
 def test_forest_fp32_features_equal_fp64_features():
