@@ -458,7 +458,7 @@ struct RouteArgs {
 constexpr int kRouteWarps = kRouteThreads / 32;
 constexpr int kSub = 64;                                    // entries per warp step (2 per lane)
 
-template <int M, int NBUF, bool FULLKEY>
+template <int M, int NBUF, int MERGE>   // MERGE: 0 plain shared atomics, 1 whole-key merge, 2 per-feature merge
 __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_level_kernel(const RouteArgs a) {
     extern __shared__ __align__(16) uint32_t sm_u32[];
     const int m = M > 0 ? M : a.m;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                     uint32_t* hist = sh_hist + side * hsz;
                     const uint32_t lab = (tile[lab_pos + i * 4] >> lab_sh) & 0xffu;
                     const uint32_t w = k ? e1.y : e0.y;
-                    if (M > 0 && FULLKEY) {
+                    if (M > 0 && MERGE == 1) {
                         // whole-key merge: lanes with identical (child, all M bins, label) are combined
                         constexpr int NW = (M + 1 + 3) / 4;
                         uint32_t keys[NW];
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                             for (int j = 0; j < M; ++j)
                                 atomicAdd(&hist[j * nbC + ((keys[j >> 2] >> (8 * (j & 3))) & 0xff) * a.C + lab], sum);
                         }
-                    } else if (M > 0) {
+                    } else if (M > 0 && MERGE == 2) {
                         // per-feature merge: lanes that hit the same (child, feature, bin, label) counter are combined with
                         // match.any; the group's bag-weight sum comes from three ballots shared by all features
                         const uint32_t tag = (lab << 8) | ((uint32_t)side << 16);
@@ -642,8 +642,10 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
 
 static int route_variant() {                                // tuning knob (tile buffers per warp, merge strategy)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;                                               // bit0: 2 tiles per warp, bit1: per-feature merge
+    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? atoi(e) : 4; }
+    return v;        // bit0: 2 tiles per warp; bits 1-2: merge of equal lanes before the shared atomics (0 whole-key, 1 per-feature,
+                     // 2 none).  Default 4 = one tile, no merge: after row de-duplication equal keys inside a warp are rare and
+                     // redux/match cost more than the conflicts they remove (measured: 26 ms vs 46 ms per KDD-full fit)
 }
 
 static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
@@ -810,11 +812,13 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     }
 #define B2F_ROUTE_CASE(MM)                                                                                                     \
     case MM:                                                                                                                   \
-        switch (route_variant() & 3) {                                                                                         \
-            case 0: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, true>)) break;                                            \
-            case 1: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, true>)) break;                                            \
-            case 2: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, false>)) break;                                           \
-            default: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, false>)) break;                                          \
+        switch (route_variant() & 7) {                                                                                         \
+            case 0: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 1>)) break;                                               \
+            case 1: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 1>)) break;                                               \
+            case 2: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 2>)) break;                                               \
+            case 3: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 2>)) break;                                               \
+            case 4: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 0>)) break;                                               \
+            default: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 0>)) break;                                              \
         }                                                                                                                      \
         break;
     switch ((m <= 12 && C <= 128) ? m : 0) {

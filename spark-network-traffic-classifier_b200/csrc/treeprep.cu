@@ -215,30 +215,47 @@ __global__ void __launch_bounds__(256) dedup_emit_kernel(const uint8_t* __restri
 constexpr int kBagBlockRows = 1024;
 
 // W[tree][uid[row]] += Poisson weight of (tree, row).  grid = (row blocks of 1024, tree quads); a thread owns 4 consecutive
-// rows; one Philox call per row yields the weights of the quad's 4 trees.  Rows of one duplicate group are adjacent lanes
-// only by chance, so the adds are global REDs (the hot groups serialise in L2; measured in profiles/).
+// rows; one Philox call per row yields the weights of the quad's 4 trees.  Lanes whose rows belong to the same duplicate
+// group are merged first (match.any on the unique id + three ballots for the weights 1..3), so a hot group — the smurf
+// flood is a third of KDD99 — costs one global RED per warp and tree instead of one per row.
 __global__ void __launch_bounds__(256) bag_weights_kernel(uint64_t seed, int T, int64_t row_offset, int64_t n,
                                                           const uint32_t* __restrict__ cdf, const int32_t* __restrict__ uid, int64_t U,
                                                           uint32_t* W) {
     __shared__ uint32_t cdf_sh[32];
-    const int tq = blockIdx.y;
+    const int tq = blockIdx.y, lane = lane_id();
     if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
     __syncthreads();
     const int64_t rb = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int64_t i = rb + k;
-        if (i >= n) break;
-        const int64_t u = uid ? uid[i] : i;
-        uint32_t w[4] = {1u, 1u, 1u, 1u};
-        if (cdf) {
-            const uint4 r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
-            w[0] = poisson_weight(r.x, cdf_sh); w[1] = poisson_weight(r.y, cdf_sh);
-            w[2] = poisson_weight(r.z, cdf_sh); w[3] = poisson_weight(r.w, cdf_sh);
+        const bool live = i < n;
+        const int64_t u = live ? (uid ? (int64_t)uid[i] : i) : 0;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (live) {
+            if (cdf) {
+                const uint4 r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
+                w[0] = poisson_weight(r.x, cdf_sh); w[1] = poisson_weight(r.y, cdf_sh);
+                w[2] = poisson_weight(r.z, cdf_sh); w[3] = poisson_weight(r.w, cdf_sh);
+            } else { w[0] = w[1] = w[2] = w[3] = 1u; }
         }
+        if (uid) {
+            const uint32_t g = __match_any_sync(0xffffffffu, live ? (int)u : -1 - lane);     // dead lanes form singleton groups
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (tq * 4 + q < T && w[q]) atomicAdd(&W[(int64_t)(tq * 4 + q) * U + u], w[q]);
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t b1 = __ballot_sync(0xffffffffu, w[q] == 1), b2 = __ballot_sync(0xffffffffu, w[q] == 2),
+                               b3 = __ballot_sync(0xffffffffu, w[q] == 3);
+                if (tq * 4 + q >= T || !w[q]) continue;
+                uint32_t* addr = &W[(int64_t)(tq * 4 + q) * U + u];
+                const uint32_t gg = g & (b1 | b2 | b3);
+                if (w[q] > 3) atomicAdd(addr, w[q]);
+                else if ((int)(__ffs(gg) - 1) == lane) atomicAdd(addr, (uint32_t)(__popc(gg & b1) + 2 * __popc(gg & b2) + 3 * __popc(gg & b3)));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (tq * 4 + q < T && w[q]) atomicAdd(&W[(int64_t)(tq * 4 + q) * U + u], w[q]);
+        }
     }
 }
 
