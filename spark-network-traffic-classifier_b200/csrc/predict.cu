@@ -8,8 +8,12 @@
 namespace b200flow {
 
 // ------------------------------------------------------------------ R9 predict
-// One thread per row; the row's bins live in registers-free transposed smem (word k of thread t at
-// [k*blockDim + t]); votes accumulate in fp64 in tree order in smem ([class*blockDim + t]).
+// A thread owns kPredRows rows and walks them through each tree TOGETHER: the walk is a chain of dependent 16-byte node
+// loads (L1/L2 hits: the pool of a 100-tree depth-16 forest is a few MB), so two independent chains per thread double the
+// memory-level parallelism.  A row's bins live in transposed smem (word k of thread t at [k*blockDim + t], conflict-free);
+// votes accumulate in fp64, in tree order, in smem ([class*blockDim + t]).
+constexpr int kPredRows = 2;
+
 __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict__ tp, int stride, int64_t n,
                                                       const b200flow_node* __restrict__ nodes,
                                                       const unsigned long long* __restrict__ node_mask,
@@ -19,42 +23,66 @@ __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict_
     extern __shared__ __align__(16) uint8_t sm[];
     const int bd = blockDim.x, tid = threadIdx.x;
     const int words = stride / 4;
-    uint32_t* binw = (uint32_t*)sm;                               // [words][bd]
-    double* votes = (double*)(sm + (size_t)words * bd * 4);       // [C][bd]
-    for (int64_t base = (int64_t)blockIdx.x * bd; base < n; base += (int64_t)gridDim.x * bd) {
-        const int64_t i = base + tid;
-        const bool live = i < n;
-        if (live) {
-            const uint4* src = (const uint4*)(tp + i * stride);
-            for (int q = 0; q < words / 4; ++q) {
-                uint4 v = ld_stream_u4(src + q);
-                binw[(4 * q + 0) * bd + tid] = v.x; binw[(4 * q + 1) * bd + tid] = v.y;
-                binw[(4 * q + 2) * bd + tid] = v.z; binw[(4 * q + 3) * bd + tid] = v.w;
-            }
-            for (int k = 0; k < C; ++k) votes[k * bd + tid] = 0.0;
-            for (int t = 0; t < T; ++t) {
-                int idx = t;
-                b200flow_node nd = nodes[idx];
-                while (nd.feat >= 0) {
-                    const int f = nd.feat;
-                    const int bin = (binw[(f >> 2) * bd + tid] >> ((f & 3) * 8)) & 0xff;
-                    bool left;
-                    if ((nd.kind_bin >> 16) == 0) left = bin <= (nd.kind_bin & 0xffff);
-                    else left = (node_mask[(int64_t)idx * 4 + (bin >> 6)] >> (bin & 63)) & 1ull;
-                    idx = nd.left + (left ? 0 : 1);
-                    nd = nodes[idx];
+    uint32_t* binw = (uint32_t*)sm;                                           // [kPredRows][words][bd]
+    double* votes = (double*)(sm + (size_t)kPredRows * words * bd * 4);       // [kPredRows][C][bd]
+    for (int64_t base = (int64_t)blockIdx.x * bd * kPredRows; base < n; base += (int64_t)gridDim.x * bd * kPredRows) {
+        int64_t row[kPredRows]; bool live[kPredRows];
+#pragma unroll
+        for (int r = 0; r < kPredRows; ++r) {
+            row[r] = base + (int64_t)r * bd + tid; live[r] = row[r] < n;
+            uint32_t* bw = binw + (size_t)r * words * bd;
+            if (live[r]) {
+                const uint4* src = (const uint4*)(tp + row[r] * stride);
+                for (int q = 0; q < words / 4; ++q) {
+                    const uint4 v = ld_stream_u4(src + q);
+                    bw[(4 * q + 0) * bd + tid] = v.x; bw[(4 * q + 1) * bd + tid] = v.y;
+                    bw[(4 * q + 2) * bd + tid] = v.z; bw[(4 * q + 3) * bd + tid] = v.w;
                 }
-                if (dt_mode) { for (int k = 0; k < C; ++k) votes[k * bd + tid] += (double)pool_counts[(int64_t)idx * C + k]; }
-                else { for (int k = 0; k < C; ++k) votes[k * bd + tid] += leaf_prob[(int64_t)idx * C + k]; }
             }
-            double s = 0.0; int arg = 0; double best = votes[tid];
-            for (int k = 0; k < C; ++k) { double v = votes[k * bd + tid]; s += v; if (v > best) { best = v; arg = k; } }
+            for (int k = 0; k < C; ++k) votes[((size_t)r * C + k) * bd + tid] = 0.0;
+        }
+        for (int t = 0; t < T; ++t) {
+            int idx[kPredRows]; b200flow_node nd[kPredRows];
+#pragma unroll
+            for (int r = 0; r < kPredRows; ++r) { idx[r] = t; nd[r] = nodes[t]; if (!live[r]) nd[r].feat = -1; }
+            bool any = true;
+            while (any) {
+                any = false;
+#pragma unroll
+                for (int r = 0; r < kPredRows; ++r) {
+                    if (nd[r].feat >= 0) {
+                        const int f = nd[r].feat;
+                        const int bin = (binw[((size_t)r * words + (f >> 2)) * bd + tid] >> ((f & 3) * 8)) & 0xff;
+                        bool left;
+                        if ((nd[r].kind_bin >> 16) == 0) left = bin <= (nd[r].kind_bin & 0xffff);
+                        else left = (node_mask[(int64_t)idx[r] * 4 + (bin >> 6)] >> (bin & 63)) & 1ull;
+                        idx[r] = nd[r].left + (left ? 0 : 1);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kPredRows; ++r)
+                    if (nd[r].feat >= 0) { nd[r] = nodes[idx[r]]; any = any || nd[r].feat >= 0; }
+            }
+#pragma unroll
+            for (int r = 0; r < kPredRows; ++r) {
+                if (!live[r]) continue;
+                double* vt = votes + (size_t)r * C * bd + tid;
+                if (dt_mode) { for (int k = 0; k < C; ++k) vt[k * bd] += (double)pool_counts[(int64_t)idx[r] * C + k]; }
+                else { for (int k = 0; k < C; ++k) vt[k * bd] += leaf_prob[(int64_t)idx[r] * C + k]; }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kPredRows; ++r) {
+            if (!live[r]) continue;
+            const double* vt = votes + (size_t)r * C * bd + tid;
+            double s = 0.0; int arg = 0; double best = vt[0];
+            for (int k = 0; k < C; ++k) { const double v = vt[k * bd]; s += v; if (v > best) { best = v; arg = k; } }
             for (int k = 0; k < C; ++k) {
-                double v = votes[k * bd + tid];
-                if (raw) raw[i * C + k] = v;
-                if (prob) prob[i * C + k] = s != 0.0 ? v / s : 0.0;
+                const double v = vt[k * bd];
+                if (raw) raw[row[r] * C + k] = v;
+                if (prob) prob[row[r] * C + k] = s != 0.0 ? v / s : 0.0;
             }
-            pred[i] = (double)arg;
+            pred[row[r]] = (double)arg;
         }
     }
 }
@@ -144,13 +172,13 @@ extern "C" int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_
     B2F_REQUIRE(dt_mode ? pool_counts != nullptr : leaf_prob != nullptr, "predict: missing leaf payload");
     B2F_REQUIRE(((uintptr_t)tp & 15) == 0, "predict: tp must be 16-byte aligned");
     int bd = 128;
-    size_t per_thread = (size_t)tp_stride + (size_t)C * 8;
+    size_t per_thread = ((size_t)tp_stride + (size_t)C * 8) * kPredRows;
     while (bd > 32 && per_thread * bd > 96 * 1024) bd >>= 1;
     size_t smem = per_thread * bd;
     B2F_REQUIRE(smem <= 200 * 1024, "predict: too many classes/features for shared memory");
     cudaError_t e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("predict: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
-    int grid = grid_for(n_rows, bd, kNumSMs * 16);
+    int grid = grid_for(n_rows, bd * kPredRows, kNumSMs * 16);
     predict_kernel<<<grid, bd, smem, (cudaStream_t)stream>>>(tp, tp_stride, n_rows, nodes, (const unsigned long long*)node_mask, leaf_prob,
                                                              pool_counts, T, C, dt_mode, raw, prob, pred);
     return check_launch("predict");

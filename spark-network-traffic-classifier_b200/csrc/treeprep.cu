@@ -7,14 +7,19 @@
 
 namespace b200flow {
 
-// ------------------------------------------------------------------ exclusive scan (single CTA)
+// ------------------------------------------------------------------ exclusive scan
+// Small inputs: one CTA.  Large inputs: three launches without extra scratch — (1) every 4096-element block writes its local
+// exclusive scan and parks its total in the first slot of the NEXT block (whose local value is always 0), (2) one CTA scans
+// those parked totals in place (they become the final value of that slot), (3) every block adds its offset to the rest.
+constexpr int kScanBlock = 4096;
+
 __global__ void __launch_bounds__(1024) scan_i32_i64_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* out,
                                                             int64_t* total) {
     __shared__ int sh[33];
     __shared__ long long carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int64_t base = 0; base < n; base += 4096) {
+    for (int64_t base = 0; base < n; base += kScanBlock) {
         int64_t i0 = base + (int64_t)threadIdx.x * 4;
         int v[4]; int s = 0;
 #pragma unroll
@@ -29,6 +34,57 @@ __global__ void __launch_bounds__(1024) scan_i32_i64_kernel(const int32_t* __res
         __syncthreads();
     }
     if (threadIdx.x == 0) { out[n] = carry; if (total) *total = carry; }
+}
+
+__global__ void __launch_bounds__(1024) scan_local_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* out) {
+    __shared__ int sh[33];
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock;
+    const int64_t i0 = base + (int64_t)threadIdx.x * 4;
+    int v[4]; int s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+    int tot;
+    const int ex = block_exclusive_scan(s, sh, &tot);
+    long long c = ex;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (i0 + k < n && (threadIdx.x | k)) out[i0 + k] = c; c += v[k]; }   // slot 0 belongs to the previous block's total
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) out[0] = 0;
+        const int64_t park = min(n, base + kScanBlock);       // first slot of the next block, or out[n] for the last block
+        out[park] = tot;
+    }
+}
+__global__ void __launch_bounds__(1024) scan_totals_kernel(int64_t n, int64_t n_blocks, int64_t* out, int64_t* total) {
+    __shared__ long long sh_w[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const int64_t b = b0 + threadIdx.x;
+        const int64_t idx = min(n, (b + 1) * (int64_t)kScanBlock);
+        long long v = b < n_blocks ? out[idx] : 0;
+        long long inc = v;                                     // warp inclusive scan (64-bit)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, inc, o); if (lane_id() >= o) inc += u; }
+        if (lane_id() == 31) sh_w[warp_id()] = inc;
+        __syncthreads();
+        long long woff = 0;
+        for (int q = 0; q < warp_id(); ++q) woff += sh_w[q];
+        if (b < n_blocks) out[idx] = carry + woff + inc;       // inclusive prefix = offset of block b+1 (= grand total for the last)
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += woff + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = out[n];
+}
+__global__ void __launch_bounds__(1024) scan_add_kernel(int64_t n, int64_t* out) {
+    const int64_t base = (int64_t)(blockIdx.x + 1) * kScanBlock;    // block 0 needs no offset
+    const long long off = out[base];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = base + (int64_t)threadIdx.x * 4 + k;
+        if (i < n && (threadIdx.x | k)) out[i] += off;
+    }
 }
 
 // ------------------------------------------------------------------ R4 sample rows
@@ -297,7 +353,14 @@ using namespace b200flow;
 
 extern "C" int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* out, int64_t* total, void* stream) {
     B2F_REQUIRE(in && out && n >= 0, "scan: bad arguments");
-    scan_i32_i64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(in, n, out, total);
+    if (n <= 16 * kScanBlock) {
+        scan_i32_i64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(in, n, out, total);
+    } else {
+        const int64_t nb = (n + kScanBlock - 1) / kScanBlock;
+        scan_local_kernel<<<(unsigned)nb, 1024, 0, (cudaStream_t)stream>>>(in, n, out);
+        scan_totals_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, nb, out, total);
+        scan_add_kernel<<<(unsigned)(nb - 1), 1024, 0, (cudaStream_t)stream>>>(n, out);
+    }
     return check_launch("exclusive_scan");
 }
 
