@@ -134,9 +134,18 @@ int b200flow_dedup_rows(const uint8_t* tp, int64_t n_rows, int32_t tp_stride, in
 
 /* R6  BaggedPoint.convertToBaggedRDD: W[tree][uid[row]] += Poisson weight of (tree, global row).  poisson_cdf: 32 increasing
  * uint32 thresholds, weight = #{k: cdf[k] != 2^32-1 && r >= cdf[k]} with r = word tree%4 of Philox(seed,'BAGG', row, tree/4);
- * NULL = no bagging (weight 1 per row, numTrees==1).  uid NULL = identity.  W uint32[T][n_unique], caller zeroes. */
+ * NULL = no bagging (weight 1 per row, numTrees==1); poisson_cdf_host = the same 32 values in host memory (the first
+ * thresholds travel as kernel arguments).  uid NULL = identity.  perm (optional) = the rows grouped by unique id
+ * (b200flow_group_rows); uid is then given in that order (uperm): a duplicate group is a run of adjacent lanes and costs one
+ * RED per warp and tree.  W uint32[T][n_unique], caller zeroes. */
 int b200flow_bag_weights(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows,
-                         const uint32_t* poisson_cdf, const int32_t* uid, int64_t n_unique, uint32_t* W, void* stream);
+                         const uint32_t* poisson_cdf, const uint32_t* poisson_cdf_host,
+                         const int32_t* uid, const int32_t* perm, int64_t n_unique, uint32_t* W, void* stream);
+
+/* counting sort of the rows by unique id: perm[p] = row, uperm[p] = uid[perm[p]] (non-decreasing).  Scratch: gsize/cursor
+ * int32[n_unique], goff int64[n_unique+1]. */
+int b200flow_group_rows(const int32_t* uid, int64_t n_rows, int64_t n_unique, int32_t* gsize, int64_t* goff,
+                        int32_t* cursor, int32_t* perm, int32_t* uperm, void* stream);
 
 /* entries of every tree = its non-zero (unique record, summed weight) pairs in unique-id order.  Pass 1: non-zeros per
  * (tree, block of 1024 uniques) -> blk_cnt[T][n_blocks]. */
@@ -269,6 +278,10 @@ int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_rows,
                      const double* leaf_prob, const uint32_t* pool_counts,
                      int32_t T, int32_t C, int32_t dt_mode,
                      double* raw, double* prob, double* pred, void* stream);
+
+/* out[i] = src[idx[i]] for rows of row_bytes (multiple of 4): spreads the predictions computed once per UNIQUE test record
+ * (b200flow_dedup_rows) back to the rows. */
+int b200flow_gather_rows(const void* src, int32_t row_bytes, const int32_t* idx, int64_t n_rows, void* out, void* stream);
 
 /* R10 MulticlassMetrics: confusion matrix cm[label*C + pred] += 1 (int64, caller zeroes).
  * pred / label are fp64 columns (as in the prediction DataFrame). */

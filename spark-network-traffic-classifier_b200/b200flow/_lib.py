@@ -38,7 +38,8 @@ _SIGNATURES = {
     "b200flow_find_splits": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P],
     "b200flow_bin_rows": [_P, _I32, _I64, _I32, _I64, _P, _P, _P, _I32, _P, _P, _I32, _P, _P],
     "b200flow_dedup_rows": [_P, _I64, _I32, _I32, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P],
-    "b200flow_bag_weights": [_U64, _I32, _I64, _I64, _P, _P, _I64, _P, _P],
+    "b200flow_bag_weights": [_U64, _I32, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P],
+    "b200flow_group_rows": [_P, _I64, _I64, _P, _P, _P, _P, _P, _P],
     "b200flow_bag_count": [_P, _I32, _I64, _P, _P],
     "b200flow_bag_fill": [_P, _I32, _I64, _P, _P, _P],
     "b200flow_exclusive_scan_i32_to_i64": [_P, _I64, _P, _P, _P],
@@ -52,6 +53,7 @@ _SIGNATURES = {
     "b200flow_next_segments": [_I32, _P, _P, _P, _P, _P, _P, _P],
     "b200flow_finalize_forest": [_I64, _P, _I32, _P, _P],
     "b200flow_predict": [_P, _I32, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
+    "b200flow_gather_rows": [_P, _I32, _P, _I64, _P, _P],
     "b200flow_confusion": [_P, _P, _I64, _I32, _P, _P],
     "b200flow_random_split": [_U64, _I64, _I64, _P, _I32, _P, _P],
     "b200flow_compact_rows": [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P],
@@ -60,7 +62,7 @@ EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version",
 
 _lib = None
 launches = 0   # kernels of OURS launched so far (counted per C-ABI call); bench.py reads the delta over the timed region
-_KERNELS_PER_CALL = {"b200flow_grow_level": 3, "b200flow_compact_rows": 3, "b200flow_route_hist_level": 2, "b200flow_dedup_rows": 5}
+_KERNELS_PER_CALL = {"b200flow_grow_level": 3, "b200flow_compact_rows": 3, "b200flow_route_hist_level": 2, "b200flow_dedup_rows": 5, "b200flow_group_rows": 3}
 
 
 def load():

@@ -115,6 +115,25 @@ def build_metadata(n_rows, F, num_classes, arity, max_bins, num_trees, strategy=
     return mpb, kind, max(1, min(m, F))
 
 
+def dedup_rows(tp, key_bytes):
+    """unique TreePoint records of a binned batch: -> (tp_unique [U, stride], uid int32 [n], U).  Flow records repeat
+    massively (KDD99: 4.9 M rows, ~1.07 M distinct), so both the level loop and the batch predictor run per unique record."""
+    n, stride = tp.shape
+    dev = tp.device
+    cap_tab = 1
+    while cap_tab < 2 * n:
+        cap_tab <<= 1
+    table = torch.empty(cap_tab, dtype=torch.int32, device=dev); minrow = torch.empty(cap_tab, dtype=torch.int32, device=dev)
+    slot_of = torch.empty(n, dtype=torch.int32, device=dev); rep = torch.empty(n, dtype=torch.int32, device=dev)
+    flag = torch.empty(n, dtype=torch.int32, device=dev); pos = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    uid = torch.empty(n, dtype=torch.int32, device=dev); total = torch.zeros(1, dtype=torch.int64, device=dev)
+    tpu = torch.empty_like(tp)
+    _timed("dedup_rows", "b200flow_dedup_rows", ptr(tp), n, stride, key_bytes, ptr(table), ptr(minrow), cap_tab, ptr(slot_of), ptr(rep),
+           ptr(flag), ptr(pos), ptr(total), ptr(uid), ptr(tpu))
+    U = int(total.item())
+    return tpu[:U], uid, U
+
+
 def _i32(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(dev)
 
@@ -154,9 +173,22 @@ class ForestModel:
         return raw, prob, pred
 
     def predict(self, x, want_raw=True, want_prob=True):
-        """RandomForestClassificationModel.transform (R9): rawPrediction, probability, prediction."""
+        """RandomForestClassificationModel.transform (R9): rawPrediction, probability, prediction.  The trees are walked
+        once per UNIQUE binned record; the results are then spread back to the rows."""
         tp, _ = self.bin(x)
-        return self.predict_binned(tp, want_raw, want_prob)
+        n = tp.shape[0]
+        if not DEDUP or n == 0:
+            return self.predict_binned(tp, want_raw, want_prob)
+        tpu, uid, U = dedup_rows(tp, self.F)                 # the label byte is not part of a test record's identity
+        raw_u, prob_u, pred_u = self.predict_binned(tpu, want_raw, want_prob)
+
+        def spread(src, width):
+            if src is None:
+                return None
+            out = torch.empty((n, width) if width > 1 else (n,), dtype=torch.float64, device=tp.device)
+            call("b200flow_gather_rows", ptr(src), 8 * width, ptr(uid), n, ptr(out))
+            return out
+        return spread(raw_u, self.C), spread(prob_u, self.C), spread(pred_u, 1)
 
     def export(self):
         """Canonical host copy, nodes ordered by (tree, MLlib node id) — what parity tests compare."""
@@ -279,28 +311,24 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     # ---- de-duplicate the binned rows: the level loop runs on UNIQUE TreePoint records carrying summed bag weights
     total = torch.zeros(1, dtype=torch.int64, device=dev)
     if n > 0 and DEDUP:
-        cap_tab = 1
-        while cap_tab < 2 * n:
-            cap_tab <<= 1
-        table = torch.empty(cap_tab, dtype=torch.int32, device=dev); minrow = torch.empty(cap_tab, dtype=torch.int32, device=dev)
-        slot_of = torch.empty(n, dtype=torch.int32, device=dev); rep = torch.empty(n, dtype=torch.int32, device=dev)
-        flag = torch.empty(n, dtype=torch.int32, device=dev); pos = torch.empty(n + 1, dtype=torch.int64, device=dev)
-        uid = torch.empty(n, dtype=torch.int32, device=dev)
-        tpu = torch.empty_like(tp)
-        _timed("dedup_rows", "b200flow_dedup_rows", ptr(tp), n, stride, F + 1, ptr(table), ptr(minrow), cap_tab, ptr(slot_of), ptr(rep),
-               ptr(flag), ptr(pos), ptr(total), ptr(uid), ptr(tpu))
-        U = int(total.item())
-        tp = tpu[:U]
-        del table, minrow, slot_of, rep, flag, pos, tpu
+        tp, uid, U = dedup_rows(tp, F + 1)
     else:
         uid, U = None, n
     # ---- R6 bagging: W[tree][unique] = summed Poisson weights; entries = non-zero (unique, weight) pairs per tree
     bagging = p.bootstrap and T > 1
-    cdf = torch.from_numpy(poisson_cdf_table(p.subsampling_rate).view(np.int32).copy()).to(dev) if bagging else None
+    cdf_host = np.ascontiguousarray(poisson_cdf_table(p.subsampling_rate)) if bagging else None
+    cdf = torch.from_numpy(cdf_host.view(np.int32).copy()).to(dev) if bagging else None
     nb = (U + 1023) // 1024
     W = torch.zeros(max(T * U, 1), dtype=torch.int32, device=dev)
     if n > 0:
-        _timed("bag_weights", "b200flow_bag_weights", seed, T, int(row_offset), n, ptr(cdf), ptr(uid), U, ptr(W))
+        perm = uperm = None
+        if uid is not None and bagging and U < n:           # group the rows by unique id: one RED per (warp run, tree)
+            gsize = torch.empty(U, dtype=torch.int32, device=dev); cursor = torch.empty(U, dtype=torch.int32, device=dev)
+            goff = torch.empty(U + 1, dtype=torch.int64, device=dev)
+            perm = torch.empty(n, dtype=torch.int32, device=dev); uperm = torch.empty(n, dtype=torch.int32, device=dev)
+            _timed("group_rows", "b200flow_group_rows", ptr(uid), n, U, ptr(gsize), ptr(goff), ptr(cursor), ptr(perm), ptr(uperm))
+        _timed("bag_weights", "b200flow_bag_weights", seed, T, int(row_offset), n, ptr(cdf),
+               cdf_host.ctypes.data if bagging else None, ptr(uperm if perm is not None else uid), ptr(perm), U, ptr(W))
     blk_cnt = torch.zeros(max(T * nb, 1), dtype=torch.int32, device=dev)
     blk_off = torch.zeros(T * nb + 1, dtype=torch.int64, device=dev)
     if U > 0:

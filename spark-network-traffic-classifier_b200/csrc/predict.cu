@@ -41,27 +41,29 @@ __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict_
             }
             for (int k = 0; k < C; ++k) votes[((size_t)r * C + k) * bd + tid] = 0.0;
         }
+        const uint32_t* bw0 = binw + tid;                                   // this thread's column of the transposed bins
+        const int4* nodes4 = (const int4*)nodes;                            // {feat, kind<<16|bin, left, nid}
         for (int t = 0; t < T; ++t) {
-            int idx[kPredRows]; b200flow_node nd[kPredRows];
+            int idx[kPredRows]; int4 nd[kPredRows];
 #pragma unroll
-            for (int r = 0; r < kPredRows; ++r) { idx[r] = t; nd[r] = nodes[t]; if (!live[r]) nd[r].feat = -1; }
-            bool any = true;
-            while (any) {
-                any = false;
+            for (int r = 0; r < kPredRows; ++r) { idx[r] = t; nd[r] = __ldg(nodes4 + t); if (!live[r]) nd[r].x = -1; }
+            while (true) {
+                bool any = false;
 #pragma unroll
                 for (int r = 0; r < kPredRows; ++r) {
-                    if (nd[r].feat >= 0) {
-                        const int f = nd[r].feat;
-                        const int bin = (binw[((size_t)r * words + (f >> 2)) * bd + tid] >> ((f & 3) * 8)) & 0xff;
-                        bool left;
-                        if ((nd[r].kind_bin >> 16) == 0) left = bin <= (nd[r].kind_bin & 0xffff);
-                        else left = (node_mask[(int64_t)idx[r] * 4 + (bin >> 6)] >> (bin & 63)) & 1ull;
-                        idx[r] = nd[r].left + (left ? 0 : 1);
+                    if (nd[r].x >= 0) {
+                        const int f = nd[r].x;
+                        const int bin = (bw0[(r * words + (f >> 2)) * bd] >> ((f & 3) * 8)) & 0xff;
+                        const int right = nd[r].y < 65536 ? (bin > nd[r].y)
+                                                          : !((node_mask[(int64_t)idx[r] * 4 + (bin >> 6)] >> (bin & 63)) & 1ull);
+                        idx[r] = nd[r].z + right;
+                        any = true;
                     }
                 }
+                if (!any) break;
 #pragma unroll
                 for (int r = 0; r < kPredRows; ++r)
-                    if (nd[r].feat >= 0) { nd[r] = nodes[idx[r]]; any = any || nd[r].feat >= 0; }
+                    if (nd[r].x >= 0) nd[r] = __ldg(nodes4 + idx[r]);
             }
 #pragma unroll
             for (int r = 0; r < kPredRows; ++r) {
@@ -84,6 +86,16 @@ __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict_
             }
             pred[row[r]] = (double)arg;
         }
+    }
+}
+
+// ------------------------------------------------------------------ row gather (predictions of unique records -> rows)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint32_t* __restrict__ src, int words, const int32_t* __restrict__ idx,
+                                                          int64_t n, uint32_t* out) {
+    const int64_t total = n * words;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / words; const int w = (int)(e - r * words);
+        out[e] = __ldg(src + (int64_t)idx[r] * words + w);
     }
 }
 
@@ -182,6 +194,14 @@ extern "C" int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_
     predict_kernel<<<grid, bd, smem, (cudaStream_t)stream>>>(tp, tp_stride, n_rows, nodes, (const unsigned long long*)node_mask, leaf_prob,
                                                              pool_counts, T, C, dt_mode, raw, prob, pred);
     return check_launch("predict");
+}
+
+extern "C" int b200flow_gather_rows(const void* src, int32_t row_bytes, const int32_t* idx, int64_t n_rows, void* out, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(src && idx && out && row_bytes > 0 && (row_bytes & 3) == 0, "gather_rows: bad arguments");
+    const int words = row_bytes / 4;
+    gather_rows_kernel<<<grid_for(n_rows * words, 256 * 4, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, words, idx, n_rows, (uint32_t*)out);
+    return check_launch("gather_rows");
 }
 
 extern "C" int b200flow_confusion(const double* pred, const double* label, int64_t n_rows, int32_t C, int64_t* cm, void* stream) {

@@ -267,6 +267,28 @@ __global__ void __launch_bounds__(256) dedup_emit_kernel(const uint8_t* __restri
     }
 }
 
+// rows grouped by unique id (counting sort): perm[p] = row, uperm[p] = its unique id, non-decreasing in p.  With the rows of
+// a duplicate group adjacent, bag_weights merges a whole group inside a warp and issues ONE global RED per (warp-run, tree)
+// instead of one per row.  Atomics on the group counters are warp-aggregated (match.any on the id).
+__global__ void __launch_bounds__(256) group_count_kernel(const int32_t* __restrict__ uid, int64_t n, int32_t* gsize) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int u = i < n ? uid[i] : -1 - (int)lane_id();
+    const uint32_t g = __match_any_sync(0xffffffffu, u);
+    if (i < n && (int)(__ffs(g) - 1) == lane_id()) atomicAdd(&gsize[u], __popc(g));
+}
+__global__ void __launch_bounds__(256) group_fill_kernel(const int32_t* __restrict__ uid, int64_t n, const int64_t* __restrict__ goff,
+                                                         int32_t* cursor, int32_t* perm, int32_t* uperm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = lane_id();
+    const int u = i < n ? uid[i] : -1 - lane;
+    const uint32_t g = __match_any_sync(0xffffffffu, u);
+    const int leader = __ffs(g) - 1;
+    int base = 0;
+    if (i < n && leader == lane) base = atomicAdd(&cursor[u], __popc(g));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n) { const int64_t p = goff[u] + base + __popc(g & ((1u << lane) - 1u)); perm[p] = (int32_t)i; uperm[p] = u; }
+}
+
 // ------------------------------------------------------------------ R6 bagging
 constexpr int kBagBlockRows = 1024;
 
@@ -274,25 +296,36 @@ constexpr int kBagBlockRows = 1024;
 // rows; one Philox call per row yields the weights of the quad's 4 trees.  Lanes whose rows belong to the same duplicate
 // group are merged first (match.any on the unique id + three ballots for the weights 1..3), so a hot group — the smurf
 // flood is a third of KDD99 — costs one global RED per warp and tree instead of one per row.
+struct CdfHead { uint32_t c[6]; };       // first thresholds of the inverse CDF, passed by value (uniform registers)
+
+__device__ __forceinline__ uint32_t poisson_weight_fast(uint32_t r, const CdfHead& h, const uint32_t* cdf_sh) {
+    uint32_t k = (r >= h.c[0]) + (r >= h.c[1]) + (r >= h.c[2]) + (r >= h.c[3]) + (r >= h.c[4]) + (r >= h.c[5]);   // increasing thresholds
+    if (k == 6) while (k < 32 && cdf_sh[k] != 0xFFFFFFFFu && r >= cdf_sh[k]) ++k;                                 // P(w >= 6) = 6e-4 at lambda = 1
+    return k;
+}
+
 __global__ void __launch_bounds__(256) bag_weights_kernel(uint64_t seed, int T, int64_t row_offset, int64_t n,
-                                                          const uint32_t* __restrict__ cdf, const int32_t* __restrict__ uid, int64_t U,
-                                                          uint32_t* W) {
+                                                          const uint32_t* __restrict__ cdf, const CdfHead head,
+                                                          const int32_t* __restrict__ uid, const int32_t* __restrict__ perm,
+                                                          int64_t U, uint32_t* W) {
     __shared__ uint32_t cdf_sh[32];
     const int tq = blockIdx.y, lane = lane_id();
     if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
     __syncthreads();
-    const int64_t rb = (int64_t)blockIdx.x * kBagBlockRows + threadIdx.x * 4;
+    // position p of the (optionally grouped) order: lane-consecutive positions so that a duplicate group is a run of lanes
+    const int64_t pb = (int64_t)blockIdx.x * kBagBlockRows + (threadIdx.x >> 5) * 128 + lane;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int64_t i = rb + k;
-        const bool live = i < n;
-        const int64_t u = live ? (uid ? (int64_t)uid[i] : i) : 0;
+        const int64_t p = pb + k * 32;
+        const bool live = p < n;
+        const int64_t i = live ? (perm ? (int64_t)perm[p] : p) : 0;          // the row behind position p
+        const int64_t u = live ? (uid ? (int64_t)uid[p] : i) : 0;            // uid is given in POSITION order when perm is
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (live) {
             if (cdf) {
                 const uint4 r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
-                w[0] = poisson_weight(r.x, cdf_sh); w[1] = poisson_weight(r.y, cdf_sh);
-                w[2] = poisson_weight(r.z, cdf_sh); w[3] = poisson_weight(r.w, cdf_sh);
+                w[0] = poisson_weight_fast(r.x, head, cdf_sh); w[1] = poisson_weight_fast(r.y, head, cdf_sh);
+                w[2] = poisson_weight_fast(r.z, head, cdf_sh); w[3] = poisson_weight_fast(r.w, head, cdf_sh);
             } else { w[0] = w[1] = w[2] = w[3] = 1u; }
         }
         if (uid) {
@@ -438,13 +471,32 @@ extern "C" int b200flow_dedup_rows(const uint8_t* tp, int64_t n_rows, int32_t tp
     return check_launch("dedup_rows");
 }
 
+extern "C" int b200flow_group_rows(const int32_t* uid, int64_t n_rows, int64_t n_unique, int32_t* gsize, int64_t* goff, int32_t* cursor,
+                                   int32_t* perm, int32_t* uperm, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(uid && gsize && goff && cursor && perm && uperm && n_unique > 0, "group_rows: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(gsize, 0, (size_t)n_unique * 4, st);
+    cudaMemsetAsync(cursor, 0, (size_t)n_unique * 4, st);
+    const unsigned grid = (unsigned)((n_rows + 255) / 256);
+    group_count_kernel<<<grid, 256, 0, st>>>(uid, n_rows, gsize);
+    int rc = b200flow_exclusive_scan_i32_to_i64(gsize, n_unique, goff, nullptr, stream);
+    if (rc) return rc;
+    group_fill_kernel<<<grid, 256, 0, st>>>(uid, n_rows, goff, cursor, perm, uperm);
+    return check_launch("group_rows");
+}
+
 extern "C" int b200flow_bag_weights(uint64_t seed, int32_t T, int64_t row_offset, int64_t n_rows, const uint32_t* poisson_cdf,
-                                    const int32_t* uid, int64_t n_unique, uint32_t* W, void* stream) {
+                                    const uint32_t* poisson_cdf_host, const int32_t* uid, const int32_t* perm, int64_t n_unique,
+                                    uint32_t* W, void* stream) {
     if (n_rows <= 0) return B200FLOW_OK;
     B2F_REQUIRE(W && T > 0 && T <= 65535 * 4 && n_unique > 0, "bag_weights: bad arguments");
+    B2F_REQUIRE((poisson_cdf == nullptr) == (poisson_cdf_host == nullptr), "bag_weights: pass the CDF table both as device and host pointer");
+    CdfHead head;
+    for (int k = 0; k < 6; ++k) head.c[k] = poisson_cdf_host ? poisson_cdf_host[k] : 0xFFFFFFFFu;
     const int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
-    bag_weights_kernel<<<dim3((unsigned)nb, (unsigned)((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, uid,
-                                                                                                   n_unique, W);
+    bag_weights_kernel<<<dim3((unsigned)nb, (unsigned)((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, head,
+                                                                                                   uid, perm, n_unique, W);
     return check_launch("bag_weights");
 }
 

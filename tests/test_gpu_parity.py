@@ -139,16 +139,26 @@ def test_bagging_weights_and_entries_match_oracle():
     w = oracle.bag_weights(seed, T, n, cdf, row_offset=17)
     cdf_t = torch.from_numpy(cdf.view(np.int32).copy()).to(DEV)
     W = torch.zeros(T * n, dtype=torch.int32, device=DEV)
-    _lib.call("b200flow_bag_weights", seed, T, 17, n, _lib.ptr(cdf_t), None, n, _lib.ptr(W))       # identity uid
+    _lib.call("b200flow_bag_weights", seed, T, 17, n, _lib.ptr(cdf_t), cdf.ctypes.data, None, None, n, _lib.ptr(W))       # identity uid
     assert np.array_equal(W.cpu().numpy().reshape(T, n), w.astype(np.int32))
     # duplicate groups: weights of the rows of a group are summed into its unique record
     uid = torch.randint(0, 37, (n,), dtype=torch.int32, device=DEV)
     W2 = torch.zeros(T * 37, dtype=torch.int32, device=DEV)
-    _lib.call("b200flow_bag_weights", seed, T, 17, n, _lib.ptr(cdf_t), _lib.ptr(uid), 37, _lib.ptr(W2))
+    _lib.call("b200flow_bag_weights", seed, T, 17, n, _lib.ptr(cdf_t), cdf.ctypes.data, _lib.ptr(uid), None, 37, _lib.ptr(W2))
     want = np.zeros((T, 37), np.int64)
     for t in range(T):
         np.add.at(want[t], uid.cpu().numpy(), w[t])
     assert np.array_equal(W2.cpu().numpy().reshape(T, 37), want)
+    # the same through the grouped order (rows of a group adjacent): identical sums
+    gsize = torch.empty(37, dtype=torch.int32, device=DEV); cursor = torch.empty(37, dtype=torch.int32, device=DEV)
+    goff = torch.empty(38, dtype=torch.int64, device=DEV)
+    perm = torch.empty(n, dtype=torch.int32, device=DEV); uperm = torch.empty(n, dtype=torch.int32, device=DEV)
+    _lib.call("b200flow_group_rows", _lib.ptr(uid), n, 37, _lib.ptr(gsize), _lib.ptr(goff), _lib.ptr(cursor), _lib.ptr(perm), _lib.ptr(uperm))
+    assert torch.equal(torch.sort(perm)[0], torch.arange(n, dtype=torch.int32, device=DEV)) and torch.equal(uperm, uid[perm.long()])
+    assert bool((uperm[1:] >= uperm[:-1]).all())
+    W3 = torch.zeros(T * 37, dtype=torch.int32, device=DEV)
+    _lib.call("b200flow_bag_weights", seed, T, 17, n, _lib.ptr(cdf_t), cdf.ctypes.data, _lib.ptr(uperm), _lib.ptr(perm), 37, _lib.ptr(W3))
+    assert torch.equal(W3, W2)
     # entries = non-zero (unique, weight) pairs per tree, in unique-id order
     nb = (n + 1023) // 1024
     blk = torch.zeros(T * nb, dtype=torch.int32, device=DEV)
