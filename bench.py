@@ -303,7 +303,7 @@ def main():
         "bin_rows": (ntr_rows + nte) * (41 * 4 + 64),
         "hist_level": ent_per_step * (4 + 1) + min(ent_per_step, float(ntr_rows) * kern.get("hist_level", {}).get("launches_per_step", 1)) * (F + 1),
         "partition_level": ent_per_step * (4 + 1 + 1 + 5),
-        "route_hist_level": route_entries / a.steps * (4 + 1 + (F + 1) + 4 + 1),
+        "route_hist_level": route_entries / a.steps * (8 + (F + 1) + 8),      # entry in + TreePoint gather + entry out
         "predict": nte * (64 + 8 + 2 * 8 * a.classes),
     }
     for k in kern:
@@ -320,8 +320,9 @@ def main():
                 "frac": d.get("frac_of_hbm_peak"), "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": d["launches_per_step"], "avg_launch_ms": d["ms_per_step"] / max(d["launches_per_step"], 1),
                 "share_of_step": d["share_of_step"],
-                "note": "achieved = algorithmic bytes / CUDA-event kernel time inside the timed steps; the histogram kernel is "
-                        "shared-memory-atomic bound, not HBM bound (DESIGN.md)"}
+                "note": "achieved = algorithmic bytes / CUDA-event kernel time inside the timed steps; after row de-duplication the "
+                        "unique TreePoints (~80 MB) are L2-resident and the level kernel is bound by shared-memory atomic "
+                        "throughput (1 lane/clk/SM), not by HBM (DESIGN.md section 3)"}
 
     # ---- CPU baseline (oracle, bounded sample) ---------------------------------------------------------
     cpu = None
@@ -339,6 +340,7 @@ def main():
             "dtype": "u8 bins / uint32 histograms / f64 split scoring (f32 feature matrix)", "data": "synthetic",
             "config": workload_config(a, world), "macro_f1": f1, "forest_nodes": n_nodes,
             "train_levels": stats["levels"], "bagged_entries": stats["entries"],
+            "train_rows": stats.get("rows"), "unique_binned_rows": stats.get("unique_rows"),
             "clocks": sampler.summary() if sampler else None, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "kernels": kern, "cpu_baseline": cpu}
     print(json.dumps(line))
