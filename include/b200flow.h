@@ -253,14 +253,17 @@ int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, in
 int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
                               const void* ent, void* ent_out,
                               int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
-                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
+                              const int64_t* chunk_off, const int64_t* n_chunks_dev /* = chunk_off[n_slots], on the device */,
+                              int64_t n_chunks_max /* host upper bound: sizes the scratch and the table launch */,
+                              int32_t chunk_rows,
                               const b200flow_split* split, const int32_t* child_slot, int32_t* cursors,
-                              void* chunk_scratch /* 16 bytes per chunk, 16-byte aligned */,
+                              void* chunk_scratch /* 16 bytes per chunk (n_chunks_max), 16-byte aligned */,
                               const uint16_t* subset_next, int32_t m, int32_t n_bins, int32_t C,
                               uint32_t* hist_next, void* stream);
 
 /* segment table of the next level from the parents' ranges and the partition cursors */
-int b200flow_next_segments(int32_t n_next, const int32_t* next_parent,
+int b200flow_next_segments(int32_t n_next /* or an upper bound */, const int64_t* n_next_dev /* NULL or the device-side count */,
+                           const int32_t* next_parent,
                            const int64_t* seg_begin, const int64_t* seg_end,
                            const int32_t* cursors, int64_t* next_begin, int64_t* next_end,
                            void* stream);

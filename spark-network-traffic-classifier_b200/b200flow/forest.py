@@ -23,6 +23,7 @@ import os as _os
 ROUTE_CHUNK_ROWS = int(_os.environ.get("B200FLOW_ROUTE_CHUNK", "512"))   # entries per CTA in the fused route_hist_level kernel
 FUSED = True                       # use route_hist_level (partition + next-level histogram in one pass) when it fits
 DEDUP = True                       # run the level loop on unique binned records (flow records repeat massively)
+_PIN = True                        # read the per-level counts into pinned host memory
 PROFILE = None                     # set to a dict to collect per-kernel CUDA-event timings (bench.py)
 
 
@@ -409,17 +410,23 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
             PROFILE.setdefault("_route_entries", []).append(torch.where(routed, lens_, torch.zeros_like(lens_)).sum())
         return roff
 
-    def run_route(roff, rch, n_parents, split_, child_slot_, cursors_, next_subset_, n_next_):
-        """fused pass: route the entries of the planned parent slots to their children and build the children's
-        histograms (returns the zero-initialised, now filled, histogram buffer of the next level)."""
-        hist_next = torch.zeros(n_next_ * hsz, dtype=torch.int32, device=dev)
-        scratch = torch.empty(max(rch, 1) * 4, dtype=torch.int32, device=dev)
+    route_chunks_max = E // route_ch + 1                 # + one ragged chunk per parent slot, added per call
+
+    def run_route(roff, rch_dev, n_parents, split_, child_slot_, cursors_, next_subset_, n_next_cap):
+        """fused pass: route the entries of the planned parent slots to their children and build the children's histograms
+        (returns the zero-initialised, now filled, histogram buffer of the next level).  The chunk count stays on the device
+        (rch_dev), so the pass can be enqueued before the host knows how many children were created."""
+        hist_next = torch.zeros(n_next_cap * hsz, dtype=torch.int32, device=dev)
+        cmax = route_chunks_max + n_parents
+        scratch = torch.empty(cmax * 4, dtype=torch.int32, device=dev)
         _timed("route_hist_level", "b200flow_route_hist_level", ptr(tp), stride, F, ptr(ent), ptr(ent2), n_parents,
-               ptr(seg_begin), ptr(seg_end), ptr(roff), rch, route_ch, ptr(split_), ptr(child_slot_), ptr(cursors_), ptr(scratch),
-               ptr(next_subset_), m, n_bins, C, ptr(hist_next))
+               ptr(seg_begin), ptr(seg_end), ptr(roff), ptr(rch_dev), cmax, route_ch, ptr(split_), ptr(child_slot_), ptr(cursors_),
+               ptr(scratch), ptr(next_subset_), m, n_bins, C, ptr(hist_next))
         stats["hist_launches"] += 1
         return hist_next
 
+    side_stream = torch.cuda.Stream(device=dev)
+    host_cnt = torch.empty(5, dtype=torch.int64).pin_memory() if _PIN else None
     subset = level_subsets(n_slots, slot_tree, slot_nid)
     hist_ready = None                  # histogram of the CURRENT level when the fused kernel already built it
     if fused and n_slots * hsz * 4 <= HIST_BUDGET_BYTES and E > 0:
@@ -430,7 +437,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                               torch.full((T,), -1, dtype=torch.int32, device=dev)], 1).contiguous().view(-1)
         cursors0 = torch.zeros(2 * T, dtype=torch.int32, device=dev)
         roff0 = plan_route(torch.ones(T, dtype=torch.bool, device=dev), seg_end - seg_begin, total)
-        hist_ready = run_route(roff0, int(total.item()), T, pseudo_t, child0, cursors0, subset, T)
+        hist_ready = run_route(roff0, total, T, pseudo_t, child0, cursors0, subset, T)
         ent, ent2 = ent2, ent          # the pass copied every entry into the other buffer, same segments
     while n_slots > 0:
         grow_pool(pool_size + 2 * n_slots)
@@ -483,12 +490,30 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                ptr(left_counts), ptr(right_counts), C, ptr(nodes), ptr(node_mask), ptr(pool_counts), ptr(node_tree),
                cap_nodes, ptr(next_tree), ptr(next_nid), ptr(next_node), ptr(next_parent), ptr(child_slot), ptr(counters))
         node_gain[slot_node.long()] = split.view(torch.float64)[:, 2]
-        roff = None
-        if fused:                                       # plan the routing pass before the level's only host sync
+        n_cap = 2 * n_slots                              # upper bound on the number of next-level slots
+        speculative = fused and n_cap * hsz * 4 <= HIST_BUDGET_BYTES
+        if speculative:
+            # Everything the next level needs is enqueued NOW with device-side counts (children created, routing chunks);
+            # the host reads the counts on a side stream while the routing pass runs, so the GPU never waits for Python.
+            ev_grown = torch.cuda.Event(); ev_grown.record()
             flags = split.view(torch.int32)[:, 3]
             routed = ((flags & 1) == 0) & ((flags & 6) != 6)          # split parents with at least one non-leaf child
             roff = plan_route(routed, lens, counters[4:5])
-        cnt = counters[:5].cpu()
+            ev_planned = torch.cuda.Event(); ev_planned.record()
+            with torch.cuda.stream(side_stream):
+                side_stream.wait_event(ev_planned)
+                cnt = counters[:5].to("cpu", non_blocking=True) if host_cnt is None else host_cnt.copy_(counters[:5], non_blocking=True)
+                ev_read = torch.cuda.Event(); ev_read.record(side_stream)
+            next_subset = level_subsets(n_cap, next_tree, next_nid)
+            cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
+            hist_next = run_route(roff, counters[4:5], n_slots, split, child_slot, cursors, next_subset, n_cap)
+            next_begin = torch.empty(n_cap, dtype=torch.int64, device=dev)
+            next_end = torch.empty(n_cap, dtype=torch.int64, device=dev)
+            call("b200flow_next_segments", n_cap, ptr(counters[1:2]), ptr(next_parent), ptr(seg_begin), ptr(seg_end), ptr(cursors),
+                 ptr(next_begin), ptr(next_end))
+            ev_read.synchronize()
+        else:
+            cnt = counters[:5].cpu()
         if int(cnt[2]) != 0:
             raise B200FlowError("node pool overflow (capacity %d)" % cap_nodes)
         pool_size, n_next = int(cnt[0]), int(cnt[1])
@@ -496,21 +521,21 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         if n_next == 0:
             break
         next_tree, next_nid, next_node = next_tree[:n_next], next_nid[:n_next], next_node[:n_next]
-        next_subset = level_subsets(n_next, next_tree, next_nid)
-        cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
-        if fused and n_next * hsz * 4 <= HIST_BUDGET_BYTES:
-            # route every entry to its child AND build the children's histograms in the same pass
-            hist_ready = run_route(roff, int(cnt[4]), n_slots, split, child_slot, cursors, next_subset, n_next)
+        if speculative:
+            hist_ready = hist_next
+            next_subset, next_begin, next_end = next_subset[:n_next], next_begin[:n_next], next_end[:n_next]
         else:
+            next_subset = level_subsets(n_next, next_tree, next_nid)
+            cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
             if chunk_off is None:
                 nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()
                 chunk_off, n_chunks = chunk_table(nch)
             _timed("partition_level", "b200flow_partition_level", ptr(tp), stride, ptr(ent), ptr(ent2),
                    n_slots, ptr(seg_begin), ptr(seg_end), ptr(chunk_off), n_chunks, CHUNK_ROWS, ptr(split), ptr(cursors))
-        next_begin = torch.empty(n_next, dtype=torch.int64, device=dev)
-        next_end = torch.empty(n_next, dtype=torch.int64, device=dev)
-        call("b200flow_next_segments", n_next, ptr(next_parent), ptr(seg_begin), ptr(seg_end), ptr(cursors),
-             ptr(next_begin), ptr(next_end))
+            next_begin = torch.empty(n_next, dtype=torch.int64, device=dev)
+            next_end = torch.empty(n_next, dtype=torch.int64, device=dev)
+            call("b200flow_next_segments", n_next, None, ptr(next_parent), ptr(seg_begin), ptr(seg_end), ptr(cursors),
+                 ptr(next_begin), ptr(next_end))
         ent, ent2 = ent2, ent
         slot_tree, slot_nid, slot_node, subset = next_tree, next_nid, next_node, next_subset
         seg_begin, seg_end = next_begin, next_end

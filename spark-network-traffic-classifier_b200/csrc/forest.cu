@@ -428,11 +428,11 @@ constexpr int kRouteThreads = 256;
 
 struct RouteChunk { int32_t slot; int32_t n; long long begin; };   // 16 bytes, one per chunk
 
-__global__ void route_chunks_kernel(const int64_t* __restrict__ chunk_off, int n_slots, int64_t n_chunks,
+__global__ void route_chunks_kernel(const int64_t* __restrict__ chunk_off, int n_slots, const int64_t* __restrict__ n_chunks_dev,
                                     const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end, int CH,
                                     RouteChunk* out) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_chunks) return;
+    if (c >= *n_chunks_dev) return;                            // the count lives on the device: the host never waits for it
     const int s = find_slot(chunk_off, n_slots, c);
     RouteChunk rc; rc.slot = s; rc.begin = seg_begin[s] + (c - chunk_off[s]) * CH;
     rc.n = (int)(min(seg_end[s], (int64_t)rc.begin + CH) - rc.begin);
@@ -442,7 +442,7 @@ __global__ void route_chunks_kernel(const int64_t* __restrict__ chunk_off, int n
 struct RouteArgs {
     const uint8_t* tp; int stride; int F;
     const b2f_entry* ent; b2f_entry* ent_out;
-    const RouteChunk* chunks; int64_t n_chunks; int CH;
+    const RouteChunk* chunks; const int64_t* n_chunks_dev; int CH;
     const int64_t* seg_begin; const int64_t* seg_end;
     const b200flow_split* split; const int32_t* child_slot; int32_t* cursors;
     const uint16_t* subset_next; int m; int n_bins; int C; uint32_t* hist_next;
@@ -473,7 +473,8 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     __shared__ b200flow_split sh_split;
     __shared__ int sh_child[2];
 
-    const int64_t c0 = a.n_chunks * blockIdx.x / gridDim.x, c1 = a.n_chunks * (blockIdx.x + 1) / gridDim.x;
+    const int64_t n_chunks = *a.n_chunks_dev;
+    const int64_t c0 = n_chunks * blockIdx.x / gridDim.x, c1 = n_chunks * (blockIdx.x + 1) / gridDim.x;
     if (c0 >= c1) return;
     auto flush = [&]() {
         for (int side = 0; side < 2; ++side) {
@@ -655,11 +656,11 @@ static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
     return (size_t)kRouteWarps * nbuf * nq * kSub * 16 + 2 * (size_t)m * n_bins * C * 4 + 2 * (size_t)m * 4 + 64;
 }
 
-__global__ void next_segments_kernel(int n_next, const int32_t* __restrict__ next_parent, const int64_t* __restrict__ seg_begin,
-                                     const int64_t* __restrict__ seg_end, const int32_t* __restrict__ cursors,
-                                     int64_t* next_begin, int64_t* next_end) {
+__global__ void next_segments_kernel(int n_next, const int64_t* __restrict__ n_next_dev, const int32_t* __restrict__ next_parent,
+                                     const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end,
+                                     const int32_t* __restrict__ cursors, int64_t* next_begin, int64_t* next_end) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_next) return;
+    if (i >= n_next || (n_next_dev && i >= *n_next_dev)) return;
     const int p = next_parent[i], ps = p >> 1;
     if ((p & 1) == 0) { next_begin[i] = seg_begin[ps]; next_end[i] = seg_begin[ps] + cursors[2 * ps]; }
     else { next_begin[i] = seg_end[ps] - cursors[2 * ps + 1]; next_end[i] = seg_end[ps]; }
@@ -759,11 +760,11 @@ extern "C" int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride, co
     return check_launch("partition_level");
 }
 
-extern "C" int b200flow_next_segments(int32_t n_next, const int32_t* next_parent, const int64_t* seg_begin, const int64_t* seg_end,
-                                      const int32_t* cursors, int64_t* next_begin, int64_t* next_end, void* stream) {
+extern "C" int b200flow_next_segments(int32_t n_next, const int64_t* n_next_dev, const int32_t* next_parent, const int64_t* seg_begin,
+                                      const int64_t* seg_end, const int32_t* cursors, int64_t* next_begin, int64_t* next_end, void* stream) {
     B2F_REQUIRE(next_parent && seg_begin && seg_end && cursors && next_begin && next_end, "next_segments: null pointer");
     if (n_next <= 0) return B200FLOW_OK;
-    next_segments_kernel<<<(n_next + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_next, next_parent, seg_begin, seg_end, cursors, next_begin, next_end);
+    next_segments_kernel<<<(n_next + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_next, n_next_dev, next_parent, seg_begin, seg_end, cursors, next_begin, next_end);
     return check_launch("next_segments");
 }
 
@@ -781,21 +782,22 @@ extern "C" int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, in
 
 extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const void* ent, void* ent_out,
                                          int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end, const int64_t* chunk_off,
-                                         int64_t n_chunks, int32_t chunk_rows, const b200flow_split* split, const int32_t* child_slot,
+                                         const int64_t* n_chunks_dev, int64_t n_chunks_max, int32_t chunk_rows,
+                                         const b200flow_split* split, const int32_t* child_slot,
                                          int32_t* cursors, void* chunk_scratch, const uint16_t* subset_next, int32_t m, int32_t n_bins,
                                          int32_t C, uint32_t* hist_next, void* stream) {
-    B2F_REQUIRE(tp && ent && ent_out && seg_begin && seg_end && chunk_off && split && child_slot && cursors && chunk_scratch &&
+    B2F_REQUIRE(tp && ent && ent_out && seg_begin && seg_end && chunk_off && n_chunks_dev && split && child_slot && cursors && chunk_scratch &&
                     subset_next && hist_next, "route_hist_level: null pointer");
     B2F_REQUIRE((tp_stride & 15) == 0 && tp_stride >= (F + 1 + 15) / 16 * 16 && ((uintptr_t)tp & 15) == 0, "route_hist_level: bad TreePoint stride/alignment");
     B2F_REQUIRE(((uintptr_t)chunk_scratch & 15) == 0, "route_hist_level: chunk_scratch must be 16-byte aligned");
     B2F_REQUIRE(b200flow_route_hist_fits(F, m, n_bins, C, chunk_rows), "route_hist_level: does not fit shared memory (use partition_level + hist_level)");
-    if (n_slots <= 0 || n_chunks <= 0) return B200FLOW_OK;
+    if (n_slots <= 0 || n_chunks_max <= 0) return B200FLOW_OK;
     const size_t smem = route_hist_smem(F, m, n_bins, C, chunk_rows);
     RouteChunk* chunks = (RouteChunk*)chunk_scratch;
-    route_chunks_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chunk_off, n_slots, n_chunks, seg_begin, seg_end,
-                                                                                            chunk_rows, chunks);
+    route_chunks_kernel<<<(unsigned)((n_chunks_max + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chunk_off, n_slots, n_chunks_dev, seg_begin,
+                                                                                                seg_end, chunk_rows, chunks);
     RouteArgs a;
-    a.tp = tp; a.stride = tp_stride; a.F = F; a.ent = (const b2f_entry*)ent; a.ent_out = (b2f_entry*)ent_out; a.chunks = chunks; a.n_chunks = n_chunks; a.CH = chunk_rows;
+    a.tp = tp; a.stride = tp_stride; a.F = F; a.ent = (const b2f_entry*)ent; a.ent_out = (b2f_entry*)ent_out; a.chunks = chunks; a.n_chunks_dev = n_chunks_dev; a.CH = chunk_rows;
     a.seg_begin = seg_begin; a.seg_end = seg_end; a.split = split; a.child_slot = child_slot; a.cursors = cursors;
     a.subset_next = subset_next; a.m = m; a.n_bins = n_bins; a.C = C; a.hist_next = hist_next;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -803,7 +805,7 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     if (per_sm > max_per_sm) per_sm = max_per_sm;
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (int64_t)kNumSMs * per_sm;
-    const unsigned grid = (unsigned)(n_chunks < want ? n_chunks : want);
+    const unsigned grid = (unsigned)(n_chunks_max < want ? n_chunks_max : want);
 #define B2F_ROUTE_LAUNCH(KERNEL)                                                                                               \
     {                                                                                                                          \
         cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
