@@ -458,7 +458,7 @@ struct RouteArgs {
 constexpr int kRouteWarps = kRouteThreads / 32;
 constexpr int kSub = 64;                                    // entries per warp step (2 per lane)
 
-template <int M, int NBUF, int MERGE>   // MERGE: 0 plain shared atomics, 1 whole-key merge, 2 per-feature merge
+template <int M, int NBUF, int MERGE>   // MERGE: 0 plain shared atomics, 1 whole-key merge, 2 per-feature merge, 3 top-group merge
 __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_level_kernel(const RouteArgs a) {
     extern __shared__ __align__(16) uint32_t sm_u32[];
     const int m = M > 0 ? M : a.m;
@@ -616,6 +616,23 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                             const uint32_t sum = __reduce_add_sync(gg, w);
                             if ((int)(__ffs(gg) - 1) == lane) atomicAdd(&hist[j * nbC + bin * a.C + lab], sum);
                         }
+                    } else if (M > 0 && MERGE == 3) {
+                        // top-group merge: per feature, the lanes that share the first active lane's (bin, label, child) counter are
+                        // summed with ONE redux (every participant passes the same mask, so it is a single REDUX) and issue one
+                        // shared atomic; the other lanes add alone.  Further rounds were measured slower (27 / 36 ms vs 20.6 ms).
+                        const uint32_t tag = (lab << 8) | ((uint32_t)side << 16);
+#pragma unroll
+                        for (int j = 0; j < M; ++j) {
+                            const int fp = fpos[j];
+                            const uint32_t bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu;
+                            const uint32_t key = bin | tag;
+                            uint32_t* addr = &hist[j * nbC + bin * a.C + lab];
+                            const int l0 = __ffs(active) - 1;
+                            const uint32_t m0 = __ballot_sync(active, key == __shfl_sync(active, key, l0));
+                            bool done = (m0 >> lane) & 1u;
+                            if (done) { const uint32_t sum = __reduce_add_sync(m0, w); if (lane == l0) atomicAdd(addr, sum); }
+                            if (!done) atomicAdd(addr, w);
+                        }
                     } else {
                         for (int j = 0; j < m; ++j) {
                             const int fp = fpos[j];
@@ -643,10 +660,11 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
 
 static int route_variant() {                                // tuning knob (tile buffers per warp, merge strategy)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? atoi(e) : 4; }
-    return v;        // bit0: 2 tiles per warp; bits 1-2: merge of equal lanes before the shared atomics (0 whole-key, 1 per-feature,
-                     // 2 none).  Default 4 = one tile, no merge: after row de-duplication equal keys inside a warp are rare and
-                     // redux/match cost more than the conflicts they remove (measured: 26 ms vs 46 ms per KDD-full fit)
+    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? atoi(e) : 6; }
+    return v;        // bit0: 2 tiles per warp; bits 1-3: merge of equal lanes before the shared atomics (0 whole-key, 1 per-feature,
+                     // 2 none, 3 top-group).  Default 6 = one tile, top-group merge.  Measured per KDD-full fit after row
+                     // de-duplication: top-group 20.6 ms, none 26 ms, whole-key 46 ms, per-feature 80 ms (a redux per distinct
+                     // mask serialises; one shared mask does not)
 }
 
 static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
@@ -814,12 +832,13 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     }
 #define B2F_ROUTE_CASE(MM)                                                                                                     \
     case MM:                                                                                                                   \
-        switch (route_variant() & 7) {                                                                                         \
+        switch (route_variant() & 15) {                                                                                        \
             case 0: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 1>)) break;                                               \
             case 1: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 1>)) break;                                               \
             case 2: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 2>)) break;                                               \
             case 3: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 2>)) break;                                               \
             case 4: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 0>)) break;                                               \
+            case 6: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 3>)) break;                                               \
             default: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 0>)) break;                                              \
         }                                                                                                                      \
         break;
