@@ -522,7 +522,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
             break
         next_tree, next_nid, next_node = next_tree[:n_next], next_nid[:n_next], next_node[:n_next]
         if speculative:
-            hist_ready = hist_next
+            hist_ready = hist_next[:n_next * hsz]             # only the slots that exist travel through the all-reduce
             next_subset, next_begin, next_end = next_subset[:n_next], next_begin[:n_next], next_end[:n_next]
         else:
             next_subset = level_subsets(n_next, next_tree, next_nid)

@@ -123,148 +123,173 @@ __device__ __forceinline__ double split_gain(const uint32_t* L, const uint32_t* 
     return gain;
 }
 
-constexpr int kScoreWarps = 8;
+constexpr int kScoreThreads = 256;
 
-// one CTA per slot, one warp per feature of the node's subset (looping when m > warps)
-__global__ void __launch_bounds__(32 * kScoreWarps) score_level_kernel(
+// One CTA per slot, two phases so that the expensive part is balanced across the whole CTA:
+//   1. per feature of the node's subset (a warp each, looping): class-wise prefix sums over its bins in shared memory
+//      (continuous), or the centroid ranking + prefix sums in ranked order (ordered categorical), or the raw per-category
+//      counts (unordered categorical).  Cost ~ bins of that feature — uneven (2-bin flags next to 70-bin rates).
+//   2. ALL candidate splits of ALL staged features form one flat list (feature-major, split-minor = MLlib's scan order);
+//      thread t evaluates candidates t, t+256, ... in fp64 (calculateImpurityStats, no FMA) and keeps its first maximum;
+//      a shuffle/smem reduction with the (gain desc, feature asc, split asc) order reproduces "first max over splits, then
+//      first max over features".
+// Features are staged in batches when m * n_bins * C exceeds the shared-memory budget (DecisionTree: all features).
+__global__ void __launch_bounds__(kScoreThreads) score_level_kernel(
     const uint32_t* __restrict__ hist, int n_slots, const uint16_t* __restrict__ subset, int m, int n_bins, int C,
     const int32_t* __restrict__ feat_bins, const int32_t* __restrict__ feat_kind, int level, int max_depth, int min_inst,
-    double min_gain, b200flow_split* split, uint32_t* node_counts, uint32_t* left_counts, uint32_t* right_counts) {
+    double min_gain, int batch, b200flow_split* split, uint32_t* node_counts, uint32_t* left_counts, uint32_t* right_counts) {
     extern __shared__ __align__(8) uint8_t sm_raw[];
     const int s = blockIdx.x;
-    const int w = warp_id(), lane = lane_id(), nw = blockDim.x >> 5;
+    const int tid = threadIdx.x, w = warp_id(), lane = lane_id(), nw = kScoreThreads / 32;
     const int nbC = n_bins * C;
-    // per-warp scratch: cum[nbC] u32, tmp[nbC] u32, cen[n_bins] f64, order[n_bins] i32, bestL[C] u32
-    const size_t per_warp = ((size_t)2 * nbC * 4 + (size_t)n_bins * 8 + (size_t)n_bins * 4 + (size_t)C * 4 + 7) & ~(size_t)7;
-    uint32_t* tot = (uint32_t*)sm_raw;                                         // [C] node class counts
-    uint8_t* wbase = sm_raw + (((size_t)C * 4 + 7) & ~(size_t)7) + per_warp * w;
-    double* cen = (double*)wbase;
-    uint32_t* cum = (uint32_t*)(cen + n_bins);
-    uint32_t* tmp = cum + nbC;
-    int* order = (int*)(tmp + nbC);
-    uint32_t* bestL = (uint32_t*)(order + n_bins);
-    __shared__ double sh_gain[kScoreWarps];
-    __shared__ int sh_j[kScoreWarps], sh_s[kScoreWarps];
-    __shared__ unsigned long long sh_mask[kScoreWarps][4];
+    // layout: tot[C] | bestL[C] | per-warp {cen[n_bins] f64, raw[nbC] u32} (8-byte multiples) | cum[batch][nbC] | order[batch][n_bins]
+    uint32_t* tot = (uint32_t*)sm_raw;
+    uint32_t* bestL = tot + C;
+    const size_t per_warp = ((size_t)n_bins * 8 + (size_t)nbC * 4 + 7) & ~(size_t)7;
+    uint8_t* wbase = (uint8_t*)(bestL + C);
+    double* cen = (double*)(wbase + per_warp * w);
+    uint32_t* raw = (uint32_t*)(cen + n_bins);
+    uint32_t* cum_all = (uint32_t*)(wbase + per_warp * nw);
+    int* order_all = (int*)(cum_all + (size_t)batch * nbC);
+    __shared__ int sh_feat[64], sh_nsplit[64], sh_off[65], sh_kind[64], sh_nb[64];
+    __shared__ double sh_wg[kScoreThreads / 32];
+    __shared__ int sh_wj[kScoreThreads / 32], sh_ws[kScoreThreads / 32];
+    __shared__ double sh_best_gain; __shared__ int sh_best_j, sh_best_s, sh_best_kind;
+    __shared__ unsigned long long sh_best_mask[4];
 
     const uint32_t* h0 = hist + (int64_t)s * m * nbC;
-    // node class counts = Σ over the bins of the first subset feature
-    {
-        const int f0 = subset[(int64_t)s * m];
-        const int nb0 = feat_bins[f0];
-        for (int k = threadIdx.x; k < C; k += blockDim.x) {
-            uint32_t a = 0;
-            for (int b = 0; b < nb0; ++b) a += h0[b * C + k];
-            tot[k] = a;
-        }
+    {   // node class counts = sum over the bins of the first subset feature
+        const int nb0 = feat_bins[subset[(int64_t)s * m]];
+        for (int k = tid; k < C; k += kScoreThreads) { uint32_t a = 0; for (int b = 0; b < nb0; ++b) a += h0[b * C + k]; tot[k] = a; }
     }
+    if (tid == 0) { sh_best_gain = -DBL_MAX; sh_best_j = -1; sh_best_s = -1; sh_best_kind = 0; }
     __syncthreads();
     double ptot = 0.0;
     for (int k = 0; k < C; ++k) ptot += (double)tot[k];
     const double parent_imp = gini_u32(tot, C, ptot);
 
-    double wbest = -DBL_MAX; int wj = -1, ws = -1;
-    unsigned long long wmask[4] = {0, 0, 0, 0};
-    for (int j = w; j < m; j += nw) {
-        const int f = subset[(int64_t)s * m + j];
-        const int nb = feat_bins[f], kind = feat_kind[f];
-        const uint32_t* h = h0 + (int64_t)j * nbC;
-        double lbest = -DBL_MAX; int ls = -1;            // this lane's best split for feature j
-        __syncwarp();
-        if (kind == 0) {
-            for (int i = lane; i < nb * C; i += 32) cum[i] = h[i];
-            __syncwarp();
-            for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int b = 0; b < nb; ++b) { a += cum[b * C + k]; cum[b * C + k] = a; } }
-            __syncwarp();
-            for (int sp = lane; sp < nb - 1; sp += 32) {
-                double g = split_gain(cum + sp * C, tot, C, parent_imp, min_inst, min_gain);
-                if (g > lbest) { lbest = g; ls = sp; }
-            }
-        } else if (kind == 1) {
-            for (int i = lane; i < nb * C; i += 32) tmp[i] = h[i];
-            __syncwarp();
-            for (int c = lane; c < nb; c += 32) {        // centroid per category
-                double cnt = 0.0;
-                for (int k = 0; k < C; ++k) cnt += (double)tmp[c * C + k];
-                double ce;
-                if (cnt == 0.0) ce = DBL_MAX;
-                else if (C > 2) ce = gini_u32(tmp + c * C, C, cnt);
-                else ce = (double)tmp[c * C + 1];
-                cen[c] = ce;
-            }
-            __syncwarp();
-            for (int c = lane; c < nb; c += 32) {        // stable rank by centroid
-                const double ce = cen[c]; int rk = 0;
-                for (int c2 = 0; c2 < nb; ++c2) { double o = cen[c2]; rk += (o < ce || (o == ce && c2 < c)) ? 1 : 0; }
-                order[rk] = c;
+    for (int j0 = 0; j0 < m; j0 += batch) {
+        const int nb_feats = min(batch, m - j0);
+        // ---- phase 1: stage the batch
+        for (int jj = w; jj < nb_feats; jj += nw) {
+            const int f = subset[(int64_t)s * m + j0 + jj];
+            const int nb = feat_bins[f], kind = feat_kind[f];
+            const uint32_t* h = h0 + (int64_t)(j0 + jj) * nbC;
+            uint32_t* cum = cum_all + (size_t)jj * nbC;
+            int* order = order_all + (size_t)jj * n_bins;
+            if (lane == 0) { sh_feat[jj] = f; sh_kind[jj] = kind; sh_nb[jj] = nb; sh_nsplit[jj] = kind == 2 ? (1 << (nb - 1)) - 1 : nb - 1; }
+            if (kind == 0) {
+                for (int i = lane; i < nb * C; i += 32) cum[i] = h[i];
+                __syncwarp();
+                for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int b = 0; b < nb; ++b) { a += cum[b * C + k]; cum[b * C + k] = a; } }
+            } else if (kind == 1) {
+                for (int i = lane; i < nb * C; i += 32) raw[i] = h[i];
+                __syncwarp();
+                for (int c = lane; c < nb; c += 32) {            // centroid per category
+                    double cnt = 0.0;
+                    for (int k = 0; k < C; ++k) cnt += (double)raw[c * C + k];
+                    cen[c] = cnt == 0.0 ? DBL_MAX : (C > 2 ? gini_u32(raw + c * C, C, cnt) : (double)raw[c * C + 1]);
+                }
+                __syncwarp();
+                for (int c = lane; c < nb; c += 32) {            // stable rank by centroid
+                    const double ce = cen[c]; int rk = 0;
+                    for (int c2 = 0; c2 < nb; ++c2) { const double o = cen[c2]; rk += (o < ce || (o == ce && c2 < c)) ? 1 : 0; }
+                    order[rk] = c;
+                }
+                __syncwarp();
+                for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int i = 0; i < nb; ++i) { a += raw[order[i] * C + k]; cum[i * C + k] = a; } }
+            } else {
+                for (int i = lane; i < nb * C; i += 32) cum[i] = h[i];   // raw per-category counts; subsets are summed per candidate
             }
             __syncwarp();
-            for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int i = 0; i < nb; ++i) { a += tmp[order[i] * C + k]; cum[i * C + k] = a; } }
-            __syncwarp();
-            for (int sp = lane; sp < nb - 1; sp += 32) {
-                double g = split_gain(cum + sp * C, tot, C, parent_imp, min_inst, min_gain);
-                if (g > lbest) { lbest = g; ls = sp; }
-            }
-        } else {
-            for (int i = lane; i < nb * C; i += 32) tmp[i] = h[i];
-            __syncwarp();
-            const int ns = (1 << (nb - 1)) - 1;           // nb <= 6 -> ns <= 31: one split per lane
-            if (lane < ns) {
-                const unsigned bits = (unsigned)(lane + 1);
-                uint32_t* L = cum + lane * C;
-                for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += tmp[c * C + k]; L[k] = a; }
-                double g = split_gain(L, tot, C, parent_imp, min_inst, min_gain);
-                if (g > lbest) { lbest = g; ls = lane; }
-            }
         }
-        // first max over splits: larger gain wins, ties -> smaller split index
-        double g = lbest; int sp = ls;
+        __syncthreads();
+        if (tid == 0) { int o = 0; for (int jj = 0; jj < nb_feats; ++jj) { sh_off[jj] = o; o += max(sh_nsplit[jj], 0); } sh_off[nb_feats] = o; }
+        __syncthreads();
+        // ---- phase 2: every candidate split of the batch, flat over the CTA
+        const int n_items = sh_off[nb_feats];
+        double tbest = -DBL_MAX; int tj = -1, ts = -1;
+        for (int it = tid; it < n_items; it += kScoreThreads) {
+            int jj = 0;
+            while (it >= sh_off[jj + 1]) ++jj;
+            const int sp = it - sh_off[jj];
+            const uint32_t* cum = cum_all + (size_t)jj * nbC;
+            double g;
+            if (sh_kind[jj] != 2) {
+                g = split_gain(cum + sp * C, tot, C, parent_imp, min_inst, min_gain);
+            } else {
+                // unordered: left = sum of the categories whose bit is set in (sp + 1); evaluated without materialising L
+                const unsigned bits = (unsigned)(sp + 1); const int nb = sh_nb[jj];
+                double lc = 0.0, rc = 0.0;
+                for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += cum[c * C + k]; lc += (double)a; rc += (double)(tot[k] - a); }
+                if (lc < (double)min_inst || rc < (double)min_inst) g = -DBL_MAX;
+                else {
+                    const double t = lc + rc; double gl = 1.0, gr = 1.0;
+                    if (lc == 0.0) gl = 0.0; else for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += cum[c * C + k]; const double fq = (double)a / lc; gl -= fq * fq; }
+                    if (rc == 0.0) gr = 0.0; else for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += cum[c * C + k]; const double fq = (double)(tot[k] - a) / rc; gr -= fq * fq; }
+                    const double lw = lc / t, rw = rc / t;
+                    g = parent_imp - lw * gl - rw * gr;
+                    if (g < min_gain) g = -DBL_MAX;
+                }
+            }
+            if (g > tbest) { tbest = g; tj = j0 + jj; ts = sp; }      // items ascend in (feature, split): strict > keeps the first
+        }
+        // CTA argmax under (gain desc, feature asc, split asc); threads without a valid candidate carry tj = -1
+        double g = tbest; int bj = tj, bs = ts;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            double og = __shfl_xor_sync(0xffffffffu, g, o); int os = __shfl_xor_sync(0xffffffffu, sp, o);
-            if (os >= 0 && (sp < 0 || og > g || (og == g && os < sp))) { g = og; sp = os; }
+            const double og = __shfl_xor_sync(0xffffffffu, g, o); const int oj = __shfl_xor_sync(0xffffffffu, bj, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (oj >= 0 && og > -DBL_MAX && (bj < 0 || !(g > -DBL_MAX) || og > g || (og == g && (oj < bj || (oj == bj && os < bs))))) { g = og; bj = oj; bs = os; }
         }
-        if (sp >= 0 && g > wbest) {                        // first max over this warp's features (ascending j)
-            wbest = g; wj = j; ws = sp;
-            __syncwarp();
-            for (int k = lane; k < C; k += 32) bestL[k] = cum[sp * C + k];
-            wmask[0] = wmask[1] = wmask[2] = wmask[3] = 0;
-            if (kind == 1) { for (int i = 0; i <= sp; ++i) { int c = order[i]; wmask[c >> 6] |= 1ull << (c & 63); } }
-            else if (kind == 2) wmask[0] = (unsigned long long)(sp + 1);
-            __syncwarp();
+        if (lane == 0) { sh_wg[w] = g; sh_wj[w] = (g > -DBL_MAX) ? bj : -1; sh_ws[w] = bs; }
+        __syncthreads();
+        if (tid == 0) {
+            double bg = sh_best_gain; int gj = sh_best_j, gs = sh_best_s; bool improved = false;
+            for (int q = 0; q < nw; ++q)
+                if (sh_wj[q] >= 0 && (sh_wg[q] > bg)) { bg = sh_wg[q]; gj = sh_wj[q]; gs = sh_ws[q]; improved = true; }
+                else if (sh_wj[q] >= 0 && improved && sh_wg[q] == bg && (sh_wj[q] < gj || (sh_wj[q] == gj && sh_ws[q] < gs))) { gj = sh_wj[q]; gs = sh_ws[q]; }
+            if (improved) {                                           // earlier batches win ties (their features come first)
+                sh_best_gain = bg; sh_best_j = gj; sh_best_s = gs;
+                const int jj = gj - j0; const int kind = sh_kind[jj], nb = sh_nb[jj];
+                const uint32_t* cum = cum_all + (size_t)jj * nbC;
+                sh_best_kind = kind;
+                unsigned long long mk[4] = {0, 0, 0, 0};
+                if (kind == 2) {
+                    const unsigned bits = (unsigned)(gs + 1);
+                    for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += cum[c * C + k]; bestL[k] = a; }
+                    mk[0] = bits;
+                } else {
+                    for (int k = 0; k < C; ++k) bestL[k] = cum[gs * C + k];
+                    if (kind == 1) { const int* order = order_all + (size_t)jj * n_bins; for (int i = 0; i <= gs; ++i) { const int c = order[i]; mk[c >> 6] |= 1ull << (c & 63); } }
+                }
+                for (int q = 0; q < 4; ++q) sh_best_mask[q] = mk[q];
+            }
         }
+        __syncthreads();
     }
-    if (lane == 0) { sh_gain[w] = wbest; sh_j[w] = wj; sh_s[w] = ws; for (int q = 0; q < 4; ++q) sh_mask[w][q] = wmask[q]; }
-    __syncthreads();
-    // first max over features: larger gain, ties -> smaller j
-    int bw = -1; double bg = -DBL_MAX; int bj = -1;
-    for (int q = 0; q < nw; ++q)
-        if (sh_j[q] >= 0 && (bw < 0 || sh_gain[q] > bg || (sh_gain[q] == bg && sh_j[q] < bj))) { bw = q; bg = sh_gain[q]; bj = sh_j[q]; }
-    if (w != (bw < 0 ? 0 : bw)) return;
-    // the winning warp (or warp 0 when there is no valid split) writes the records
-    const bool has = bw >= 0;
-    for (int k = lane; k < C; k += 32) {
+    // ---- outputs
+    const bool has = sh_best_j >= 0;
+    for (int k = tid; k < C; k += kScoreThreads) {
         node_counts[(int64_t)s * C + k] = tot[k];
-        uint32_t l = has ? bestL[k] : 0u;
+        const uint32_t l = has ? bestL[k] : 0u;
         left_counts[(int64_t)s * C + k] = l;
         right_counts[(int64_t)s * C + k] = has ? tot[k] - l : 0u;
     }
-    __syncwarp();
-    if (lane == 0) {
+    if (tid == 0) {
         b200flow_split o;
+        const double bg = sh_best_gain;
         o.gain = has ? bg : -DBL_MAX; o.impurity = parent_imp;
         const bool leaf = !(has && bg > 0.0) || level >= max_depth;
         int flags = leaf ? 1 : 0;
         o.feat = -1; o.kind = 0; o.bin_thr = 0;
         o.mask[0] = o.mask[1] = o.mask[2] = o.mask[3] = 0;
         if (!leaf) {
-            const int f = subset[(int64_t)s * m + bj];
-            o.feat = f; o.kind = feat_kind[f] == 0 ? 0 : 1; o.bin_thr = sh_s[bw];
-            for (int q = 0; q < 4; ++q) o.mask[q] = sh_mask[bw][q];
+            o.feat = subset[(int64_t)s * m + sh_best_j]; o.kind = sh_best_kind == 0 ? 0 : 1; o.bin_thr = sh_best_s;
+            for (int q = 0; q < 4; ++q) o.mask[q] = sh_best_mask[q];
             double lc = 0.0, rc = 0.0, gl = 1.0, gr = 1.0;
             for (int k = 0; k < C; ++k) { lc += (double)bestL[k]; rc += (double)(tot[k] - bestL[k]); }
-            if (lc == 0.0) gl = 0.0; else for (int k = 0; k < C; ++k) { double fq = (double)bestL[k] / lc; gl -= fq * fq; }
-            if (rc == 0.0) gr = 0.0; else for (int k = 0; k < C; ++k) { double fq = (double)(tot[k] - bestL[k]) / rc; gr -= fq * fq; }
+            if (lc == 0.0) gl = 0.0; else for (int k = 0; k < C; ++k) { const double fq = (double)bestL[k] / lc; gl -= fq * fq; }
+            if (rc == 0.0) gr = 0.0; else for (int k = 0; k < C; ++k) { const double fq = (double)(tot[k] - bestL[k]) / rc; gr -= fq * fq; }
             if (level + 1 == max_depth || gl == 0.0) flags |= 2;
             if (level + 1 == max_depth || gr == 0.0) flags |= 4;
         }
@@ -733,16 +758,19 @@ extern "C" int b200flow_score_level(const uint32_t* hist, int32_t n_slots, const
     B2F_REQUIRE(hist && subset && feat_bins && feat_kind && split && node_counts && left_counts && right_counts, "score_level: null pointer");
     B2F_REQUIRE(m > 0 && n_bins > 0 && n_bins <= 256 && C > 0 && C <= 256, "score_level: bad shape");
     if (n_slots <= 0) return B200FLOW_OK;
-    int nw = m < kScoreWarps ? m : kScoreWarps;
-    size_t per_warp = ((size_t)2 * n_bins * C * 4 + (size_t)n_bins * 8 + (size_t)n_bins * 4 + (size_t)C * 4 + 7) & ~(size_t)7;
-    while (nw > 1 && per_warp * nw + C * 4 + 64 > 100 * 1024) --nw;
-    size_t smem = (((size_t)C * 4 + 7) & ~(size_t)7) + per_warp * nw;
+    // shared memory: tot + bestL + per-feature {prefix sums, rank order} for a batch of features + per-warp scratch
+    const size_t per_feat = (size_t)n_bins * C * 4 + (size_t)n_bins * 4;
+    const size_t per_warp = ((size_t)n_bins * 8 + (size_t)n_bins * C * 4 + 7) & ~(size_t)7;
+    const size_t fixed = (size_t)2 * C * 4 + 16 + per_warp * (kScoreThreads / 32) + 16;
+    int batch = m < 64 ? m : 64;
+    while (batch > 1 && fixed + per_feat * batch > 160 * 1024) --batch;
+    const size_t smem = fixed + per_feat * batch;
     B2F_REQUIRE(smem <= 200 * 1024, "score_level: scratch exceeds shared memory");
     cudaError_t e = cudaFuncSetAttribute(score_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("score_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
-    score_level_kernel<<<n_slots, 32 * nw, smem, (cudaStream_t)stream>>>(hist, n_slots, subset, m, n_bins, C, feat_bins, feat_kind, level,
-                                                                        max_depth, min_instances, min_info_gain, split, node_counts,
-                                                                        left_counts, right_counts);
+    score_level_kernel<<<n_slots, kScoreThreads, smem, (cudaStream_t)stream>>>(hist, n_slots, subset, m, n_bins, C, feat_bins, feat_kind, level,
+                                                                              max_depth, min_instances, min_info_gain, batch, split,
+                                                                              node_counts, left_counts, right_counts);
     return check_launch("score_level");
 }
 
