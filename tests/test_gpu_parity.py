@@ -278,6 +278,24 @@ def test_decision_tree_deterministic_anchor_kdd_binary():
     _check_predictions(model, fo, meta, x[:3000], dt_mode=True)
 
 
+@pytest.mark.parametrize("depth", [2, 4])
+def test_decision_tree_cuda_matches_exact_cart(depth):
+    # independent anchor (tests/test_oracle_vs_sklearn.py): with fewer distinct values than maxBins every midpoint is a
+    # candidate threshold, so the CUDA DecisionTree must equal scikit-learn's exact CART node for node
+    sktree = pytest.importorskip("sklearn.tree")
+    rng = np.random.default_rng(depth)
+    xn = rng.integers(0, 20, size=(3000, 6)).astype(np.float64)
+    score = (xn[:, 0] > 9.5) * 1.0 + (xn[:, 2] > 4.5) * 1.0 + (xn[:, 4] > 14.5) * 0.7 + rng.normal(0, 0.6, 3000)
+    yn = np.digitize(score, [0.8, 1.7]).astype(np.int32)
+    model = fr.fit_forest(torch.from_numpy(xn).to(DEV), torch.from_numpy(yn).to(DEV), 3, [0] * 6,
+                          fr.ForestParams(num_trees=1, max_bins=32, max_depth=depth, bootstrap=False, seed=depth))
+    sk = sktree.DecisionTreeClassifier(criterion="gini", max_depth=depth, random_state=0).fit(xn, yn)
+    assert model.n_nodes == sk.tree_.node_count
+    raw, prob, pred = model.predict(torch.from_numpy(xn).to(DEV))
+    assert np.array_equal(pred.cpu().numpy(), sk.predict(xn).astype(np.float64))
+    assert np.abs(prob.cpu().numpy() - sk.predict_proba(xn)).max() < 1e-15
+
+
 @pytest.mark.parametrize("n_classes,depth,trees", [(2, 5, 20), (5, 8, 10), (23, 6, 6)])
 def test_random_forest_kdd_matches_oracle(n_classes, depth, trees):
     x, y, arity, C = _features(40000, n_classes, 77 + n_classes)
