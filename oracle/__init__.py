@@ -224,6 +224,13 @@ def random_split(seed, n, cum_bounds, row_offset=0):
 
 
 # ---- host-side restatement of DecisionTreeMetadata.buildMetadata (A.1) and the fit driver ----
+def check_shared_reciprocal_division(small_b=3000, n_random=100_000_000):
+    """mismatch count of the shared-reciprocal exact division identity used by the CUDA split scorer (0 expected)."""
+    f = lib().orc_check_shared_reciprocal_division
+    f.restype = C.c_int64
+    return int(f(C.c_int32(small_b), C.c_int64(n_random)))
+
+
 def poisson_cdf_table(rate=1.0):
     """32 uint32 thresholds floor(CDF(k)·2^32) (saturating) for the bagging inverse-CDF (A.4)."""
     import math

@@ -538,4 +538,28 @@ int32_t orc_find_splits_1d(const double* samples, int32_t n, int32_t num_splits,
     return nt;
 }
 
+// Checks the identity the CUDA split scorer relies on (forest.cu div_rn): for integers 0 <= a <= b, with y = RN(1/b),
+// q = RN(a*y), RN(q + (a - b*q)*y) == RN(a/b) (std::fma = one rounding).  Exhaustive for b <= small_b, then n_random random
+// pairs below 2^32 and their a/(a+b) forms.  Returns the number of mismatches (0 expected).
+int64_t orc_check_shared_reciprocal_division(int32_t small_b, int64_t n_random) {
+    auto mdiv = [](double a, double b, double y) { double q = a * y; double r = std::fma(-b, q, a); return std::fma(r, y, q); };
+    int64_t bad = 0;
+#pragma omp parallel for reduction(+ : bad) schedule(dynamic, 16)
+    for (int32_t b = 1; b <= small_b; ++b) {
+        const double y = 1.0 / (double)b;
+        for (int32_t a = 0; a <= b; ++a) bad += mdiv(a, b, y) != (double)a / (double)b;
+    }
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+    for (int64_t i = 0; i < n_random; ++i) {
+        U4 r = philox_keyed(0x1234, 0x44495653u, (uint32_t)i, (uint32_t)(i >> 32), 0, 0);
+        uint32_t bb = r.x >> (r.z & 31); if (!bb) bb = 1;
+        const uint32_t aa = (uint32_t)(((uint64_t)r.y * ((uint64_t)bb + 1)) >> 32);
+        const double a = aa, b = bb, t = a + b;
+        bad += mdiv(a, b, 1.0 / b) != a / b;
+        bad += mdiv(a, t, 1.0 / t) != a / t;
+        bad += mdiv(b, t, 1.0 / t) != b / t;
+    }
+    return bad;
+}
+
 }  // extern "C"

@@ -100,10 +100,20 @@ __global__ void __launch_bounds__(256) hist_level_kernel(const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------ R8 split scoring (HOT LOOP B)
+// Correctly rounded a / b with the reciprocal y = RN(1/b) shared by all numerators over the same denominator (Markstein:
+// q = RN(a*y), r = a - b*q exact by FMA, RN(q + r*y) = RN(a/b) when b's significand is not all ones — b is an integer
+// below 2^33 here).  Bit-identical to the oracle's `/`, at 3 fp64 instructions per quotient instead of a full division;
+// tests/test_oracle_known_answers.py checks the identity exhaustively for small b and on 10^8 random pairs.
+__device__ __forceinline__ double div_rn(double a, double b, double y) {
+    const double q = __dmul_rn(a, y);
+    return __fma_rn(__fma_rn(-b, q, a), y, q);
+}
+
 __device__ __forceinline__ double gini_u32(const uint32_t* c, int C, double tot) {
     if (tot == 0.0) return 0.0;
+    const double y = __drcp_rn(tot);
     double imp = 1.0;
-    for (int k = 0; k < C; ++k) { double f = (double)c[k] / tot; imp -= f * f; }
+    for (int k = 0; k < C; ++k) { double f = div_rn((double)c[k], tot, y); imp -= f * f; }
     return imp;
 }
 
@@ -115,9 +125,10 @@ __device__ __forceinline__ double split_gain(const uint32_t* L, const uint32_t* 
     if (lc < (double)min_inst || rc < (double)min_inst) return -DBL_MAX;
     const double t = lc + rc;
     double gl = 1.0, gr = 1.0;
-    if (lc == 0.0) gl = 0.0; else for (int k = 0; k < C; ++k) { double f = (double)L[k] / lc; gl -= f * f; }
-    if (rc == 0.0) gr = 0.0; else for (int k = 0; k < C; ++k) { double f = (double)(tot[k] - L[k]) / rc; gr -= f * f; }
-    const double lw = lc / t, rw = rc / t;
+    if (lc == 0.0) gl = 0.0; else { const double y = __drcp_rn(lc); for (int k = 0; k < C; ++k) { double f = div_rn((double)L[k], lc, y); gl -= f * f; } }
+    if (rc == 0.0) gr = 0.0; else { const double y = __drcp_rn(rc); for (int k = 0; k < C; ++k) { double f = div_rn((double)(tot[k] - L[k]), rc, y); gr -= f * f; } }
+    const double yt = __drcp_rn(t);
+    const double lw = div_rn(lc, t, yt), rw = div_rn(rc, t, yt);
     const double gain = parent_imp - lw * gl - rw * gr;
     if (gain < min_gain) return -DBL_MAX;
     return gain;
@@ -125,14 +136,16 @@ __device__ __forceinline__ double split_gain(const uint32_t* L, const uint32_t* 
 
 constexpr int kScoreThreads = 256;
 
-// One CTA per slot, two phases so that the expensive part is balanced across the whole CTA:
-//   1. per feature of the node's subset (a warp each, looping): class-wise prefix sums over its bins in shared memory
-//      (continuous), or the centroid ranking + prefix sums in ranked order (ordered categorical), or the raw per-category
-//      counts (unordered categorical).  Cost ~ bins of that feature — uneven (2-bin flags next to 70-bin rates).
-//   2. ALL candidate splits of ALL staged features form one flat list (feature-major, split-minor = MLlib's scan order);
+// One CTA per slot.  The slot's histogram block is staged ONCE (all loads in flight together), then
+//   B. per feature of the node's subset (a warp each): class-wise prefix sums over its bins in shared memory, split into
+//      32/C lane segments (continuous); or the centroid ranking + prefix sums in ranked order (ordered categorical); or the
+//      raw per-category counts (unordered categorical).  The warp also lists the candidate splits that can win: a split
+//      whose left counts equal the previous split's (empty bin / category in between) has exactly the previous gain and
+//      "first max" never picks it, so only as many fp64 evaluations remain as there are occupied bins.
+//   C. ALL listed candidates of ALL staged features form one flat list (feature-major, split-minor = MLlib's scan order);
 //      thread t evaluates candidates t, t+256, ... in fp64 (calculateImpurityStats, no FMA) and keeps its first maximum;
-//      a shuffle/smem reduction with the (gain desc, feature asc, split asc) order reproduces "first max over splits, then
-//      first max over features".
+//      a shuffle/smem reduction under (gain desc, feature asc, split asc) reproduces "first max over splits, then first
+//      max over features".
 // Features are staged in batches when m * n_bins * C exceeds the shared-memory budget (DecisionTree: all features).
 __global__ void __launch_bounds__(kScoreThreads) score_level_kernel(
     const uint32_t* __restrict__ hist, int n_slots, const uint16_t* __restrict__ subset, int m, int n_bins, int C,
@@ -143,6 +156,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_level_kernel(
     const int tid = threadIdx.x, w = warp_id(), lane = lane_id(), nw = kScoreThreads / 32;
     const int nbC = n_bins * C;
     // layout: tot[C] | bestL[C] | per-warp {cen[n_bins] f64, raw[nbC] u32} (8-byte multiples) | cum[batch][nbC] | order[batch][n_bins]
+    //         | cand[batch][n_bins] u8
     uint32_t* tot = (uint32_t*)sm_raw;
     uint32_t* bestL = tot + C;
     const size_t per_warp = ((size_t)n_bins * 8 + (size_t)nbC * 4 + 7) & ~(size_t)7;
@@ -151,39 +165,35 @@ __global__ void __launch_bounds__(kScoreThreads) score_level_kernel(
     uint32_t* raw = (uint32_t*)(cen + n_bins);
     uint32_t* cum_all = (uint32_t*)(wbase + per_warp * nw);
     int* order_all = (int*)(cum_all + (size_t)batch * nbC);
-    __shared__ int sh_feat[64], sh_nsplit[64], sh_off[65], sh_kind[64], sh_nb[64];
+    uint8_t* cand_all = (uint8_t*)(order_all + (size_t)batch * n_bins);
+    __shared__ int sh_ncand[64], sh_kind[64], sh_nb[64];
     __shared__ double sh_wg[kScoreThreads / 32];
     __shared__ int sh_wj[kScoreThreads / 32], sh_ws[kScoreThreads / 32];
     __shared__ double sh_best_gain; __shared__ int sh_best_j, sh_best_s, sh_best_kind;
     __shared__ unsigned long long sh_best_mask[4];
 
     const uint32_t* h0 = hist + (int64_t)s * m * nbC;
-    {   // node class counts = sum over the bins of the first subset feature
-        const int nb0 = feat_bins[subset[(int64_t)s * m]];
-        for (int k = tid; k < C; k += kScoreThreads) { uint32_t a = 0; for (int b = 0; b < nb0; ++b) a += h0[b * C + k]; tot[k] = a; }
-    }
     if (tid == 0) { sh_best_gain = -DBL_MAX; sh_best_j = -1; sh_best_s = -1; sh_best_kind = 0; }
-    __syncthreads();
-    double ptot = 0.0;
-    for (int k = 0; k < C; ++k) ptot += (double)tot[k];
-    const double parent_imp = gini_u32(tot, C, ptot);
+    double parent_imp = 0.0;
 
     for (int j0 = 0; j0 < m; j0 += batch) {
         const int nb_feats = min(batch, m - j0);
-        // ---- phase 1: stage the batch
+        // ---- A: stage the batch's histograms (contiguous in global memory)
+        {
+            const uint32_t* src = h0 + (int64_t)j0 * nbC;
+            const int nwords = nb_feats * nbC;
+            for (int i = tid; i < nwords; i += kScoreThreads) cum_all[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        // ---- B: prefix sums + candidate lists, one warp per feature
         for (int jj = w; jj < nb_feats; jj += nw) {
             const int f = subset[(int64_t)s * m + j0 + jj];
             const int nb = feat_bins[f], kind = feat_kind[f];
-            const uint32_t* h = h0 + (int64_t)(j0 + jj) * nbC;
             uint32_t* cum = cum_all + (size_t)jj * nbC;
             int* order = order_all + (size_t)jj * n_bins;
-            if (lane == 0) { sh_feat[jj] = f; sh_kind[jj] = kind; sh_nb[jj] = nb; sh_nsplit[jj] = kind == 2 ? (1 << (nb - 1)) - 1 : nb - 1; }
-            if (kind == 0) {
-                for (int i = lane; i < nb * C; i += 32) cum[i] = h[i];
-                __syncwarp();
-                for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int b = 0; b < nb; ++b) { a += cum[b * C + k]; cum[b * C + k] = a; } }
-            } else if (kind == 1) {
-                for (int i = lane; i < nb * C; i += 32) raw[i] = h[i];
+            if (lane == 0) { sh_kind[jj] = kind; sh_nb[jj] = nb; }
+            if (kind == 1) {
+                for (int i = lane; i < nb * C; i += 32) raw[i] = cum[i];
                 __syncwarp();
                 for (int c = lane; c < nb; c += 32) {            // centroid per category
                     double cnt = 0.0;
@@ -198,21 +208,60 @@ __global__ void __launch_bounds__(kScoreThreads) score_level_kernel(
                 }
                 __syncwarp();
                 for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int i = 0; i < nb; ++i) { a += raw[order[i] * C + k]; cum[i * C + k] = a; } }
-            } else {
-                for (int i = lane; i < nb * C; i += 32) cum[i] = h[i];   // raw per-category counts; subsets are summed per candidate
-            }
+            } else if (kind == 0) {
+                if (C <= 16) {                                   // lane = (class k, bin segment): 32/C segments scanned side by side
+                    const int nseg = 32 / C, seg_len = (nb + nseg - 1) / nseg;
+                    const int k = lane % C, seg = lane / C;
+                    const bool act = seg < nseg;
+                    const int b0 = min(nb, seg * seg_len), b1 = act ? min(nb, b0 + seg_len) : b0;
+                    uint32_t a = 0;
+                    for (int b = b0; b < b1; ++b) a += cum[b * C + k];
+                    uint32_t run = 0;
+                    for (int s2 = 0; s2 < nseg; ++s2) { const uint32_t v = __shfl_sync(0xffffffffu, a, s2 * C + k); if (s2 < seg) run += v; }
+                    for (int b = b0; b < b1; ++b) { run += cum[b * C + k]; cum[b * C + k] = run; }
+                } else {
+                    for (int k = lane; k < C; k += 32) { uint32_t a = 0; for (int b = 0; b < nb; ++b) { a += cum[b * C + k]; cum[b * C + k] = a; } }
+                }
+            }                                                    // kind 2: raw per-category counts stay; subsets are summed per candidate
             __syncwarp();
+            if (j0 == 0 && jj == 0) {                            // node class counts = all bins of the first subset feature
+                for (int k = lane; k < C; k += 32) {
+                    uint32_t a;
+                    if (kind == 2) { a = 0; for (int c = 0; c < nb; ++c) a += cum[c * C + k]; }
+                    else a = cum[(nb - 1) * C + k];
+                    tot[k] = a;
+                }
+            }
+            uint8_t* cand = cand_all + (size_t)jj * n_bins;
+            const int ns = kind == 2 ? (1 << (nb - 1)) - 1 : nb - 1;
+            int n_cand = 0;
+            for (int sp0 = 0; sp0 < ns; sp0 += 32) {
+                const int sp = sp0 + lane;
+                bool keep = sp < ns;
+                if (keep && kind != 2 && sp > 0) {
+                    keep = false;
+                    for (int k = 0; k < C; ++k) keep |= cum[sp * C + k] != cum[(sp - 1) * C + k];
+                }
+                const uint32_t mk = __ballot_sync(0xffffffffu, keep);
+                if (keep) cand[n_cand + __popc(mk & ((1u << lane) - 1u))] = (uint8_t)sp;
+                n_cand += __popc(mk);
+            }
+            if (lane == 0) sh_ncand[jj] = n_cand;
         }
         __syncthreads();
-        if (tid == 0) { int o = 0; for (int jj = 0; jj < nb_feats; ++jj) { sh_off[jj] = o; o += max(sh_nsplit[jj], 0); } sh_off[nb_feats] = o; }
-        __syncthreads();
-        // ---- phase 2: every candidate split of the batch, flat over the CTA
-        const int n_items = sh_off[nb_feats];
+        if (j0 == 0) {                                           // parent impurity: once per warp, broadcast
+            double pi = 0.0;
+            if (lane == 0) { double ptot = 0.0; for (int k = 0; k < C; ++k) ptot += (double)tot[k]; pi = gini_u32(tot, C, ptot); }
+            parent_imp = __shfl_sync(0xffffffffu, pi, 0);
+        }
+        // ---- C: every listed candidate of the batch, flat over the CTA
+        int n_items = 0;
+        for (int jj = 0; jj < nb_feats; ++jj) n_items += sh_ncand[jj];
         double tbest = -DBL_MAX; int tj = -1, ts = -1;
         for (int it = tid; it < n_items; it += kScoreThreads) {
-            int jj = 0;
-            while (it >= sh_off[jj + 1]) ++jj;
-            const int sp = it - sh_off[jj];
+            int jj = 0, o = 0;
+            while (it >= o + sh_ncand[jj]) { o += sh_ncand[jj]; ++jj; }
+            const int sp = cand_all[(size_t)jj * n_bins + (it - o)];
             const uint32_t* cum = cum_all + (size_t)jj * nbC;
             double g;
             if (sh_kind[jj] != 2) {
@@ -225,9 +274,10 @@ __global__ void __launch_bounds__(kScoreThreads) score_level_kernel(
                 if (lc < (double)min_inst || rc < (double)min_inst) g = -DBL_MAX;
                 else {
                     const double t = lc + rc; double gl = 1.0, gr = 1.0;
-                    if (lc == 0.0) gl = 0.0; else for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += cum[c * C + k]; const double fq = (double)a / lc; gl -= fq * fq; }
-                    if (rc == 0.0) gr = 0.0; else for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += cum[c * C + k]; const double fq = (double)(tot[k] - a) / rc; gr -= fq * fq; }
-                    const double lw = lc / t, rw = rc / t;
+                    if (lc == 0.0) gl = 0.0; else { const double y = __drcp_rn(lc); for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += cum[c * C + k]; const double fq = div_rn((double)a, lc, y); gl -= fq * fq; } }
+                    if (rc == 0.0) gr = 0.0; else { const double y = __drcp_rn(rc); for (int k = 0; k < C; ++k) { uint32_t a = 0; for (int c = 0; c < nb; ++c) if ((bits >> c) & 1u) a += cum[c * C + k]; const double fq = div_rn((double)(tot[k] - a), rc, y); gr -= fq * fq; } }
+                    const double yt = __drcp_rn(t);
+                    const double lw = div_rn(lc, t, yt), rw = div_rn(rc, t, yt);
                     g = parent_imp - lw * gl - rw * gr;
                     if (g < min_gain) g = -DBL_MAX;
                 }
@@ -239,15 +289,17 @@ __global__ void __launch_bounds__(kScoreThreads) score_level_kernel(
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double og = __shfl_xor_sync(0xffffffffu, g, o); const int oj = __shfl_xor_sync(0xffffffffu, bj, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
-            if (oj >= 0 && og > -DBL_MAX && (bj < 0 || !(g > -DBL_MAX) || og > g || (og == g && (oj < bj || (oj == bj && os < bs))))) { g = og; bj = oj; bs = os; }
+            if (oj >= 0 && (bj < 0 || og > g || (og == g && (oj < bj || (oj == bj && os < bs))))) { g = og; bj = oj; bs = os; }
         }
-        if (lane == 0) { sh_wg[w] = g; sh_wj[w] = (g > -DBL_MAX) ? bj : -1; sh_ws[w] = bs; }
+        if (lane == 0) { sh_wg[w] = g; sh_wj[w] = bj; sh_ws[w] = bs; }
         __syncthreads();
         if (tid == 0) {
             double bg = sh_best_gain; int gj = sh_best_j, gs = sh_best_s; bool improved = false;
-            for (int q = 0; q < nw; ++q)
-                if (sh_wj[q] >= 0 && (sh_wg[q] > bg)) { bg = sh_wg[q]; gj = sh_wj[q]; gs = sh_ws[q]; improved = true; }
-                else if (sh_wj[q] >= 0 && improved && sh_wg[q] == bg && (sh_wj[q] < gj || (sh_wj[q] == gj && sh_ws[q] < gs))) { gj = sh_wj[q]; gs = sh_ws[q]; }
+            for (int q = 0; q < nw; ++q) {
+                if (sh_wj[q] < 0) continue;
+                if (sh_wg[q] > bg) { bg = sh_wg[q]; gj = sh_wj[q]; gs = sh_ws[q]; improved = true; }
+                else if (improved && sh_wg[q] == bg && (sh_wj[q] < gj || (sh_wj[q] == gj && sh_ws[q] < gs))) { gj = sh_wj[q]; gs = sh_ws[q]; }
+            }
             if (improved) {                                           // earlier batches win ties (their features come first)
                 sh_best_gain = bg; sh_best_j = gj; sh_best_s = gs;
                 const int jj = gj - j0; const int kind = sh_kind[jj], nb = sh_nb[jj];
@@ -759,7 +811,7 @@ extern "C" int b200flow_score_level(const uint32_t* hist, int32_t n_slots, const
     B2F_REQUIRE(m > 0 && n_bins > 0 && n_bins <= 256 && C > 0 && C <= 256, "score_level: bad shape");
     if (n_slots <= 0) return B200FLOW_OK;
     // shared memory: tot + bestL + per-feature {prefix sums, rank order} for a batch of features + per-warp scratch
-    const size_t per_feat = (size_t)n_bins * C * 4 + (size_t)n_bins * 4;
+    const size_t per_feat = (size_t)n_bins * C * 4 + (size_t)n_bins * 4 + (size_t)n_bins;
     const size_t per_warp = ((size_t)n_bins * 8 + (size_t)n_bins * C * 4 + 7) & ~(size_t)7;
     const size_t fixed = (size_t)2 * C * 4 + 16 + per_warp * (kScoreThreads / 32) + 16;
     int batch = m < 64 ? m : 64;

@@ -145,3 +145,9 @@ def test_metadata_unordered_rule():
     with pytest.raises(ValueError):
         oracle.build_metadata(10 ** 6, 41, 2, [0] * 38 + [3, 70, 11], 32, 1)
     assert oracle.build_metadata(10 ** 6, 78, 15, [0] * 78, 78, 20)[2] == 9
+
+
+def test_shared_reciprocal_division_is_correctly_rounded():
+    # forest.cu scores splits with q = RN(a*y), RN(q + (a - b*q)*y), y = RN(1/b) instead of a division per class count;
+    # Markstein's theorem makes that the correctly rounded a/b for integer operands — checked here against `/`
+    assert oracle.check_shared_reciprocal_division(3000, 100_000_000) == 0
