@@ -156,9 +156,10 @@ def step_resident(rec, dicts, a, grp):
     dev = rec.device
     n = rec.shape[0]
     luts, ordered = {}, {}
-    for c in synth.KDD_CATEGORICAL + ["label"]:                                     # R1 StringIndexer.fit
-        cnt = bdist.all_reduce_sum_(enc.category_counts(rec, schema, c, len(dicts[c])), grp).cpu().numpy()
-        ordered[c], luts[c] = enc.string_index_order(cnt, dicts[c])
+    cols = synth.KDD_CATEGORICAL + ["label"]                                        # R1 StringIndexer.fit (4 columns, one sync)
+    counts = [bdist.all_reduce_sum_(enc.category_counts(rec, schema, c, len(dicts[c])), grp) for c in cols]
+    for c, cnt in zip(cols, counts):
+        ordered[c], luts[c] = enc.string_index_order(cnt.cpu().numpy(), dicts[c])
     plan = enc.EncodePlan(schema)
     for c in synth.KDD_COLUMNS:
         if c not in synth.KDD_CATEGORICAL and c != "label":

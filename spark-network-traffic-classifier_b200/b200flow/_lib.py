@@ -111,6 +111,16 @@ def call(name, *args):
         raise B200FlowError("%s failed (%d): %s" % (name, rc, lib.b200flow_last_error().decode()))
 
 
+def h2d(a, device):
+    """small host array -> device tensor through a pinned staging block, asynchronously.  A pageable cudaMemcpy blocks the
+    host until the stream reaches it, which stops the level loop from running ahead of the GPU; pinned + non_blocking does
+    not (torch's caching host allocator keeps the block alive until the copy has run)."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if torch.device(device).type != "cuda":
+        return t.clone()
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise B200FlowError("no CUDA device: the b200flow product path has no CPU fallback")

@@ -126,9 +126,9 @@ class EncodePlan:
     # ---- running --------------------------------------------------------------------
     def _device_tables(self, device):
         if self._dev is None or self._dev[0] != device:
-            slots = torch.from_numpy(self.slot_array().view(np.uint8).copy()).to(device)
+            slots = _lib.h2d(self.slot_array().view(np.uint8), device)
             lut = self.lut_array()
-            lut_t = torch.from_numpy(lut.copy()).to(device) if len(lut) else None
+            lut_t = _lib.h2d(lut, device) if len(lut) else None
             self._dev = (device, slots, lut_t, len(lut))
         return self._dev
 

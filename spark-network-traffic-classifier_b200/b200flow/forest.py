@@ -136,7 +136,7 @@ def dedup_rows(tp, key_bytes):
 
 
 def _i32(a, dev):
-    return torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(dev)
+    return _lib.h2d(np.ascontiguousarray(a, np.int32), dev)
 
 
 class ForestModel:
@@ -318,7 +318,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     # ---- R6 bagging: W[tree][unique] = summed Poisson weights; entries = non-zero (unique, weight) pairs per tree
     bagging = p.bootstrap and T > 1
     cdf_host = np.ascontiguousarray(poisson_cdf_table(p.subsampling_rate)) if bagging else None
-    cdf = torch.from_numpy(cdf_host.view(np.int32).copy()).to(dev) if bagging else None
+    cdf = _lib.h2d(cdf_host.view(np.int32), dev) if bagging else None
     nb = (U + 1023) // 1024
     W = torch.zeros(max(T * U, 1), dtype=torch.int32, device=dev)
     if n > 0:
@@ -351,7 +351,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     node_tree = torch.zeros(cap_nodes, dtype=torch.int32, device=dev)
     node_gain = torch.zeros(cap_nodes, dtype=torch.float64, device=dev)
     root = np.zeros(T, NODE_DTYPE); root["feat"] = -1; root["left"] = -1; root["nid"] = 1
-    nodes[:T] = torch.from_numpy(root.view(np.uint8).reshape(T, 16).copy()).to(dev)
+    nodes[:T] = _lib.h2d(root.view(np.uint8).reshape(T, 16), dev)
     node_tree[:T] = torch.arange(T, dtype=torch.int32, device=dev)
     pool_size = T
 
@@ -432,7 +432,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     if fused and n_slots * hsz * 4 <= HIST_BUDGET_BYTES and E > 0:
         # level 0 through the same kernel: T pseudo-parents whose split sends every entry "left" into the tree's root
         pseudo = np.zeros(T, SPLIT_DTYPE); pseudo["bin_thr"] = 255; pseudo["flags"] = 4
-        pseudo_t = torch.from_numpy(pseudo.view(np.uint8).reshape(T, 64).copy()).to(dev)
+        pseudo_t = _lib.h2d(pseudo.view(np.uint8).reshape(T, 64), dev)
         child0 = torch.stack([torch.arange(T, dtype=torch.int32, device=dev),
                               torch.full((T,), -1, dtype=torch.int32, device=dev)], 1).contiguous().view(-1)
         cursors0 = torch.zeros(2 * T, dtype=torch.int32, device=dev)
@@ -480,7 +480,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         # grow the pool by this level's children and emit the next level's slots
         nblk = (n_slots + 255) // 256
         counters = torch.zeros(8 + nblk + 1, dtype=torch.int64, device=dev)   # [pool, n_next, overflow, pool_before, route chunks, ...]
-        counters[0] = pool_size
+        counters[0:1].fill_(pool_size)                   # a kernel argument, not a pageable H2D copy (which would block the host)
         next_tree = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_nid = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_node = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
