@@ -206,7 +206,10 @@ def step_e2e(host_rec, dicts, a):
     pred = rf.fit(train).transform(test)
     ev = MulticlassClassificationEvaluator(labelCol="label_num", predictionCol="prediction", metricName="macroF1")
     f1 = ev.evaluate(pred)
-    host_pred = pred._cols["prediction"].data.cpu()                                 # D2H of the step's result
+    dev_pred = pred._cols["prediction"].data                                        # D2H of the step's result (pinned)
+    host_pred = torch.empty(dev_pred.shape, dtype=dev_pred.dtype, pin_memory=True)
+    host_pred.copy_(dev_pred, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
     return f1, host_pred
 
 

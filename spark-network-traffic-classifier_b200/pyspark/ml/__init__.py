@@ -32,6 +32,10 @@ class Pipeline(Estimator):
             if not isinstance(s, (Estimator, Transformer)):
                 raise TypeError("Cannot recognize a pipeline stage of type %s." % type(s))
         last_est = max([i for i, s in enumerate(stages) if isinstance(s, Estimator)], default=-1)
+        from .feature import StringIndexer, _prefetch_category_counts
+        for s in stages:                                   # enqueue every StringIndexer's count kernel before the first host read
+            if isinstance(s, StringIndexer) and hasattr(dataset, "_cat_counts"):
+                _prefetch_category_counts(dataset, s.getOrDefault("inputCol"))
         fitted, cur = [], dataset
         for i, s in enumerate(stages):
             if isinstance(s, Estimator):

@@ -11,7 +11,7 @@ import torch
 
 from b200flow import dist as bdist
 from b200flow import encode as enc
-from b200flow._lib import B200FlowError
+from b200flow._lib import SRC_F32, SRC_INDEX, SRC_ONEHOT, B200FlowError
 from b200flow.encode import EncodePlan, RecordSchema
 
 from . import Estimator, Model, Transformer
@@ -45,6 +45,27 @@ def _materialize(df, name):
     return (d.reshape(d.shape[0], -1) if d.dim() == 1 else d).to(torch.float64).contiguous()
 
 
+def _prefetch_category_counts(df, col):
+    """enqueue the count kernel of a raw code field without waiting for it (Pipeline.fit does this for every
+    StringIndexer stage up front, so the four fits of kdd99.py:34-37 cost one host sync instead of four)."""
+    if df._rec is None or col not in df._cols or col in df._cat_counts:
+        return
+    c = df._cols[col]
+    if c.kind == "field" and df._schema.type_of[col] == "code":
+        cnt = enc.category_counts(df._rec, df._schema, col, max(len(df._dicts[col]), 1))
+        df._cat_counts[col] = bdist.all_reduce_sum_(cnt)               # ranks share the dictionaries
+
+
+def _category_counts(df, col):
+    """global category counts of a raw code field as a host array (cached per record buffer)."""
+    _prefetch_category_counts(df, col)
+    cnt = df._cat_counts[col]
+    if torch.is_tensor(cnt):
+        cnt = cnt.cpu().numpy()[:len(df._dicts[col])]
+        df._cat_counts[col] = cnt
+    return cnt
+
+
 # ----------------------------------------------------------------------------------- StringIndexer
 class StringIndexer(Estimator):
     _defaults = {"inputCol": None, "outputCol": None, "handleInvalid": "error", "stringOrderType": "frequencyDesc"}
@@ -60,8 +81,7 @@ class StringIndexer(Estimator):
         order = self.getOrDefault("stringOrderType")
         if c.kind == "field" and df._schema.type_of[col] == "code":
             strings = df._dicts[col]
-            counts = enc.category_counts(df._rec, df._schema, col, max(len(strings), 1))
-            counts = bdist.all_reduce_sum_(counts).cpu().numpy()[:len(strings)]     # ranks share the dictionaries
+            counts = _category_counts(df, col)
         else:                                              # numeric column: cast to string like Spark does
             vals, cnt = torch.unique(_materialize(df, col)[:, 0], return_counts=True)
             keep = ~torch.isnan(vals)
@@ -113,8 +133,17 @@ class StringIndexerModel(Model):
             prov_ok = False
         lut = np.array([rank_of.get(s, K if hi == "keep" else -1) for s in strings] or [0], np.int32)
         plan = EncodePlan(schema).add_index(field, lut)
-        vals, _, valid = plan.run(rec, torch.float64)
         labels = self.labels + (["__unknown"] if hi == "keep" else [])
+        if prov_ok and col in df._cat_counts and (hi == "keep" or
+                                                  int(np.asarray(_category_counts(df, col))[lut[:len(strings)] < 0].sum()) == 0):
+            # every row's label is known (the counts of this very record buffer say so): nothing to check, nothing to drop.
+            # The index column is fully described by its provenance, so its kernel is deferred until the values are read —
+            # VectorAssembler fuses the lookup into the one encode pass instead (SURVEY 8a R2+R3).
+            newc = ColumnData("numeric", None, "f64", {"ml_attr": {"type": "nominal", "vals": labels}},
+                              ("index", field, lut, labels), thunk=lambda: plan.run(rec, torch.float64, want_valid=False)[0].view(-1))
+            cols = dict(df._cols); cols[out] = newc
+            return df._with(cols=cols)
+        vals, _, valid = plan.run(rec, torch.float64)
         newc = ColumnData("numeric", vals.view(-1), "f64", {"ml_attr": {"type": "nominal", "vals": labels}},
                           ("index", field, lut, labels) if prov_ok else None)
         cols = dict(df._cols); cols[out] = newc
@@ -172,7 +201,10 @@ class VectorAssembler(Transformer):
                 else:
                     raise B200FlowError("unknown provenance %r" % (p,))
             plan.check_nan = 1
-            feats, _, valid = plan.run(df._rec, torch.float64)
+            # f32 record fields, index ranks and one-hot flags are exact in f32: keep the vector in f32 (half the bytes through
+            # assemble, randomSplit and binning); values widen to the same doubles whenever they are read as f64
+            exact32 = all(s[0] in (SRC_F32, SRC_INDEX, SRC_ONEHOT) and s[5] == 0.0 and s[6] == 1.0 for s in plan.slots)
+            feats, _, valid = plan.run(df._rec, torch.float32 if exact32 else torch.float64)
             prov = ("plan", plan)
         else:                                               # columns without raw provenance: concatenate, then one pass
             parts = [_materialize(df, c) for c in cols_in]
@@ -191,7 +223,7 @@ class VectorAssembler(Transformer):
             plan.check_nan = 1
             feats, _, valid = plan.run(dense.view(torch.uint8).reshape(dense.shape[0], -1), torch.float64)
             prov = None
-        newc = ColumnData("vector", feats, "f64", {"attrs": attrs}, prov)
+        newc = ColumnData("vector", feats, "f32" if feats.dtype == torch.float32 else "f64", {"attrs": attrs}, prov)
         cols = dict(df._cols); cols[out] = newc
         res = df._with(cols=cols)
         if hi != "keep":

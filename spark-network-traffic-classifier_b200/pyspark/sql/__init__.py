@@ -25,8 +25,21 @@ class ColumnData:
     'vector' ([n, D] tensor).  meta carries ML attributes (nominal values / per-slot attrs);
     prov records how the column derives from raw record fields so later stages can fuse."""
 
-    def __init__(self, kind, data=None, dtype=None, meta=None, prov=None):
-        self.kind, self.data, self.dtype, self.meta, self.prov = kind, data, dtype, dict(meta or {}), prov
+    def __init__(self, kind, data=None, dtype=None, meta=None, prov=None, thunk=None):
+        self.kind, self._data, self.dtype, self.meta, self.prov = kind, data, dtype, dict(meta or {}), prov
+        self._thunk = thunk                    # lazy column: () -> tensor, run on first access of .data
+
+    @property
+    def data(self):
+        """the column's tensor.  A transformer whose output is fully described by `prov` (e.g. StringIndexerModel on a raw
+        code field) defers its kernel until somebody reads the values — a later VectorAssembler fuses it instead."""
+        if self._data is None and self._thunk is not None:
+            self._data, self._thunk = self._thunk(), None
+        return self._data
+
+    @data.setter
+    def data(self, v):
+        self._data, self._thunk = v, None
 
 
 class Column:
@@ -170,8 +183,11 @@ class _GroupedData:
 
 # ----------------------------------------------------------------------------------- DataFrame
 class DataFrame:
-    def __init__(self, n, rec, schema, dicts, cols, session=None):
+    def __init__(self, n, rec, schema, dicts, cols, session=None, cat_counts=None):
         self._n = int(n)
+        # per-record-buffer cache of category counts of raw code fields (device tensor while pending, numpy once read):
+        # shared by every DataFrame that views the same record buffer, dropped when rows are filtered
+        self._cat_counts = cat_counts if cat_counts is not None else {}
         self._rec, self._schema, self._dicts = rec, schema, dict(dicts or {})
         self._cols = cols                      # ordered: name -> ColumnData
         self._session = session
@@ -194,15 +210,17 @@ class DataFrame:
         return DataFrame(rec.shape[0], rec, schema, dicts, cols, session)
 
     def _with(self, cols=None, n=None, rec="same", dicts=None):
+        same = isinstance(rec, str) and n is None and dicts is None
         return DataFrame(self._n if n is None else n, self._rec if isinstance(rec, str) else rec, self._schema,
-                         self._dicts if dicts is None else dicts, dict(self._cols) if cols is None else cols, self._session)
+                         self._dicts if dicts is None else dicts, dict(self._cols) if cols is None else cols, self._session,
+                         self._cat_counts if same else None)
 
     def _device(self):
         if self._rec is not None:
             return self._rec.device
         for c in self._cols.values():
-            if c.data is not None:
-                return c.data.device
+            if c._data is not None:
+                return c._data.device
         return torch.device("cuda")
 
     # ---- basic API

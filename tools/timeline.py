@@ -6,13 +6,21 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "spark-network-t
 import torch, bench
 from torch.profiler import profile, ProfilerActivity
 from b200flow import synth
+E2E = "--shim" in sys.argv
+if E2E:
+    sys.argv.remove("--shim")
 a = bench.parse()
 rec, dicts = synth.make_kdd(a.rows, a.classes, seed=2019, device="cuda")
+if E2E:                                                  # the pyspark.ml-shaped path from pinned host records
+    host = rec.cpu().pin_memory(); del rec
+    step = lambda: bench.step_e2e(host, dicts, a)
+else:
+    step = lambda: bench.step_resident(rec, dicts, a, None)
 for _ in range(3):
-    bench.step_resident(rec, dicts, a, None)
+    step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    bench.step_resident(rec, dicts, a, None)
+    step()
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: e.time_range.start)
@@ -26,10 +34,18 @@ for i, e in enumerate(ev):
 print("span %.3f ms, busy %.3f ms, idle %.3f ms, %d device activities" % ((t1 - t0) / 1e3, busy / 1e3, (t1 - t0 - busy) / 1e3, len(ev)))
 gaps.sort(reverse=True)
 print("largest gaps (us) : after -> before   @ms")
-for g in gaps[:40]:
+for g in gaps[:int(os.environ.get("GAPS", "40"))]:
     print("%8.1f  %-60s -> %-60s @%.2f" % g)
 import collections
 hist = collections.Counter()
 for g in gaps:
     hist["<5us" if g[0] < 5 else "<20us" if g[0] < 20 else "<100us" if g[0] < 100 else ">=100us"] += g[0]
 print({k: round(v / 1e3, 3) for k, v in hist.items()}, "ms by gap size;", len(gaps), "gaps")
+
+import collections as _c
+agg = _c.defaultdict(lambda: [0, 0.0])
+for e in ev:
+    k = e.name.split("(")[0][:70]; agg[k][0] += 1; agg[k][1] += (e.time_range.end - e.time_range.start) / 1e3
+print("device activities by total time (ms):")
+for k, v in sorted(agg.items(), key=lambda x: -x[1][1])[:int(os.environ.get("TOPK", "25"))]:
+    print("%9.3f %5d  %s" % (v[1], v[0], k))
