@@ -46,6 +46,10 @@ def profile_totals():
 
 
 HIST_BUDGET_BYTES = 4 << 30        # node-group cap for the histogram buffer (MLlib: maxMemoryInMB)
+# Multi-GPU: level histograms of at least this many bytes are REDUCE-SCATTERED by node (each rank then scores only its own
+# nodes and the 64-byte split records are all-gathered) instead of all-reduced: half the NVLink bytes, 1/world of the scoring.
+# Smaller levels are latency-bound and keep the single all-reduce.
+RS_MIN_BYTES = int(_os.environ.get("B200FLOW_RS_MIN_BYTES", str(8 << 20)))
 
 
 @dataclass
@@ -412,11 +416,35 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
 
     route_chunks_max = E // route_ch + 1                 # + one ragged chunk per parent slot, added per call
 
+    world = dist.get_world_size(group) if group is not None else 1
+    rank = dist.get_rank(group) if group is not None else 0
+    REC = 64 + 12 * C                                    # bytes per slot of the scored result: split record + 3 count vectors
+
+    def score_sharded(h_full, gs, sub, lvl, split_, nc_, lc_, rc_):
+        """R7r + R8 over `world` ranks: reduce-scatter the level histograms by node block, score this rank's block, all-gather
+        the results.  h_full holds world * per slots (the tail beyond gs is zero padding)."""
+        per = -(-gs // world)
+        mine = torch.empty(per * hsz, dtype=torch.int32, device=dev)
+        dist.reduce_scatter_tensor(mine, h_full[:world * per * hsz], group=group)
+        lo = rank * per
+        cnt = max(0, min(per, gs - lo))
+        local = torch.empty(per * REC, dtype=torch.uint8, device=dev)
+        sec = [local[:per * 64], local[per * 64:per * (64 + 4 * C)], local[per * (64 + 4 * C):per * (64 + 8 * C)], local[per * (64 + 8 * C):]]
+        if cnt > 0:
+            _timed("score_level", "b200flow_score_level", ptr(mine), cnt, ptr(sub[lo:lo + cnt]), m, n_bins, C, ptr(feat_bins), ptr(feat_kind),
+                   lvl, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(sec[0]), ptr(sec[1]), ptr(sec[2]), ptr(sec[3]))
+        gathered = torch.empty((world, per * REC), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, local, group=group)
+        o = 0
+        for dst, width in ((split_, 64), (nc_.view(torch.uint8), 4 * C), (lc_.view(torch.uint8), 4 * C), (rc_.view(torch.uint8), 4 * C)):
+            dst.view(-1)[:world * per * width].view(world, per * width).copy_(gathered[:, o:o + per * width])
+            o += per * width
+
     def run_route(roff, rch_dev, n_parents, split_, child_slot_, cursors_, next_subset_, n_next_cap):
         """fused pass: route the entries of the planned parent slots to their children and build the children's histograms
         (returns the zero-initialised, now filled, histogram buffer of the next level).  The chunk count stays on the device
         (rch_dev), so the pass can be enqueued before the host knows how many children were created."""
-        hist_next = torch.zeros(n_next_cap * hsz, dtype=torch.int32, device=dev)
+        hist_next = torch.zeros((n_next_cap + world - 1) * hsz, dtype=torch.int32, device=dev)   # + padding for the node-block scatter
         cmax = route_chunks_max + n_parents
         scratch = torch.empty(cmax * 4, dtype=torch.int32, device=dev)
         _timed("route_hist_level", "b200flow_route_hist_level", ptr(tp), stride, F, ptr(ent), ptr(ent2), n_parents,
@@ -437,15 +465,17 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                               torch.full((T,), -1, dtype=torch.int32, device=dev)], 1).contiguous().view(-1)
         cursors0 = torch.zeros(2 * T, dtype=torch.int32, device=dev)
         roff0 = plan_route(torch.ones(T, dtype=torch.bool, device=dev), seg_end - seg_begin, total)
-        hist_ready = run_route(roff0, total, T, pseudo_t, child0, cursors0, subset, T)
+        hist_full = run_route(roff0, total, T, pseudo_t, child0, cursors0, subset, T)
+        hist_ready = hist_full[:T * hsz]
         ent, ent2 = ent2, ent          # the pass copied every entry into the other buffer, same segments
     while n_slots > 0:
         grow_pool(pool_size + 2 * n_slots)
         lens = seg_end - seg_begin
-        split = torch.empty((n_slots, 64), dtype=torch.uint8, device=dev)
-        node_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
-        left_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
-        right_counts = torch.empty((n_slots, C), dtype=torch.int32, device=dev)
+        n_alloc = n_slots + world - 1                        # room for the padded node blocks of the sharded scoring
+        split = torch.empty((n_alloc, 64), dtype=torch.uint8, device=dev)
+        node_counts = torch.empty((n_alloc, C), dtype=torch.int32, device=dev)
+        left_counts = torch.empty((n_alloc, C), dtype=torch.int32, device=dev)
+        right_counts = torch.empty((n_alloc, C), dtype=torch.int32, device=dev)
         chunk_off = None
         if hist_ready is None:
             nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()
@@ -469,6 +499,10 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                 stats["hist_launches"] += 1
                 if PROFILE is not None:
                     PROFILE.setdefault("_hist_entries", []).append(lens[g0:g1].sum())
+            if group is not None and hist_ready is not None and gs * hsz * 4 >= RS_MIN_BYTES and world > 1:
+                score_sharded(hist_full, gs, subset, level, split, node_counts, left_counts, right_counts)
+                del h
+                continue
             if group is not None:                       # R7r: the one data-path collective
                 dist.all_reduce(h, group=group)
             # R8 HOT LOOP B
@@ -476,6 +510,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                    level, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(split[g0:g1]),
                    ptr(node_counts[g0:g1]), ptr(left_counts[g0:g1]), ptr(right_counts[g0:g1]))
             del h
+        split, node_counts, left_counts, right_counts = split[:n_slots], node_counts[:n_slots], left_counts[:n_slots], right_counts[:n_slots]
         hist_ready = None
         # grow the pool by this level's children and emit the next level's slots
         nblk = (n_slots + 255) // 256
@@ -523,6 +558,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         next_tree, next_nid, next_node = next_tree[:n_next], next_nid[:n_next], next_node[:n_next]
         if speculative:
             hist_ready = hist_next[:n_next * hsz]             # only the slots that exist travel through the all-reduce
+            hist_full = hist_next                             # (+ zero padding: the reduce-scatter path needs equal node blocks)
             next_subset, next_begin, next_end = next_subset[:n_next], next_begin[:n_next], next_end[:n_next]
         else:
             next_subset = level_subsets(n_next, next_tree, next_nid)

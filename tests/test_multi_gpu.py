@@ -44,8 +44,11 @@ def _worker(rank, world, port, out_dir):
         off, _ = bdist.global_offset(hi - lo, dev)
         model = fr.fit_forest(x, y, len(ordered["label"]), arity, p, row_offset=off, group=bdist.group())
         ex = model.export()
+        fr.RS_MIN_BYTES = 0            # every level through reduce-scatter -> sharded scoring -> all-gather of the split records
+        ex_rs = fr.fit_forest(x, y, len(ordered["label"]), arity, p, row_offset=off, group=bdist.group()).export()
         if rank == 0:
             np.savez(os.path.join(out_dir, "sharded.npz"), **ex)
+            np.savez(os.path.join(out_dir, "sharded_rs.npz"), **ex_rs)
             xf, yf, _ = plan.run(rec, torch.float64)
             single = fr.fit_forest(xf, yf, len(ordered["label"]), arity, p).export()
             np.savez(os.path.join(out_dir, "single.npz"), **single)
@@ -60,6 +63,8 @@ def test_two_gpu_forest_is_byte_identical_to_one_gpu(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     a, b = np.load(tmp_path / "sharded.npz"), np.load(tmp_path / "single.npz")
     assert sorted(a.files) == sorted(b.files)
+    c = np.load(tmp_path / "sharded_rs.npz")
     for k in a.files:
         assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(c[k], b[k]), "reduce-scatter path: " + k
     assert len(a["nid"]) > 500
