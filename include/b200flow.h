@@ -261,6 +261,12 @@ int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
                               const uint16_t* subset_next, int32_t m, int32_t n_bins, int32_t C,
                               uint32_t* hist_next, void* stream);
 
+/* routing plan of a scored level: n_chunks[s] = ceil(len(s) / chunk_rows) for a split parent with at least one non-leaf
+ * child, else 0 (its exclusive scan is route_hist_level's chunk_off); also scatters split[s].gain into node_gain[slot_node[s]]
+ * when node_gain != NULL (TreeEnsembleModel.featureImportances needs the gains; MLlib keeps them in the Node objects). */
+int b200flow_plan_route(int32_t n_slots, const b200flow_split* split, const int64_t* seg_begin, const int64_t* seg_end,
+                        int32_t chunk_rows, const int32_t* slot_node, double* node_gain, int32_t* n_chunks, void* stream);
+
 /* segment table of the next level from the parents' ranges and the partition cursors */
 int b200flow_next_segments(int32_t n_next /* or an upper bound */, const int64_t* n_next_dev /* NULL or the device-side count */,
                            const int32_t* next_parent,

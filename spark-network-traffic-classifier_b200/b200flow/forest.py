@@ -405,13 +405,15 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         call("b200flow_feature_subsets", seed, ns, ptr(s_tree), ptr(s_nid), F, m, ptr(sub))
         return sub
 
-    def plan_route(routed, lens_, total_out):
-        """enqueue the chunk table of a fused routing pass; the chunk count lands in the device scalar `total_out`."""
-        nch = torch.where(routed, (lens_ + (route_ch - 1)) // route_ch, torch.zeros_like(lens_)).to(torch.int32).contiguous()
-        roff = torch.empty(nch.shape[0] + 1, dtype=torch.int64, device=dev)
-        call("b200flow_exclusive_scan_i32_to_i64", ptr(nch), nch.shape[0], ptr(roff), ptr(total_out))
+    def plan_route(ns, split_, begin_, end_, total_out, s_node=None, gain_out=None):
+        """enqueue the chunk table of a fused routing pass (+ the gains of the scored nodes); the chunk count lands in the
+        device scalar `total_out`."""
+        nch = torch.empty(ns, dtype=torch.int32, device=dev)
+        call("b200flow_plan_route", ns, ptr(split_), ptr(begin_), ptr(end_), route_ch, ptr(s_node), ptr(gain_out), ptr(nch))
+        roff = torch.empty(ns + 1, dtype=torch.int64, device=dev)
+        call("b200flow_exclusive_scan_i32_to_i64", ptr(nch), ns, ptr(roff), ptr(total_out))
         if PROFILE is not None:
-            PROFILE.setdefault("_route_entries", []).append(torch.where(routed, lens_, torch.zeros_like(lens_)).sum())
+            PROFILE.setdefault("_route_entries", []).append(torch.where(nch > 0, end_ - begin_, torch.zeros_like(end_)).sum())
         return roff
 
     route_chunks_max = E // route_ch + 1                 # + one ragged chunk per parent slot, added per call
@@ -464,13 +466,13 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         child0 = torch.stack([torch.arange(T, dtype=torch.int32, device=dev),
                               torch.full((T,), -1, dtype=torch.int32, device=dev)], 1).contiguous().view(-1)
         cursors0 = torch.zeros(2 * T, dtype=torch.int32, device=dev)
-        roff0 = plan_route(torch.ones(T, dtype=torch.bool, device=dev), seg_end - seg_begin, total)
+        roff0 = plan_route(T, pseudo_t, seg_begin, seg_end, total)
         hist_full = run_route(roff0, total, T, pseudo_t, child0, cursors0, subset, T)
         hist_ready = hist_full[:T * hsz]
         ent, ent2 = ent2, ent          # the pass copied every entry into the other buffer, same segments
     while n_slots > 0:
         grow_pool(pool_size + 2 * n_slots)
-        lens = seg_end - seg_begin
+        lens = (seg_end - seg_begin) if hist_ready is None else None   # only the unfused kernels need the lengths on the host side
         n_alloc = n_slots + world - 1                        # room for the padded node blocks of the sharded scoring
         split = torch.empty((n_alloc, 64), dtype=torch.uint8, device=dev)
         node_counts = torch.empty((n_alloc, C), dtype=torch.int32, device=dev)
@@ -524,16 +526,14 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
         _timed("grow_level", "b200flow_grow_level", n_slots, ptr(slot_tree), ptr(slot_nid), ptr(slot_node), ptr(split), ptr(node_counts),
                ptr(left_counts), ptr(right_counts), C, ptr(nodes), ptr(node_mask), ptr(pool_counts), ptr(node_tree),
                cap_nodes, ptr(next_tree), ptr(next_nid), ptr(next_node), ptr(next_parent), ptr(child_slot), ptr(counters))
-        node_gain[slot_node.long()] = split.view(torch.float64)[:, 2]
         n_cap = 2 * n_slots                              # upper bound on the number of next-level slots
         speculative = fused and n_cap * hsz * 4 <= HIST_BUDGET_BYTES
+        if not speculative:
+            node_gain[slot_node.long()] = split.view(torch.float64)[:, 2]
         if speculative:
             # Everything the next level needs is enqueued NOW with device-side counts (children created, routing chunks);
             # the host reads the counts on a side stream while the routing pass runs, so the GPU never waits for Python.
-            ev_grown = torch.cuda.Event(); ev_grown.record()
-            flags = split.view(torch.int32)[:, 3]
-            routed = ((flags & 1) == 0) & ((flags & 6) != 6)          # split parents with at least one non-leaf child
-            roff = plan_route(routed, lens, counters[4:5])
+            roff = plan_route(n_slots, split, seg_begin, seg_end, counters[4:5], slot_node, node_gain)
             ev_planned = torch.cuda.Event(); ev_planned.record()
             with torch.cuda.stream(side_stream):
                 side_stream.wait_event(ev_planned)
@@ -564,6 +564,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
             next_subset = level_subsets(n_next, next_tree, next_nid)
             cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
             if chunk_off is None:
+                lens = seg_end - seg_begin
                 nch = ((lens + (CHUNK_ROWS - 1)) // CHUNK_ROWS).to(torch.int32).contiguous()
                 chunk_off, n_chunks = chunk_table(nch)
             _timed("partition_level", "b200flow_partition_level", ptr(tp), stride, ptr(ent), ptr(ent2),

@@ -442,6 +442,21 @@ __global__ void __launch_bounds__(kGrowBlock) grow_write_kernel(
     nodes[node] = nd;
 }
 
+// per-slot routing plan of a scored level: how many routing chunks each parent needs (0 when it is a leaf or both children
+// are leaves) and, on the side, the node's gain for featureImportances — one launch instead of a dozen elementwise ones
+__global__ void __launch_bounds__(256) plan_route_kernel(int n_slots, const b200flow_split* __restrict__ split,
+                                                         const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end,
+                                                         int chunk_rows, const int32_t* __restrict__ slot_node, double* node_gain,
+                                                         int32_t* n_chunks) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int flags = split[s].flags;
+    const bool routed = !(flags & 1) && (flags & 6) != 6;
+    const int64_t len = seg_end[s] - seg_begin[s];
+    n_chunks[s] = routed ? (int32_t)((len + chunk_rows - 1) / chunk_rows) : 0;
+    if (node_gain) node_gain[slot_node[s]] = split[s].gain;
+}
+
 // ------------------------------------------------------------------ row routing
 constexpr int kPartPerThread = 8;      // chunk_rows <= 256 * 8
 
@@ -845,6 +860,14 @@ extern "C" int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, co
                                                                   right_counts, C, nodes, node_mask, pool_counts, node_tree, blk, counters,
                                                                   next_tree, next_nid, next_node, next_parent, child_slot);
     return check_launch("grow_level");
+}
+
+extern "C" int b200flow_plan_route(int32_t n_slots, const b200flow_split* split, const int64_t* seg_begin, const int64_t* seg_end,
+                                   int32_t chunk_rows, const int32_t* slot_node, double* node_gain, int32_t* n_chunks, void* stream) {
+    if (n_slots <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(split && seg_begin && seg_end && n_chunks && chunk_rows > 0 && (!node_gain || slot_node), "plan_route: bad arguments");
+    plan_route_kernel<<<(n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_slots, split, seg_begin, seg_end, chunk_rows, slot_node, node_gain, n_chunks);
+    return check_launch("plan_route");
 }
 
 extern "C" int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride, const void* ent, void* ent_out, int32_t n_slots,

@@ -164,6 +164,76 @@ __global__ void __launch_bounds__(1024) find_splits_kernel(double* sample, int64
     n_thr[f] = nt;
 }
 
+// Shared-memory version (n_pad <= kFindSplitsSmemMax): the column is sorted in shared memory, the run boundaries are
+// compacted in parallel, and the stride walk only visits the boundaries it takes: for the current target the predicate
+// "|prev - target| < |cur - target|" (prev/cur = cumulative counts before/after a run) is monotone along the boundary list
+// (2*target - prev - cur decreases), so the first boundary that satisfies it is found by bisection and then re-checked
+// backwards with the very same fp64 predicate — identical thresholds to the sequential walk, ~100x fewer dependent steps.
+constexpr int kFindSplitsSmemMax = 16384;
+
+__global__ void __launch_bounds__(1024) find_splits_smem_kernel(const double* __restrict__ sample, int64_t cap, int n_s, int n_pad,
+                                                                const int32_t* __restrict__ arity, int max_bins,
+                                                                double* thresholds, int32_t* n_thr) {
+    extern __shared__ __align__(8) uint8_t fs_raw[];
+    double* v = (double*)fs_raw;                           // [n_pad]
+    int* B = (int*)(v + n_pad);                            // [n_pad] start index of every run but the first
+    __shared__ int sh[33];
+    const int f = blockIdx.x, tid = threadIdx.x, nt_threads = blockDim.x;
+    if (arity[f] > 0 || n_s <= 0) { if (tid == 0) n_thr[f] = 0; return; }
+    const double* src = sample + (int64_t)f * cap;
+    for (int i = tid; i < n_pad; i += nt_threads) v[i] = i < n_s ? src[i] : INFINITY;
+    __syncthreads();
+    for (int k = 2; k <= n_pad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (n_pad >> 1); t += nt_threads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // the lower index of the t-th compare-exchange pair
+                const int p = i | j;
+                const double a = v[i], b = v[p];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { v[i] = b; v[p] = a; }
+            }
+            __syncthreads();
+        }
+    // run boundaries, compacted in index order: thread t owns the contiguous slice [t*per, (t+1)*per)
+    const int per = (n_s + nt_threads - 1) / nt_threads;
+    const int lo = max(1, tid * per), hi = min(n_s, (tid + 1) * per);
+    int local = 0;
+    for (int i = lo; i < hi; ++i) local += v[i] != v[i - 1] ? 1 : 0;
+    int possible;
+    int pos = block_exclusive_scan(local, sh, &possible);   // possible = #distinct - 1
+    for (int i = lo; i < hi; ++i) if (v[i] != v[i - 1]) B[pos++] = i;
+    __syncthreads();
+    if (tid != 0) return;
+    const int num_splits = max_bins - 1;
+    double* thr = thresholds + (int64_t)f * num_splits;
+    int nt = 0;
+    if (possible == 0) {
+    } else if (possible <= num_splits) {
+        for (int k = 0; k < possible; ++k) { const int i = B[k]; thr[nt++] = (v[i - 1] + v[i]) / 2.0; }
+    } else {
+        const double stride = (double)n_s / (double)(num_splits + 1);
+        double target = stride;
+        auto pred = [&](int k) {                            // run k+1 starts at B[k]: prev = B[k], cur = its end
+            const double prev = (double)B[k], cur = (double)(k + 1 < possible ? B[k + 1] : n_s);
+            return fabs(prev - target) < fabs(cur - target);
+        };
+        int k0 = 0;
+        while (k0 < possible && nt < num_splits) {
+            int a = k0, b = possible;                       // first k in [k0, possible) with pred(k), or possible
+            while (a < b) { const int mid = (a + b) >> 1; if (pred(mid)) b = mid; else a = mid + 1; }
+            int k = a;
+            while (k > k0 && pred(k - 1)) --k;              // fp64 re-check: never skip an earlier boundary the walk would take
+            while (k < possible && !pred(k)) ++k;
+            if (k >= possible) break;
+            const int i = B[k];
+            thr[nt++] = (v[i - 1] + v[i]) / 2.0;
+            target += stride;
+            k0 = k + 1;
+        }
+    }
+    n_thr[f] = nt;
+}
+
 // ------------------------------------------------------------------ R5 TreePoint binning
 // thread -> (row, feature) with a fixed feature per thread; bins staged in smem, written as 16-byte words.
 template <typename T>
@@ -417,7 +487,14 @@ extern "C" int b200flow_find_splits(double* sample, int64_t cap, int32_t n_s, in
     B2F_REQUIRE(n_s >= 0 && n_s <= cap, "find_splits: n_s exceeds cap");
     int n_pad = 1; while (n_pad < n_s) n_pad <<= 1;
     B2F_REQUIRE(n_pad <= cap, "find_splits: cap must be >= pow2ceil(n_s)");
-    find_splits_kernel<<<F, 1024, 0, (cudaStream_t)stream>>>(sample, cap, n_s, n_pad, arity, max_bins, thresholds, n_thr);
+    if (n_pad <= kFindSplitsSmemMax) {
+        const size_t smem = (size_t)n_pad * 12;
+        cudaError_t e = cudaFuncSetAttribute(find_splits_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("find_splits: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
+        find_splits_smem_kernel<<<F, 1024, smem, (cudaStream_t)stream>>>(sample, cap, n_s, n_pad, arity, max_bins, thresholds, n_thr);
+    } else {
+        find_splits_kernel<<<F, 1024, 0, (cudaStream_t)stream>>>(sample, cap, n_s, n_pad, arity, max_bins, thresholds, n_thr);
+    }
     return check_launch("find_splits");
 }
 

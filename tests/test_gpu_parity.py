@@ -132,6 +132,25 @@ def test_find_splits_and_binning_exact():
     assert np.array_equal(tp32.cpu().numpy()[:, :F + 1], tp_o32[:, :F + 1])
 
 
+@pytest.mark.parametrize("n,max_bins", [(300, 32), (9000, 70), (60000, 100), (120000, 150), (120000, 256)])
+def test_find_splits_small_and_large_samples(n, max_bins):
+    # <= 16384 sampled rows: shared-memory sort + bisection walk; more: the global-memory kernel.  Columns: all-distinct
+    # reals (every run has length 1), heavy ties, a constant, and few distinct values (fewer than maxBins).
+    g = torch.Generator(device="cpu").manual_seed(n + max_bins)
+    cols = [torch.randn(n, generator=g, dtype=torch.float64), torch.randint(0, 500, (n,), generator=g).to(torch.float64) ** 2,
+            torch.zeros(n, dtype=torch.float64), torch.randint(0, 20, (n,), generator=g).to(torch.float64) * 0.25,
+            torch.floor(torch.rand(n, generator=g, dtype=torch.float64) ** 6 * 1e6)]
+    x = torch.stack(cols, 1).contiguous()
+    y = (x[:, 0] > 0).to(torch.int32)
+    p = fr.ForestParams(num_trees=1, max_bins=max_bins, max_depth=0, seed=7, bootstrap=False)
+    m = fr.fit_forest(x.to(DEV), y.to(DEV), 2, [0] * 5, p)
+    mpb = min(max_bins, n)
+    keep = int(min(1.0, max(mpb * mpb, 10000) / n) * 4294967296.0)
+    thr, n_thr, ns = oracle.find_splits(x.numpy(), 7, keep, [0] * 5, mpb)
+    assert np.array_equal(m.n_thr.cpu().numpy(), n_thr)
+    assert np.array_equal(m.thresholds.cpu().numpy(), thr)
+
+
 def test_bagging_weights_and_entries_match_oracle():
     n, T, seed = 5000, 7, 1234
     cdf = fr.poisson_cdf_table(1.0)
