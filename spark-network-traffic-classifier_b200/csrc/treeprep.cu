@@ -362,8 +362,8 @@ __global__ void __launch_bounds__(256) group_fill_kernel(const int32_t* __restri
 // ------------------------------------------------------------------ R6 bagging
 constexpr int kBagBlockRows = 1024;
 
-// W[tree][uid[row]] += Poisson weight of (tree, row).  grid = (row blocks of 1024, tree quads); a thread owns 4 consecutive
-// rows; one Philox call per row yields the weights of the quad's 4 trees.  Lanes whose rows belong to the same duplicate
+// W[tree][uid[row]] += Poisson weight of (tree, row).  grid = row blocks of 1024; a thread owns 4 positions and loops over
+// the tree quads (one Philox call per row yields the weights of a quad's 4 trees; the duplicate-group search is per row, not per tree).  Lanes whose rows belong to the same duplicate
 // group are merged first (match.any on the unique id + three ballots for the weights 1..3), so a hot group — the smurf
 // flood is a third of KDD99 — costs one global RED per warp and tree instead of one per row.
 struct CdfHead { uint32_t c[6]; };       // first thresholds of the inverse CDF, passed by value (uniform registers)
@@ -379,41 +379,46 @@ __global__ void __launch_bounds__(256) bag_weights_kernel(uint64_t seed, int T, 
                                                           const int32_t* __restrict__ uid, const int32_t* __restrict__ perm,
                                                           int64_t U, uint32_t* W) {
     __shared__ uint32_t cdf_sh[32];
-    const int tq = blockIdx.y, lane = lane_id();
+    const int lane = lane_id();
     if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
     __syncthreads();
+    const int n_quads = (T + 3) >> 2;
     // position p of the (optionally grouped) order: lane-consecutive positions so that a duplicate group is a run of lanes
     const int64_t pb = (int64_t)blockIdx.x * kBagBlockRows + (threadIdx.x >> 5) * 128 + lane;
-#pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int64_t p = pb + k * 32;
         const bool live = p < n;
         const int64_t i = live ? (perm ? (int64_t)perm[p] : p) : 0;          // the row behind position p
         const int64_t u = live ? (uid ? (int64_t)uid[p] : i) : 0;            // uid is given in POSITION order when perm is
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (live) {
-            if (cdf) {
-                const uint4 r = bag_draw4(seed, tq, (uint64_t)(row_offset + i));
-                w[0] = poisson_weight_fast(r.x, head, cdf_sh); w[1] = poisson_weight_fast(r.y, head, cdf_sh);
-                w[2] = poisson_weight_fast(r.z, head, cdf_sh); w[3] = poisson_weight_fast(r.w, head, cdf_sh);
-            } else { w[0] = w[1] = w[2] = w[3] = 1u; }
-        }
-        if (uid) {
-            const uint32_t g = __match_any_sync(0xffffffffu, live ? (int)u : -1 - lane);     // dead lanes form singleton groups
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t b1 = __ballot_sync(0xffffffffu, w[q] == 1), b2 = __ballot_sync(0xffffffffu, w[q] == 2),
-                               b3 = __ballot_sync(0xffffffffu, w[q] == 3);
-                if (tq * 4 + q >= T || !w[q]) continue;
-                uint32_t* addr = &W[(int64_t)(tq * 4 + q) * U + u];
-                const uint32_t gg = g & (b1 | b2 | b3);
-                if (w[q] > 3) atomicAdd(addr, w[q]);
-                else if ((int)(__ffs(gg) - 1) == lane) atomicAdd(addr, (uint32_t)(__popc(gg & b1) + 2 * __popc(gg & b2) + 3 * __popc(gg & b3)));
+        // the row's duplicate group inside this warp step, found ONCE for all trees (dead lanes form singleton groups)
+        const uint32_t g = uid ? __match_any_sync(0xffffffffu, live ? (int)u : -1 - lane) : (1u << lane);
+        const bool merged = uid && !__all_sync(0xffffffffu, g == (1u << lane));
+        const uint64_t grow = (uint64_t)(row_offset + i);
+        for (int tq = 0; tq < n_quads; ++tq) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (live) {
+                if (cdf) {
+                    const uint4 r = bag_draw4(seed, tq, grow);
+                    w[0] = poisson_weight_fast(r.x, head, cdf_sh); w[1] = poisson_weight_fast(r.y, head, cdf_sh);
+                    w[2] = poisson_weight_fast(r.z, head, cdf_sh); w[3] = poisson_weight_fast(r.w, head, cdf_sh);
+                } else { w[0] = w[1] = w[2] = w[3] = 1u; }
             }
-        } else {
+            if (merged) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (tq * 4 + q < T && w[q]) atomicAdd(&W[(int64_t)(tq * 4 + q) * U + u], w[q]);
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t b1 = __ballot_sync(0xffffffffu, w[q] == 1), b2 = __ballot_sync(0xffffffffu, w[q] == 2),
+                                   b3 = __ballot_sync(0xffffffffu, w[q] == 3);
+                    if (tq * 4 + q >= T || !w[q]) continue;
+                    uint32_t* addr = &W[(int64_t)(tq * 4 + q) * U + u];
+                    const uint32_t gg = g & (b1 | b2 | b3);
+                    if (w[q] > 3) atomicAdd(addr, w[q]);
+                    else if ((int)(__ffs(gg) - 1) == lane) atomicAdd(addr, (uint32_t)(__popc(gg & b1) + 2 * __popc(gg & b2) + 3 * __popc(gg & b3)));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (tq * 4 + q < T && w[q]) atomicAdd(&W[(int64_t)(tq * 4 + q) * U + u], w[q]);
+            }
         }
     }
 }
@@ -572,8 +577,7 @@ extern "C" int b200flow_bag_weights(uint64_t seed, int32_t T, int64_t row_offset
     CdfHead head;
     for (int k = 0; k < 6; ++k) head.c[k] = poisson_cdf_host ? poisson_cdf_host[k] : 0xFFFFFFFFu;
     const int64_t nb = (n_rows + kBagBlockRows - 1) / kBagBlockRows;
-    bag_weights_kernel<<<dim3((unsigned)nb, (unsigned)((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, head,
-                                                                                                   uid, perm, n_unique, W);
+    bag_weights_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(seed, T, row_offset, n_rows, poisson_cdf, head, uid, perm, n_unique, W);
     return check_launch("bag_weights");
 }
 
