@@ -720,10 +720,9 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                             const uint32_t key = bin | tag;
                             uint32_t* addr = &hist[j * nbC + bin * a.C + lab];
                             const int l0 = __ffs(active) - 1;
-                            const uint32_t m0 = __ballot_sync(active, key == __shfl_sync(active, key, l0));
-                            bool done = (m0 >> lane) & 1u;
-                            if (done) { const uint32_t sum = __reduce_add_sync(m0, w); if (lane == l0) atomicAdd(addr, sum); }
-                            if (!done) atomicAdd(addr, w);
+                            const bool top = key == __shfl_sync(active, key, l0);          // same counter as the first active lane
+                            const uint32_t sum = __reduce_add_sync(active, top ? w : 0u);  // no divergence: the others contribute 0
+                            if (!top || lane == l0) atomicAdd(addr, top ? sum : w);
                         }
                     } else {
                         for (int j = 0; j < m; ++j) {
