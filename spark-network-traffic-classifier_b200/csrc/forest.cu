@@ -550,7 +550,7 @@ struct RouteArgs {
 constexpr int kRouteWarps = kRouteThreads / 32;
 constexpr int kSub = 64;                                    // entries per warp step (2 per lane)
 
-template <int M, int NBUF, int MERGE>   // MERGE: 0 plain shared atomics, 1 whole-key merge, 2 per-feature merge, 3 top-group merge
+template <int M, int NBUF, int MERGE>   // MERGE: 0 plain shared atomics, 1 top-group merge
 __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_level_kernel(const RouteArgs a) {
     extern __shared__ __align__(16) uint32_t sm_u32[];
     const int m = M > 0 ? M : a.m;
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     const int tile_words = nq * kSub * 4;
     uint32_t* tiles = sm_u32 + (size_t)wid * NBUF * tile_words; // this warp's NBUF [nq][64] quad tiles
     uint32_t* sh_hist = sm_u32 + (size_t)kRouteWarps * NBUF * tile_words;   // [2][hsz]
-    int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: (word offset of the feature's byte in a tile << 5) | shift
+    int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: byte offset of the feature inside a tile (entry 0)
     __shared__ b200flow_split sh_split;
     __shared__ int sh_child[2];
 
@@ -621,10 +621,10 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     entries_of(d1, &f0, &f1);
     if (NBUF == 2) issue_gather(d0, e0, e1, tiles);
     int cur_slot = -1;
-    const int lab_pos = (F >> 4) * kSub * 4 + ((F >> 2) & 3), lab_sh = (F & 3) * 8;
+    const int lab_pos = (F >> 4) * kSub * 16 + (F & 15);         // byte of the label inside a tile (entry 0; + 16 per entry)
     for (int64_t c = c0; c < c1; ++c) {
         const int par = NBUF == 2 ? (int)((c - c0) & 1) : 0;
-        const uint32_t* tile = tiles + par * tile_words;
+        const uint8_t* tile8 = (const uint8_t*)(tiles + par * tile_words);   // [nq][64 entries][16 bytes]
         entries_of(d2, &g0, &g1);                              // prefetch, consumed two steps later
         const int4 d3 = desc_at(c + 3);
         if (NBUF == 2) issue_gather(d1, f0, f1, tiles + (par ^ 1) * tile_words);   // in flight during this step's compute
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
             for (int j = tid; j < 2 * m; j += kRouteThreads) {
                 const int cs = a.child_slot[2 * s + (j >= m)];
                 const int f = cs >= 0 ? a.subset_next[(int64_t)cs * m + (j < m ? j : j - m)] : 0;
-                sh_fpos[j] = (((f >> 4) * kSub * 4 + ((f >> 2) & 3)) << 5) | ((f & 3) * 8);
+                sh_fpos[j] = (f >> 4) * kSub * 16 + (f & 15);
             }
             cur_slot = s;
             __syncthreads();
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
         if (cnt > 0) {
             const int cl = sh_child[0], cr = sh_child[1];
             const int fs = sh_split.feat, kind = sh_split.kind, thr = sh_split.bin_thr;
-            const int fs_pos = (fs >> 4) * kSub * 4 + ((fs >> 2) & 3), fs_sh = (fs & 3) * 8;
+            const int fs_pos = (fs >> 4) * kSub * 16 + (fs & 15);
             int nL = 0, nR = 0;
             uint32_t dec = 0;
 #pragma unroll
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                 const int i = k * 32 + lane;
                 int d = 0;
                 if (i < cnt) {
-                    const int bin = (tile[fs_pos + i * 4] >> fs_sh) & 0xff;
+                    const int bin = tile8[fs_pos + i * 16];
                     const bool left = kind == 0 ? (bin <= thr) : ((sh_split.mask[bin >> 6] >> (bin & 63)) & 1ull);
                     d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
                 }
@@ -673,50 +673,19 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                     const int side = d - 1;
                     const int* fpos = sh_fpos + side * m;
                     uint32_t* hist = sh_hist + side * hsz;
-                    const uint32_t lab = (tile[lab_pos + i * 4] >> lab_sh) & 0xffu;
+                    const uint32_t lab = tile8[lab_pos + i * 16];
                     const uint32_t w = k ? e1.y : e0.y;
-                    if (M > 0 && MERGE == 1) {
-                        // whole-key merge: lanes with identical (child, all M bins, label) are combined
-                        constexpr int NW = (M + 1 + 3) / 4;
-                        uint32_t keys[NW];
-#pragma unroll
-                        for (int q = 0; q < NW; ++q) keys[q] = 0;
-#pragma unroll
-                        for (int j = 0; j < M; ++j) {
-                            const int fp = fpos[j];
-                            keys[j >> 2] |= ((tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu) << (8 * (j & 3));
-                        }
-                        keys[M >> 2] |= (lab | ((uint32_t)side << 7)) << (8 * (M & 3));
-                        uint32_t g = active;
-#pragma unroll
-                        for (int q = 0; q < NW; ++q) g &= __match_any_sync(active, keys[q]);
-                        const uint32_t sum = __reduce_add_sync(g, w);        // weights are sums over duplicate rows: any size
-                        if ((int)(__ffs(g) - 1) == lane) {
-#pragma unroll
-                            for (int j = 0; j < M; ++j)
-                                atomicAdd(&hist[j * nbC + ((keys[j >> 2] >> (8 * (j & 3))) & 0xff) * a.C + lab], sum);
-                        }
-                    } else if (M > 0 && MERGE == 2) {
-                        // per-feature merge: lanes that hit the same (child, feature, bin, label) counter are combined with
-                        // match.any; the group's bag-weight sum comes from three ballots shared by all features
-                        const uint32_t tag = (lab << 8) | ((uint32_t)side << 16);
-#pragma unroll
-                        for (int j = 0; j < M; ++j) {
-                            const int fp = fpos[j];
-                            const uint32_t bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu;
-                            const uint32_t gg = __match_any_sync(active, bin | tag);
-                            const uint32_t sum = __reduce_add_sync(gg, w);
-                            if ((int)(__ffs(gg) - 1) == lane) atomicAdd(&hist[j * nbC + bin * a.C + lab], sum);
-                        }
-                    } else if (M > 0 && MERGE == 3) {
+                    if (M > 0 && MERGE) {
                         // top-group merge: per feature, the lanes that share the first active lane's (bin, label, child) counter are
-                        // summed with ONE redux (every participant passes the same mask, so it is a single REDUX) and issue one
-                        // shared atomic; the other lanes add alone.  Further rounds were measured slower (27 / 36 ms vs 20.6 ms).
+                        // summed with ONE redux over the whole active mask (the others contribute 0: no divergence) and issue one
+                        // shared atomic; the other lanes add alone.  Measured and dropped: whole-key match.any merge (46 ms per fit
+                        // vs 20.6), per-feature match.any merge (80 ms: a redux per distinct mask serialises), further top-group
+                        // rounds (27 / 36 ms).
                         const uint32_t tag = (lab << 8) | ((uint32_t)side << 16);
 #pragma unroll
                         for (int j = 0; j < M; ++j) {
                             const int fp = fpos[j];
-                            const uint32_t bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu;
+                            const uint32_t bin = tile8[fp + i * 16];
                             const uint32_t key = bin | tag;
                             uint32_t* addr = &hist[j * nbC + bin * a.C + lab];
                             const int l0 = __ffs(active) - 1;
@@ -727,7 +696,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                     } else {
                         for (int j = 0; j < m; ++j) {
                             const int fp = fpos[j];
-                            const uint32_t bin = (tile[(fp >> 5) + i * 4] >> (fp & 31)) & 0xffu;
+                            const uint32_t bin = tile8[fp + i * 16];
                             atomicAdd(&hist[j * nbC + bin * a.C + lab], w);
                         }
                     }
@@ -749,13 +718,10 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     flush();
 }
 
-static int route_variant() {                                // tuning knob (tile buffers per warp, merge strategy)
+static int route_variant() {                                // tuning knob: bit0 = 2 tiles per warp, bit1 = plain atomics (no merge)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? atoi(e) : 6; }
-    return v;        // bit0: 2 tiles per warp; bits 1-3: merge of equal lanes before the shared atomics (0 whole-key, 1 per-feature,
-                     // 2 none, 3 top-group).  Default 6 = one tile, top-group merge.  Measured per KDD-full fit after row
-                     // de-duplication: top-group 20.6 ms, none 26 ms, whole-key 46 ms, per-feature 80 ms (a redux per distinct
-                     // mask serialises; one shared mask does not)
+    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? atoi(e) & 3 : 0; }
+    return v;        // default 0 = one tile per warp + top-group merge (per KDD-full fit: 19.0 ms; plain atomics 26 ms)
 }
 
 static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
@@ -934,13 +900,10 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     }
 #define B2F_ROUTE_CASE(MM)                                                                                                     \
     case MM:                                                                                                                   \
-        switch (route_variant() & 15) {                                                                                        \
+        switch (route_variant()) {                                                                                             \
             case 0: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 1>)) break;                                               \
             case 1: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 1>)) break;                                               \
-            case 2: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 2>)) break;                                               \
-            case 3: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 2>)) break;                                               \
-            case 4: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 0>)) break;                                               \
-            case 6: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 3>)) break;                                               \
+            case 2: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 0>)) break;                                               \
             default: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 0>)) break;                                              \
         }                                                                                                                      \
         break;
