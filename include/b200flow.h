@@ -286,7 +286,14 @@ int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_rows,
                      const b200flow_node* nodes, const uint64_t* node_mask,
                      const double* leaf_prob, const uint32_t* pool_counts,
                      int32_t T, int32_t C, int32_t dt_mode,
+                     const void* top_nodes /* NULL or the table of b200flow_build_top_nodes */, int32_t top_levels,
                      double* raw, double* prob, double* pred, void* stream);
+
+/* shared-memory table for predict: top[tree][nid] (16-byte b200flow_node, [T][2^top_levels], entry 0 unused) = the tree's
+ * node with MLlib node id nid < 2^top_levels.  Built once per model; the walk of the first top_levels levels then reads
+ * shared memory instead of issuing one L1 request per lane and level. */
+int b200flow_build_top_nodes(const b200flow_node* nodes, const int32_t* node_tree, int64_t n_nodes, int32_t T,
+                             int32_t top_levels, void* top, void* stream);
 
 /* out[i] = src[idx[i]] for rows of row_bytes (multiple of 4): spreads the predictions computed once per UNIQUE test record
  * (b200flow_dedup_rows) back to the rows. */

@@ -53,7 +53,8 @@ _SIGNATURES = {
     "b200flow_plan_route": [_I32, _P, _P, _P, _I32, _P, _P, _P, _P],
     "b200flow_next_segments": [_I32, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200flow_finalize_forest": [_I64, _P, _I32, _P, _P],
-    "b200flow_predict": [_P, _I32, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
+    "b200flow_predict": [_P, _I32, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P],
+    "b200flow_build_top_nodes": [_P, _P, _I64, _I32, _I32, _P, _P],
     "b200flow_gather_rows": [_P, _I32, _P, _I64, _P, _P],
     "b200flow_confusion": [_P, _P, _I64, _I32, _P, _P],
     "b200flow_random_split": [_U64, _I64, _I64, _P, _I32, _P, _P],

@@ -22,6 +22,7 @@ CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_l
 import os as _os
 ROUTE_CHUNK_ROWS = int(_os.environ.get("B200FLOW_ROUTE_CHUNK", "512"))   # entries per CTA in the fused route_hist_level kernel
 FUSED = True                       # use route_hist_level (partition + next-level histogram in one pass) when it fits
+TOP_LEVELS = int(_os.environ.get("B200FLOW_TOP_LEVELS", "8"))   # tree levels the predict kernel walks in shared memory (0 = none)
 DEDUP = True                       # run the level loop on unique binned records (flow records repeat massively)
 _PIN = True                        # read the per-level counts into pinned host memory
 PROFILE = None                     # set to a dict to collect per-kernel CUDA-event timings (bench.py)
@@ -167,14 +168,25 @@ class ForestModel:
              ptr(self._arity_dev), self.max_bins, ptr(labels), ptr(tp), stride, ptr(bad))
         return tp, bad
 
+    def _top_table(self):
+        """the first TOP_LEVELS levels of every tree, heap-indexed by node id, for the predict kernel's shared-memory stage
+        (built once per model)."""
+        if TOP_LEVELS <= 0:
+            return None, 0
+        if getattr(self, "_top", None) is None:
+            self._top = torch.zeros((self.T << TOP_LEVELS, 4), dtype=torch.int32, device=self.nodes.device)
+            call("b200flow_build_top_nodes", ptr(self.nodes), ptr(self.node_tree), self.n_nodes, self.T, TOP_LEVELS, ptr(self._top))
+        return self._top, TOP_LEVELS
+
     def predict_binned(self, tp, want_raw=True, want_prob=True):
         n = tp.shape[0]
         dev = tp.device
         raw = torch.empty((n, self.C), dtype=torch.float64, device=dev) if want_raw else None
         prob = torch.empty((n, self.C), dtype=torch.float64, device=dev) if want_prob else None
         pred = torch.empty(n, dtype=torch.float64, device=dev)
+        top, K = self._top_table()
         _timed("predict", "b200flow_predict", ptr(tp), tp.shape[1], n, ptr(self.nodes), ptr(self.node_mask), ptr(self.leaf_prob),
-             ptr(self.pool_counts), self.T, self.C, 1 if self.dt_mode else 0, ptr(raw), ptr(prob), ptr(pred))
+             ptr(self.pool_counts), self.T, self.C, 1 if self.dt_mode else 0, ptr(top), K, ptr(raw), ptr(prob), ptr(pred))
         return raw, prob, pred
 
     def predict(self, x, want_raw=True, want_prob=True):

@@ -12,19 +12,41 @@ namespace b200flow {
 // loads (L1/L2 hits: the pool of a 100-tree depth-16 forest is a few MB), so two independent chains per thread double the
 // memory-level parallelism.  A row's bins live in transposed smem (word k of thread t at [k*blockDim + t], conflict-free);
 // votes accumulate in fp64, in tree order, in smem ([class*blockDim + t]).
+//
+// What bounds the walk is the L1: below the first few levels every lane of a warp is at a different node, so each level costs
+// 32 separate sector requests per warp and row (ncu: issue 36 %, LSU 29 %, long-scoreboard stalls — the t-stage serialises
+// them).  The top `top_levels` levels of the CURRENT tree (2^K - 1 nodes, heap-indexed by MLlib's node id) are therefore
+// staged in shared memory, double-buffered with cp.async one tree ahead: a scattered LDS.128 costs a handful of bank
+// wavefronts instead of 32 tag lookups, and only the levels below K go to the L1/L2.
 constexpr int kPredRows = 2;
+
+// top[tree][nid] = the tree's node with MLlib id nid, for nid < 2^K (entry 0 unused)
+__global__ void __launch_bounds__(256) build_top_kernel(const int4* __restrict__ nodes, const int32_t* __restrict__ node_tree,
+                                                        int64_t n_nodes, int K, int4* top) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const int4 nd = nodes[i];
+    if ((uint32_t)nd.w < (1u << K)) top[((int64_t)node_tree[i] << K) + nd.w] = nd;
+}
 
 __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict__ tp, int stride, int64_t n,
                                                       const b200flow_node* __restrict__ nodes,
                                                       const unsigned long long* __restrict__ node_mask,
                                                       const double* __restrict__ leaf_prob,
                                                       const uint32_t* __restrict__ pool_counts, int T, int C, int dt_mode,
+                                                      const int4* __restrict__ top, int K,
                                                       double* raw, double* prob, double* pred) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int bd = blockDim.x, tid = threadIdx.x;
     const int words = stride / 4;
     uint32_t* binw = (uint32_t*)sm;                                           // [kPredRows][words][bd]
     double* votes = (double*)(sm + (size_t)kPredRows * words * bd * 4);       // [kPredRows][C][bd]
+    const int topn = top ? (1 << K) : 0;
+    int4* topbuf = (int4*)(votes + (size_t)kPredRows * C * bd);               // [2][topn] when the top table is given
+    auto stage_top = [&](int t, int buf) {                                    // asynchronous copy of tree t's table
+        if (t < T) for (int i = tid; i < topn; i += bd) cp_async16(topbuf + (size_t)buf * topn + i, top + ((int64_t)t << K) + i);
+        cp_async_commit();
+    };
     for (int64_t base = (int64_t)blockIdx.x * bd * kPredRows; base < n; base += (int64_t)gridDim.x * bd * kPredRows) {
         int64_t row[kPredRows]; bool live[kPredRows];
 #pragma unroll
@@ -43,10 +65,17 @@ __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict_
         }
         const uint32_t* bw0 = binw + tid;                                   // this thread's column of the transposed bins
         const int4* nodes4 = (const int4*)nodes;                            // {feat, kind<<16|bin, left, nid}
+        if (top) stage_top(0, 0);
         for (int t = 0; t < T; ++t) {
-            int idx[kPredRows]; int4 nd[kPredRows];
+            const int4* tb = topbuf + (size_t)(t & 1) * topn;
+            if (top) {
+                cp_async_wait_all();
+                __syncthreads();                                            // table of tree t landed; everybody left tree t-1
+                stage_top(t + 1, (t + 1) & 1);
+            }
+            int idx[kPredRows]; uint32_t nid[kPredRows]; int4 nd[kPredRows];
 #pragma unroll
-            for (int r = 0; r < kPredRows; ++r) { idx[r] = t; nd[r] = __ldg(nodes4 + t); if (!live[r]) nd[r].x = -1; }
+            for (int r = 0; r < kPredRows; ++r) { idx[r] = t; nid[r] = 1u; nd[r] = top ? tb[1] : __ldg(nodes4 + t); if (!live[r]) nd[r].x = -1; }
             while (true) {
                 bool any = false;
 #pragma unroll
@@ -57,13 +86,14 @@ __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict_
                         const int right = nd[r].y < 65536 ? (bin > nd[r].y)
                                                           : !((node_mask[(int64_t)idx[r] * 4 + (bin >> 6)] >> (bin & 63)) & 1ull);
                         idx[r] = nd[r].z + right;
+                        nid[r] = 2u * nid[r] + (uint32_t)right;
                         any = true;
                     }
                 }
                 if (!any) break;
 #pragma unroll
                 for (int r = 0; r < kPredRows; ++r)
-                    if (nd[r].x >= 0) nd[r] = __ldg(nodes4 + idx[r]);
+                    if (nd[r].x >= 0) nd[r] = nid[r] < (uint32_t)topn ? tb[nid[r]] : __ldg(nodes4 + idx[r]);
             }
 #pragma unroll
             for (int r = 0; r < kPredRows; ++r) {
@@ -86,6 +116,7 @@ __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict_
             }
             pred[row[r]] = (double)arg;
         }
+        if (top) { cp_async_wait_all(); __syncthreads(); }                  // the look-ahead copy of the last tree is a no-op commit
     }
 }
 
@@ -176,23 +207,33 @@ __global__ void __launch_bounds__(256) compact_scatter_kernel(const uint8_t* __r
 
 using namespace b200flow;
 
+extern "C" int b200flow_build_top_nodes(const b200flow_node* nodes, const int32_t* node_tree, int64_t n_nodes, int32_t T,
+                                        int32_t top_levels, void* top, void* stream) {
+    B2F_REQUIRE(nodes && node_tree && top && T > 0 && top_levels >= 1 && top_levels <= 10 && ((uintptr_t)top & 15) == 0, "build_top_nodes: bad arguments");
+    if (n_nodes <= 0) return B200FLOW_OK;
+    build_top_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const int4*)nodes, node_tree, n_nodes, top_levels, (int4*)top);
+    return check_launch("build_top_nodes");
+}
+
 extern "C" int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_rows, const b200flow_node* nodes,
                                 const uint64_t* node_mask, const double* leaf_prob, const uint32_t* pool_counts, int32_t T,
-                                int32_t C, int32_t dt_mode, double* raw, double* prob, double* pred, void* stream) {
+                                int32_t C, int32_t dt_mode, const void* top_nodes, int32_t top_levels,
+                                double* raw, double* prob, double* pred, void* stream) {
     if (n_rows <= 0) return B200FLOW_OK;            // empty batch: nothing to do (pointers may be NULL)
     B2F_REQUIRE(tp && nodes && pred && T > 0 && C > 0 && (tp_stride & 15) == 0, "predict: bad arguments");
     B2F_REQUIRE(dt_mode ? pool_counts != nullptr : leaf_prob != nullptr, "predict: missing leaf payload");
     B2F_REQUIRE(((uintptr_t)tp & 15) == 0, "predict: tp must be 16-byte aligned");
+    B2F_REQUIRE(!top_nodes || (top_levels >= 1 && top_levels <= 10 && ((uintptr_t)top_nodes & 15) == 0), "predict: bad top table");
     int bd = 128;
     size_t per_thread = ((size_t)tp_stride + (size_t)C * 8) * kPredRows;
     while (bd > 32 && per_thread * bd > 96 * 1024) bd >>= 1;
-    size_t smem = per_thread * bd;
+    size_t smem = per_thread * bd + (top_nodes ? (size_t)2 * 16 * ((size_t)1 << top_levels) : 0);
     B2F_REQUIRE(smem <= 200 * 1024, "predict: too many classes/features for shared memory");
     cudaError_t e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("predict: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
     int grid = grid_for(n_rows, bd * kPredRows, kNumSMs * 16);
     predict_kernel<<<grid, bd, smem, (cudaStream_t)stream>>>(tp, tp_stride, n_rows, nodes, (const unsigned long long*)node_mask, leaf_prob,
-                                                             pool_counts, T, C, dt_mode, raw, prob, pred);
+                                                             pool_counts, T, C, dt_mode, (const int4*)top_nodes, top_levels, raw, prob, pred);
     return check_launch("predict");
 }
 
