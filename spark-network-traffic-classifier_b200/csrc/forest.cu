@@ -134,7 +134,7 @@ __device__ __forceinline__ double split_gain(const uint32_t* L, const uint32_t* 
     return gain;
 }
 
-constexpr int kScoreThreads = 256;
+constexpr int kScoreThreads = 128;
 
 // One CTA per slot.  The slot's histogram block is staged ONCE (all loads in flight together), then
 //   B. per feature of the node's subset (a warp each): class-wise prefix sums over its bins in shared memory, split into
