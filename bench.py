@@ -157,9 +157,11 @@ def step_resident(rec, dicts, a, grp):
     n = rec.shape[0]
     luts, ordered = {}, {}
     cols = synth.KDD_CATEGORICAL + ["label"]                                        # R1 StringIndexer.fit (4 columns, one sync)
-    counts = [bdist.all_reduce_sum_(enc.category_counts(rec, schema, c, len(dicts[c])), grp) for c in cols]
+    counts = [bdist.all_reduce_sum_(t, grp) for t in enc.category_counts_multi(rec, schema, cols, [len(dicts[c]) for c in cols])]
+    host_counts = torch.cat(counts).cpu().numpy()                                   # one D2H for the four columns
+    o = 0
     for c, cnt in zip(cols, counts):
-        ordered[c], luts[c] = enc.string_index_order(cnt.cpu().numpy(), dicts[c])
+        ordered[c], luts[c] = enc.string_index_order(host_counts[o:o + cnt.numel()], dicts[c]); o += cnt.numel()
     plan = enc.EncodePlan(schema)
     for c in synth.KDD_COLUMNS:
         if c not in synth.KDD_CATEGORICAL and c != "label":

@@ -69,6 +69,12 @@ int  b200flow_version(void);
 int b200flow_category_counts(const void* records, int64_t n_rows, int32_t row_bytes,
                              int32_t src_off, int32_t K, int64_t* counts, void* stream);
 
+/* the same for up to 8 code fields in ONE pass over the records (a Pipeline of StringIndexers, kdd99.py:34-37): counts is the
+ * concatenation [K_0 | K_1 | ...] (int64, zero-initialised by the caller); src_offs / Ks are HOST arrays of n_cols entries;
+ * sum(K) <= 8192. */
+int b200flow_category_counts_multi(const void* records, int64_t n_rows, int32_t row_bytes, int32_t n_cols,
+                                   const int32_t* src_offs_host, const int32_t* Ks_host, int64_t* counts, void* stream);
+
 /* R2+R3+R3b+R3c  StringIndexerModel.transform + OneHotEncoder + StandardScaler +
  * VectorAssembler.transform fused (kdd99.py:37,46; cicids17.py:42,46): raw AoS
  * records -> dense row-major [n_rows, n_out] matrix (out_dtype F32/F64), computed

@@ -32,6 +32,7 @@ _P, _I32, _I64, _U64, _F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_d
 # name -> argtypes, exactly the prototypes of include/b200flow.h
 _SIGNATURES = {
     "b200flow_category_counts": [_P, _I64, _I32, _I32, _I32, _P, _P],
+    "b200flow_category_counts_multi": [_P, _I64, _I32, _I32, _P, _P, _P, _P],
     "b200flow_encode": [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P],
     "b200flow_column_moments": [_P, _I32, _I64, _I32, _I64, _P, _P, _P, _P],
     "b200flow_sample_rows": [_P, _I32, _I64, _I32, _I64, _U64, _U64, _I64, _P, _I64, _P, _P],

@@ -43,6 +43,23 @@ def category_counts(records, schema, field, K):
     return counts
 
 
+def category_counts_multi(records, schema, fields, Ks):
+    """StringIndexer.fit counting for several code fields in one pass over the records -> list of int64[K] device tensors
+    (views of one concatenated buffer: read them all with a single .cpu() on `result[0]._base_all`)."""
+    Ks = [max(int(k), 1) for k in Ks]
+    if len(fields) > 8 or sum(Ks) > 8192:
+        return [category_counts(records, schema, f, k) for f, k in zip(fields, Ks)]
+    allc = torch.zeros(sum(Ks), dtype=torch.int64, device=records.device)
+    offs = np.asarray([schema.offsets[f] for f in fields], np.int32)
+    ks = np.asarray(Ks, np.int32)
+    call("b200flow_category_counts_multi", ptr(records), records.shape[0], schema.row_bytes, len(fields), offs.ctypes.data, ks.ctypes.data,
+         ptr(allc))
+    out, o = [], 0
+    for k in Ks:
+        out.append(allc[o:o + k]); o += k
+    return out
+
+
 def string_index_order(counts, labels):
     """StringIndexer.fit, ordering half (A.7): frequencyDesc, ties alphabetical; never-seen codes get rank -1.
     counts: sequence of ints (host); returns (ordered labels, int32 lut code->rank)."""

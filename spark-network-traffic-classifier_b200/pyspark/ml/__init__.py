@@ -33,9 +33,8 @@ class Pipeline(Estimator):
                 raise TypeError("Cannot recognize a pipeline stage of type %s." % type(s))
         last_est = max([i for i, s in enumerate(stages) if isinstance(s, Estimator)], default=-1)
         from .feature import StringIndexer, _prefetch_category_counts
-        for s in stages:                                   # enqueue every StringIndexer's count kernel before the first host read
-            if isinstance(s, StringIndexer) and hasattr(dataset, "_cat_counts"):
-                _prefetch_category_counts(dataset, s.getOrDefault("inputCol"))
+        if hasattr(dataset, "_cat_counts"):                # ONE count pass for every StringIndexer stage, before the first host read
+            _prefetch_category_counts(dataset, [s.getOrDefault("inputCol") for s in stages if isinstance(s, StringIndexer)])
         fitted, cur = [], dataset
         for i, s in enumerate(stages):
             if isinstance(s, Estimator):

@@ -48,22 +48,26 @@ def _materialize(df, name):
 def _prefetch_category_counts(df, col):
     """enqueue the count kernel of a raw code field without waiting for it (Pipeline.fit does this for every
     StringIndexer stage up front, so the four fits of kdd99.py:34-37 cost one host sync instead of four)."""
-    if df._rec is None or col not in df._cols or col in df._cat_counts:
-        return
-    c = df._cols[col]
-    if c.kind == "field" and df._schema.type_of[col] == "code":
-        cnt = enc.category_counts(df._rec, df._schema, col, max(len(df._dicts[col]), 1))
-        df._cat_counts[col] = bdist.all_reduce_sum_(cnt)               # ranks share the dictionaries
+    cols = [col] if isinstance(col, str) else list(col)
+    cols = [c for c in dict.fromkeys(cols) if df._rec is not None and c in df._cols and c not in df._cat_counts and
+            df._cols[c].kind == "field" and df._schema.type_of[c] == "code"]
+    for i in range(0, len(cols), 8):                                   # raw code fields: one pass per 8 columns
+        part = cols[i:i + 8]
+        for c, cnt in zip(part, enc.category_counts_multi(df._rec, df._schema, part, [len(df._dicts[c]) for c in part])):
+            df._cat_counts[c] = bdist.all_reduce_sum_(cnt)             # ranks share the dictionaries
 
 
 def _category_counts(df, col):
     """global category counts of a raw code field as a host array (cached per record buffer)."""
     _prefetch_category_counts(df, col)
-    cnt = df._cat_counts[col]
-    if torch.is_tensor(cnt):
-        cnt = cnt.cpu().numpy()[:len(df._dicts[col])]
-        df._cat_counts[col] = cnt
-    return cnt
+    if torch.is_tensor(df._cat_counts[col]):                              # fetch every pending column in ONE device->host copy
+        pend = [k for k, v in df._cat_counts.items() if torch.is_tensor(v)]
+        host = torch.cat([df._cat_counts[k].reshape(-1) for k in pend]).cpu().numpy()
+        o = 0
+        for k in pend:
+            nk = df._cat_counts[k].numel()
+            df._cat_counts[k] = host[o:o + nk][:len(df._dicts[k])]; o += nk
+    return df._cat_counts[col]
 
 
 # ----------------------------------------------------------------------------------- StringIndexer

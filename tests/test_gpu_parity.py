@@ -56,6 +56,17 @@ def test_encode_full_onehot_scaled_matches_oracle(n):
     assert (err <= 1e-6 * np.abs(want) + 1e-30).all()                                  # 1e-6 relative (north_star)
 
 
+def test_category_counts_multi_equals_single_columns():
+    rec, dicts, schema = _kdd(50021)
+    cols = synth.KDD_CATEGORICAL + ["label"]
+    multi = enc.category_counts_multi(rec, schema, cols, [len(dicts[c]) for c in cols])
+    rec_np = rec.cpu().numpy()
+    for c, m in zip(cols, multi):
+        single = enc.category_counts(rec, schema, c, len(dicts[c]))
+        assert torch.equal(m, single)
+        assert np.array_equal(m.cpu().numpy(), oracle.category_counts(rec_np, schema.row_bytes, schema.offsets[c], len(dicts[c])))
+
+
 def test_encode_invalid_codes_and_nan_rows():
     rec, dicts, schema = _kdd(5000, seed=5)
     luts, ordered = kdd_luts_gpu(rec, schema, dicts)
