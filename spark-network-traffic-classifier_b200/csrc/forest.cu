@@ -573,10 +573,11 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
             const int cs = sh_child[side];
             if (cs < 0) continue;
             uint32_t* gh = a.hist_next + (int64_t)cs * hsz;
-            const uint32_t* sh = sh_hist + side * hsz;
-            for (int i = tid; i < hsz; i += kRouteThreads) { const uint32_t v = sh[i]; if (v) atomicAdd(gh + i, v); }
+            uint32_t* sh = sh_hist + side * hsz;
+            for (int i = tid; i < hsz; i += kRouteThreads) { const uint32_t v = sh[i]; if (v) { atomicAdd(gh + i, v); sh[i] = 0; } }   // flush + re-zero
         }
     };
+    for (int i = tid; i < 2 * hsz; i += kRouteThreads) sh_hist[i] = 0;     // zero once; every flush leaves the histograms zeroed
     auto desc_at = [&](int64_t c) { return c < c1 ? __ldg((const int4*)(a.chunks + c)) : make_int4(-1, 0, 0, 0); };
     auto count_of = [&](const int4& d) { return min(kSub, d.y - wid * kSub); };
     auto entries_of = [&](const int4& d, b2f_entry* x0, b2f_entry* x1) {
@@ -636,9 +637,8 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
         const int s = d0.x;
         if (s != cur_slot) {                                   // same decision in every warp: all iterate the same chunks
             __syncthreads();
-            if (cur_slot >= 0) flush();
+            if (cur_slot >= 0) flush();                           // reads sh_child of the OLD slot: barrier before it is replaced
             __syncthreads();
-            for (int i = tid; i < 2 * hsz; i += kRouteThreads) sh_hist[i] = 0;
             if (tid < 16) ((uint32_t*)&sh_split)[tid] = ((const uint32_t*)(a.split + s))[tid];
             if (tid < 2) sh_child[tid] = a.child_slot[2 * s + tid];
             for (int j = tid; j < 2 * m; j += kRouteThreads) {
