@@ -559,9 +559,9 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     const int nq = (F + 1 + 15) / 16;                        // staged 16-byte quads per record
     const int nbC = a.n_bins * a.C, hsz = m * nbC;
     const int tile_words = nq * kSub * 4;
-    uint32_t* tiles = sm_u32 + (size_t)wid * NBUF * tile_words; // this warp's NBUF [nq][64] quad tiles
+    uint32_t* tiles = sm_u32 + (size_t)wid * NBUF * tile_words; // this warp's NBUF [64][nq] quad tiles (entry-major)
     uint32_t* sh_hist = sm_u32 + (size_t)kRouteWarps * NBUF * tile_words;   // [2][hsz]
-    int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: byte offset of the feature inside a tile (entry 0)
+    int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: byte offset of the feature inside a staged record
     __shared__ b200flow_split sh_split;
     __shared__ int sh_child[2];
 
@@ -586,15 +586,19 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
         *x0 = lane < cn ? __ldg(ep + lane) : make_uint2(0u, 0u);
         *x1 = lane + 32 < cn ? __ldg(ep + 32 + lane) : make_uint2(0u, 0u);
     };
+    // The tile is entry-major ([64 entries][nq quads]) and its 64 * nq 16-byte chunks are copied in linear order, lane after
+    // lane: neighbouring lanes fetch neighbouring quads of the SAME record (same 32-byte sector) into neighbouring shared
+    // addresses, which the L1 fills with fewer wavefronts than one scattered 16-byte fill per lane (ncu source page: the
+    // LDGSTS fills were 45 % of the kernel's shared-memory wavefronts with a quad-major tile; 23 instead of 31 per LDGSTS now).
+    // It costs two shuffles per chunk for the record index, so it only pays once the kernel is LSU-bound, not issue-bound:
+    // same time before the predicated merge, 19.0 -> 17.7 ms per fit after it.
+    const uint32_t inv_nq = 65536u / (uint32_t)nq + 1u;         // c / nq == (c * inv_nq) >> 16 for c < 1024
     auto issue_gather = [&](const int4& d, const b2f_entry& x0, const b2f_entry& x1, uint32_t* tile) {
         const int cn = count_of(d);
-        if (lane < cn) {
-            const uint8_t* src = a.tp + (int64_t)x0.x * a.stride;
-            for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + lane) * 4, src + q * 16);
-        }
-        if (lane + 32 < cn) {
-            const uint8_t* src = a.tp + (int64_t)x1.x * a.stride;
-            for (int q = 0; q < nq; ++q) cp_async16(tile + (q * kSub + 32 + lane) * 4, src + q * 16);
+        for (int c = lane; c < kSub * nq; c += 32) {           // uniform trip count (2 * nq)
+            const int e = (int)(((uint32_t)c * inv_nq) >> 16), q = c - e * nq;
+            const uint32_t r0 = __shfl_sync(0xffffffffu, x0.x, e & 31), r1 = __shfl_sync(0xffffffffu, x1.x, e & 31);
+            if (e < cn) cp_async16(tile + c * 4, a.tp + (int64_t)(e < 32 ? r0 : r1) * a.stride + q * 16);
         }
         cp_async_commit();
     };
@@ -622,10 +626,11 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     entries_of(d1, &f0, &f1);
     if (NBUF == 2) issue_gather(d0, e0, e1, tiles);
     int cur_slot = -1;
-    const int lab_pos = (F >> 4) * kSub * 16 + (F & 15);         // byte of the label inside a tile (entry 0; + 16 per entry)
+    const int rs = nq * 16;                                      // bytes per staged record
+    const int lab_pos = F;         // byte of the label inside a tile (entry 0; + 16 per entry)
     for (int64_t c = c0; c < c1; ++c) {
         const int par = NBUF == 2 ? (int)((c - c0) & 1) : 0;
-        const uint8_t* tile8 = (const uint8_t*)(tiles + par * tile_words);   // [nq][64 entries][16 bytes]
+        const uint8_t* tile8 = (const uint8_t*)(tiles + par * tile_words);   // [64 entries][nq * 16 bytes]
         entries_of(d2, &g0, &g1);                              // prefetch, consumed two steps later
         const int4 d3 = desc_at(c + 3);
         if (NBUF == 2) issue_gather(d1, f0, f1, tiles + (par ^ 1) * tile_words);   // in flight during this step's compute
@@ -644,7 +649,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
             for (int j = tid; j < 2 * m; j += kRouteThreads) {
                 const int cs = a.child_slot[2 * s + (j >= m)];
                 const int f = cs >= 0 ? a.subset_next[(int64_t)cs * m + (j < m ? j : j - m)] : 0;
-                sh_fpos[j] = (f >> 4) * kSub * 16 + (f & 15);
+                sh_fpos[j] = f;
             }
             cur_slot = s;
             __syncthreads();
@@ -653,7 +658,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
         if (cnt > 0) {
             const int cl = sh_child[0], cr = sh_child[1];
             const int fs = sh_split.feat, kind = sh_split.kind, thr = sh_split.bin_thr;
-            const int fs_pos = (fs >> 4) * kSub * 16 + (fs & 15);
+            const int fs_pos = fs;
             int nL = 0, nR = 0;
             uint32_t dec = 0;
 #pragma unroll
@@ -661,7 +666,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                 const int i = k * 32 + lane;
                 int d = 0;
                 if (i < cnt) {
-                    const int bin = tile8[fs_pos + i * 16];
+                    const int bin = tile8[fs_pos + i * rs];
                     const bool left = kind == 0 ? (bin <= thr) : ((sh_split.mask[bin >> 6] >> (bin & 63)) & 1ull);
                     d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
                 }
@@ -673,7 +678,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                     const int side = d - 1;
                     const int* fpos = sh_fpos + side * m;
                     uint32_t* hist = sh_hist + side * hsz;
-                    const uint32_t lab = tile8[lab_pos + i * 16];
+                    const uint32_t lab = tile8[lab_pos + i * rs];
                     const uint32_t w = k ? e1.y : e0.y;
                     if (M > 0 && MERGE) {
                         // top-group merge: per feature, the lanes that share the first active lane's (bin, label, child) counter are
@@ -685,7 +690,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
 #pragma unroll
                         for (int j = 0; j < M; ++j) {
                             const int fp = fpos[j];
-                            const uint32_t bin = tile8[fp + i * 16];
+                            const uint32_t bin = tile8[fp + i * rs];
                             const uint32_t key = bin | tag;
                             uint32_t* addr = &hist[j * nbC + bin * a.C + lab];
                             const int l0 = __ffs(active) - 1;
@@ -696,7 +701,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                     } else {
                         for (int j = 0; j < m; ++j) {
                             const int fp = fpos[j];
-                            const uint32_t bin = tile8[fp + i * 16];
+                            const uint32_t bin = tile8[fp + i * rs];
                             atomicAdd(&hist[j * nbC + bin * a.C + lab], w);
                         }
                     }
