@@ -336,7 +336,7 @@ def main():
 
     # ---- CPU baseline (oracle, bounded sample) ---------------------------------------------------------
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:                     # rank 0 at N = 1 only (the tier contract)
         import oracle
         if a.cpu_rows <= 0:
             a.cpu_rows = a.rows                                  # the whole per-GPU workload: about 20 s on the box's 64 threads
