@@ -316,8 +316,13 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint8_t* __rest
     }
 }
 __global__ void __launch_bounds__(256) dedup_min_kernel(int64_t n, const int32_t* __restrict__ slot_of, int32_t* minrow) {
+    // warp-aggregated: the lowest lane of a duplicate group holds the group's smallest row of this warp, and only it goes to
+    // memory — the smurf flood alone is a third of KDD99, i.e. ~10 lanes of every warp hammering ONE address otherwise
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicMin(&minrow[slot_of[i]], (int)i);
+    const int lane = lane_id();
+    const int sl = i < n ? slot_of[i] : -1 - lane;
+    const uint32_t g = __match_any_sync(0xffffffffu, sl);
+    if (i < n && (int)(__ffs(g) - 1) == lane) atomicMin(&minrow[sl], (int)i);
 }
 __global__ void __launch_bounds__(256) dedup_flag_kernel(int64_t n, const int32_t* __restrict__ slot_of, const int32_t* __restrict__ minrow,
                                                          int32_t* rep, int32_t* flag) {
