@@ -895,7 +895,9 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     const int max_per_sm = (route_variant() & 1) ? 3 : 4;   // __launch_bounds__
     if (per_sm > max_per_sm) per_sm = max_per_sm;
     if (per_sm < 1) per_sm = 1;
-    const int64_t want = (int64_t)kNumSMs * per_sm;
+    static int waves = -1;                                    // CTAs per resident slot: > 1 lets the block scheduler even out the tail
+    if (waves < 0) { const char* e = getenv("B200FLOW_ROUTE_WAVES"); waves = e ? atoi(e) : 2; if (waves < 1) waves = 1; }   // measured per fit: 17.7 (1), 17.4 (2-6), 17.6 ms (8)
+    const int64_t want = (int64_t)kNumSMs * per_sm * waves;
     const unsigned grid = (unsigned)(n_chunks_max < want ? n_chunks_max : want);
 #define B2F_ROUTE_LAUNCH(KERNEL)                                                                                               \
     {                                                                                                                          \
