@@ -117,7 +117,9 @@ int b200flow_sample_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F
  * Categorical features (arity>0) get n_thr = 0.  scratch: F * pow2ceil(n_s) doubles. */
 int b200flow_find_splits(double* sample, int64_t cap, int32_t n_s, int32_t F,
                          const int32_t* arity, int32_t max_bins,
-                         double* thresholds, int32_t* n_thr, void* stream);
+                         double* thresholds, int32_t* n_thr,
+                         const int32_t* n_s_dev /* NULL, or the device-side sample count (then n_s is a host upper bound) */,
+                         void* stream);
 
 /* R5  TreePoint.convertToTreeRDD/findBin: dense features (+ int32 labels, may be NULL)
  * -> binned TreePoint records tp[n][tp_stride] (uint8): bytes [0,F) = bin per feature

@@ -36,7 +36,7 @@ _SIGNATURES = {
     "b200flow_encode": [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P],
     "b200flow_column_moments": [_P, _I32, _I64, _I32, _I64, _P, _P, _P, _P],
     "b200flow_sample_rows": [_P, _I32, _I64, _I32, _I64, _U64, _U64, _I64, _P, _I64, _P, _P],
-    "b200flow_find_splits": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P],
+    "b200flow_find_splits": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P],
     "b200flow_bin_rows": [_P, _I32, _I64, _I32, _I64, _P, _P, _P, _I32, _P, _P, _I32, _P, _P],
     "b200flow_dedup_rows": [_P, _I64, _I32, _I32, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200flow_bag_weights": [_U64, _I32, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P],

@@ -121,7 +121,7 @@ def build_metadata(n_rows, F, num_classes, arity, max_bins, num_trees, strategy=
     return mpb, kind, max(1, min(m, F))
 
 
-def dedup_rows(tp, key_bytes):
+def dedup_rows(tp, key_bytes, sync=True):
     """unique TreePoint records of a binned batch: -> (tp_unique [U, stride], uid int32 [n], U).  Flow records repeat
     massively (KDD99: 4.9 M rows, ~1.07 M distinct), so both the level loop and the batch predictor run per unique record."""
     n, stride = tp.shape
@@ -136,6 +136,8 @@ def dedup_rows(tp, key_bytes):
     tpu = torch.empty_like(tp)
     _timed("dedup_rows", "b200flow_dedup_rows", ptr(tp), n, stride, key_bytes, ptr(table), ptr(minrow), cap_tab, ptr(slot_of), ptr(rep),
            ptr(flag), ptr(pos), ptr(total), ptr(uid), ptr(tpu))
+    if not sync:                       # caller reads the count together with its other device scalars
+        return tpu, uid, total
     U = int(total.item())
     return tpu[:U], uid, U
 
@@ -304,12 +306,14 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     if has_cont:
         call("b200flow_sample_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), seed, keep, int(row_offset),
              ptr(sample), cap, ptr(n_s_dev))
-        n_s = int(n_s_dev.item())
-        if n_s > cap:
-            raise B200FlowError("findSplits sample overflow (%d > %d)" % (n_s, cap))
         if group is not None:
+            n_s = int(n_s_dev.item())
+            if n_s > cap:
+                raise B200FlowError("findSplits sample overflow (%d > %d)" % (n_s, cap))
             sample, n_s, cap = _gather_sample(sample, n_s, cap, F, group)
-        call("b200flow_find_splits", ptr(sample), cap, n_s, F, ptr(arity_dev), mpb, ptr(thresholds), ptr(n_thr))
+            call("b200flow_find_splits", ptr(sample), cap, n_s, F, ptr(arity_dev), mpb, ptr(thresholds), ptr(n_thr), None)
+        else:       # single GPU: the sample count stays on the device (checked with the other counts below: one host sync)
+            call("b200flow_find_splits", ptr(sample), cap, cap, F, ptr(arity_dev), mpb, ptr(thresholds), ptr(n_thr), ptr(n_s_dev))
     del sample
 
     # ---- R5 binning
@@ -319,18 +323,23 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     _timed("bin_rows", "b200flow_bin_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), ptr(thresholds), ptr(n_thr),
            ptr(arity_dev), mpb, ptr(labels), ptr(tp), stride, ptr(bad))
     feat_bins = torch.where(arity_dev > 0, arity_dev, n_thr + 1).to(torch.int32).contiguous()
-    head = torch.cat([bad, feat_bins.max().reshape(1).to(torch.int32)]).cpu()
+    feat_kind = _i32(kind, dev)
+    # ---- de-duplicate the binned rows: the level loop runs on UNIQUE TreePoint records carrying summed bag weights.
+    # Everything is enqueued first; ONE host read then fetches the bad-cell count, the bin count, the sample count and U.
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    dedup = n > 0 and DEDUP
+    if dedup:
+        tp, uid, u_dev = dedup_rows(tp, F + 1, sync=False)
+    else:
+        uid, u_dev = None, torch.full((1,), n, dtype=torch.int64, device=dev)
+    head = torch.cat([bad.to(torch.int64), feat_bins.max().reshape(1).to(torch.int64), n_s_dev.to(torch.int64), u_dev]).cpu()
     if int(head[0]) != 0:
         raise ValueError("categorical feature value outside [0, arity) or non-integral in %d cells" % int(head[0]))
-    n_bins = int(head[1])
-    feat_kind = _i32(kind, dev)
-
-    # ---- de-duplicate the binned rows: the level loop runs on UNIQUE TreePoint records carrying summed bag weights
-    total = torch.zeros(1, dtype=torch.int64, device=dev)
-    if n > 0 and DEDUP:
-        tp, uid, U = dedup_rows(tp, F + 1)
-    else:
-        uid, U = None, n
+    if has_cont and group is None and int(head[2]) > cap:
+        raise B200FlowError("findSplits sample overflow (%d > %d)" % (int(head[2]), cap))
+    n_bins, U = int(head[1]), int(head[3])
+    if dedup:
+        tp = tp[:U]
     # ---- R6 bagging: W[tree][unique] = summed Poisson weights; entries = non-zero (unique, weight) pairs per tree
     bagging = p.bootstrap and T > 1
     cdf_host = np.ascontiguousarray(poisson_cdf_table(p.subsampling_rate)) if bagging else None

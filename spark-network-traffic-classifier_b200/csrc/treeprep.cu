@@ -108,8 +108,9 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const T* __restrict__ 
 // then one thread walks the distinct values with MLlib's stride rule.
 __global__ void __launch_bounds__(1024) find_splits_kernel(double* sample, int64_t cap, int n_s, int n_pad,
                                                            const int32_t* __restrict__ arity, int max_bins,
-                                                           double* thresholds, int32_t* n_thr) {
+                                                           double* thresholds, int32_t* n_thr, const int32_t* __restrict__ n_s_dev) {
     const int f = blockIdx.x;
+    if (n_s_dev) n_s = min(*n_s_dev, n_pad);               // the count stays on the device: the host did not wait for it
     __shared__ int sh_distinct;
     if (arity[f] > 0 || n_s <= 0) { if (threadIdx.x == 0) n_thr[f] = 0; return; }
     double* v = sample + (int64_t)f * cap;
@@ -173,8 +174,9 @@ constexpr int kFindSplitsSmemMax = 16384;
 
 __global__ void __launch_bounds__(1024) find_splits_smem_kernel(const double* __restrict__ sample, int64_t cap, int n_s, int n_pad,
                                                                 const int32_t* __restrict__ arity, int max_bins,
-                                                                double* thresholds, int32_t* n_thr) {
+                                                                double* thresholds, int32_t* n_thr, const int32_t* __restrict__ n_s_dev) {
     extern __shared__ __align__(8) uint8_t fs_raw[];
+    if (n_s_dev) n_s = min(*n_s_dev, n_pad);               // the count stays on the device: the host did not wait for it
     double* v = (double*)fs_raw;                           // [n_pad]
     int* B = (int*)(v + n_pad);                            // [n_pad] start index of every run but the first
     __shared__ int sh[33];
@@ -492,18 +494,18 @@ extern "C" int b200flow_sample_rows(const void* x, int32_t dtype, int64_t n_rows
 }
 
 extern "C" int b200flow_find_splits(double* sample, int64_t cap, int32_t n_s, int32_t F, const int32_t* arity,
-                                    int32_t max_bins, double* thresholds, int32_t* n_thr, void* stream) {
+                                    int32_t max_bins, double* thresholds, int32_t* n_thr, const int32_t* n_s_dev, void* stream) {
     B2F_REQUIRE(sample && arity && thresholds && n_thr && F > 0 && max_bins >= 2 && max_bins <= 256, "find_splits: bad arguments");
     B2F_REQUIRE(n_s >= 0 && n_s <= cap, "find_splits: n_s exceeds cap");
-    int n_pad = 1; while (n_pad < n_s) n_pad <<= 1;
+    int n_pad = 1; while (n_pad < n_s) n_pad <<= 1;         // with n_s_dev, n_s is the host's upper bound (the kernels clamp to n_pad)
     B2F_REQUIRE(n_pad <= cap, "find_splits: cap must be >= pow2ceil(n_s)");
     if (n_pad <= kFindSplitsSmemMax) {
         const size_t smem = (size_t)n_pad * 12;
         cudaError_t e = cudaFuncSetAttribute(find_splits_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("find_splits: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
-        find_splits_smem_kernel<<<F, 1024, smem, (cudaStream_t)stream>>>(sample, cap, n_s, n_pad, arity, max_bins, thresholds, n_thr);
+        find_splits_smem_kernel<<<F, 1024, smem, (cudaStream_t)stream>>>(sample, cap, n_s, n_pad, arity, max_bins, thresholds, n_thr, n_s_dev);
     } else {
-        find_splits_kernel<<<F, 1024, 0, (cudaStream_t)stream>>>(sample, cap, n_s, n_pad, arity, max_bins, thresholds, n_thr);
+        find_splits_kernel<<<F, 1024, 0, (cudaStream_t)stream>>>(sample, cap, n_s, n_pad, arity, max_bins, thresholds, n_thr, n_s_dev);
     }
     return check_launch("find_splits");
 }
