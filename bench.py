@@ -176,8 +176,7 @@ def step_resident(rec, dicts, a, grp):
     x, y, _ = plan.run(rec, torch.float32, want_valid=False)                        # R2+R3 fused encode
     off, _ = bdist.global_offset(n, dev, grp)
     sid = rows.random_split_ids(n, [0.75, 0.25], 2019, off, dev)
-    (xtr, ytr), ntr = rows.compact_many([x, y], sid == 0)
-    (xte, yte), nte = rows.compact_many([x, y], sid == 1)
+    ((xtr, ytr), ntr), ((xte, yte), nte) = rows.split_many([x, y], sid, 2)
     del x, y
     arity = [0] * 38 + [len(ordered[c]) for c in synth.KDD_CATEGORICAL]
     C = len(ordered["label"])

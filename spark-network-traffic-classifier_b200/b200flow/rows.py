@@ -20,15 +20,11 @@ def random_split_ids(n, weights, seed, row_offset=0, device="cuda"):
     return sid[:n]
 
 
-def compact_many(bufs, flag):
-    """keep the rows with flag != 0 in every buffer of `bufs` (each [n] or [n, k], contiguous, 4-byte multiple
-    row size); order preserved.  Returns (list of compacted tensors, kept count)."""
+def _compact_enqueue(bufs, flag):
+    """enqueue the compaction of every buffer; -> (full-size outputs, device kept-count int64[1])."""
     flag = flag.to(torch.uint8).contiguous()
     n = flag.shape[0]
     dev = flag.device
-    if n == 0 or not bufs:
-        k = int(flag.sum().item()) if n else 0
-        return [b[:k] for b in bufs], k
     nb = (n + 1023) // 1024
     scratch = torch.zeros(nb + 1 + (nb + 1) // 2 + 1, dtype=torch.int64, device=dev)
     kept = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -39,5 +35,27 @@ def compact_many(bufs, flag):
         out = torch.empty_like(b)
         call("b200flow_compact_rows", ptr(b), n, rb, ptr(flag), 1, ptr(out), ptr(scratch), ptr(kept))
         outs.append(out)
+    return outs, kept
+
+
+def compact_many(bufs, flag):
+    """keep the rows with flag != 0 in every buffer of `bufs` (each [n] or [n, k], contiguous, 4-byte multiple
+    row size); order preserved.  Returns (list of compacted tensors, kept count)."""
+    n = flag.shape[0]
+    if n == 0 or not bufs:
+        k = int(flag.sum().item()) if n else 0
+        return [b[:k] for b in bufs], k
+    outs, kept = _compact_enqueue(bufs, flag)
     k = int(kept.item())
     return [o[:k] for o in outs], k
+
+
+def split_many(bufs, split_id, n_splits):
+    """randomSplit's row movement: the rows of every split, for every buffer, with ONE host sync for all the kept counts.
+    -> [(list of compacted tensors, count)] per split."""
+    n = split_id.shape[0]
+    if n == 0 or not bufs:
+        return [compact_many(bufs, split_id == k) for k in range(n_splits)]
+    parts = [_compact_enqueue(bufs, split_id == k) for k in range(n_splits)]
+    counts = torch.cat([kept for _, kept in parts]).cpu().tolist()
+    return [([o[:int(c)] for o in outs], int(c)) for (outs, _), c in zip(parts, counts)]

@@ -323,13 +323,19 @@ class DataFrame:
             return self._field_values(name)
         return c.data
 
+    def _compact_bufs(self):
+        needs_rec = self._rec is not None and any(c.kind == "field" for c in self._cols.values())
+        names = [k for k, c in self._cols.items() if c.kind != "field"]
+        return needs_rec, names, ([self._rec] if needs_rec else []) + [self._cols[k].data for k in names]
+
     def _compact(self, flag):
         """keep rows with flag != 0 in every column (order preserved) — b200flow compaction kernel."""
         from b200flow.rows import compact_many
-        needs_rec = self._rec is not None and any(c.kind == "field" for c in self._cols.values())
-        names = [k for k, c in self._cols.items() if c.kind != "field"]
-        bufs = ([self._rec] if needs_rec else []) + [self._cols[k].data for k in names]
+        needs_rec, names, bufs = self._compact_bufs()
         outs, k = compact_many(bufs, flag)
+        return self._from_compacted(needs_rec, names, outs, k)
+
+    def _from_compacted(self, needs_rec, names, outs, k):
         rec = outs[0] if needs_rec else None
         outs = outs[1:] if needs_rec else outs
         cols = {}
@@ -361,7 +367,9 @@ class DataFrame:
         dev = self._device()
         off, _ = bdist.global_offset(self._n, dev)
         sid = random_split_ids(self._n, weights, seed, off, dev)
-        return [self._compact(sid == k) for k in range(len(weights))]
+        from b200flow.rows import split_many
+        needs_rec, names, bufs = self._compact_bufs()          # every split is enqueued, then ONE host sync for the row counts
+        return [self._from_compacted(needs_rec, names, outs, k) for outs, k in split_many(bufs, sid, len(weights))]
 
     def groupBy(self, *cols):
         cols = [c for cc in cols for c in (cc if isinstance(cc, (list, tuple)) else [cc])]
