@@ -398,6 +398,33 @@ def test_dedup_does_not_change_the_forest(monkeypatch):
     assert forests_equal(m1.export(), m2.export()) == [] and np.array_equal(m1.export()["gain"], m2.export()["gain"])
 
 
+def test_large_batch_size_independent_properties(monkeypatch):
+    # Sizes the oracle cannot finish in seconds (1.2 M rows, 24 trees, depth 12) are checked through properties that do not
+    # depend on the size: (1) the product path (fused level kernel, unique records, top-level table, sharded-style padding)
+    # builds byte for byte the forest of the plainest path (row-by-row, unfused hist + partition kernels); (2) the root
+    # histogram of every tree sums to its bag weight total: sum of the roots' class counts == sum of the entries' weights;
+    # (3) predictions do not depend on de-duplicating the test records, and raw votes sum to the number of trees.
+    x, y, arity, C = _features(1200000, 5, 909)
+    p = fr.ForestParams(num_trees=24, max_bins=70, max_depth=12, seed=77)
+    fast = fr.fit_forest(x, y, C, arity, p)
+    ex_fast = fast.export()
+    roots = ex_fast["nid"] == 1
+    assert int(roots.sum()) == 24
+    w = oracle.bag_weights(77, 24, x.shape[0], oracle.poisson_cdf_table(1.0))          # [T, n] Poisson weights (host, cheap)
+    assert np.array_equal(ex_fast["counts"][roots].sum(1), w.astype(np.int64).sum(1))
+    xt = x[:300000]
+    raw_a, prob_a, pred_a = fast.predict(xt)
+    assert np.allclose(raw_a.sum(1).cpu().numpy(), 24.0, rtol=0, atol=1e-9)
+    monkeypatch.setattr(fr, "DEDUP", False)
+    monkeypatch.setattr(fr, "FUSED", False)
+    monkeypatch.setattr(fr, "TOP_LEVELS", 0)
+    plain = fr.fit_forest(x, y, C, arity, p)
+    ex_plain = plain.export()
+    assert forests_equal(ex_fast, ex_plain) == [] and np.array_equal(ex_fast["gain"], ex_plain["gain"])
+    raw_b, prob_b, pred_b = plain.predict(xt)
+    assert torch.equal(raw_a, raw_b) and torch.equal(prob_a, prob_b) and torch.equal(pred_a, pred_b)
+
+
 def test_forest_fp32_features_equal_fp64_features():
     x, y, arity, C = _features(30000, 5, 55)
     p = fr.ForestParams(num_trees=4, max_bins=70, max_depth=6, seed=5)
