@@ -56,6 +56,46 @@ def test_encode_full_onehot_scaled_matches_oracle(n):
     assert (err <= 1e-6 * np.abs(want) + 1e-30).all()                                  # 1e-6 relative (north_star)
 
 
+def test_encode_full_size_properties():
+    # KDD99-full row count: the fused encode is checked through properties that need no CPU pass over 4.9 M rows —
+    # numeric slots are the raw fields bit for bit, an index slot is lut[code], a dropLast one-hot block has one 1 exactly when
+    # the rank is not the last one (and it sits at the rank), the label is lut[label code], and the scaled vector has
+    # mean 0 / unit sample variance per column.
+    n = 4898431
+    rec, dicts, schema = _kdd(n, seed=2019)
+    luts, ordered = kdd_luts_gpu(rec, schema, dicts)
+    faithful = kdd_plan(schema, luts, ordered)
+    x, y, _ = faithful.run(rec, torch.float32, want_valid=False)
+    raw = rec.view(torch.int32)
+    numeric = [c for c in synth.KDD_COLUMNS if c not in synth.KDD_CATEGORICAL and c != "label"]
+    for j, c in enumerate(numeric):
+        assert torch.equal(x[:, j].view(torch.int32), raw[:, schema.offsets[c] // 4])
+    for j, c in enumerate(synth.KDD_CATEGORICAL):
+        lut = torch.from_numpy(np.asarray(luts[c], np.int32)).to(DEV)
+        assert torch.equal(x[:, 38 + j], lut[raw[:, schema.offsets[c] // 4].long()].to(torch.float32))
+    lab_lut = torch.from_numpy(np.asarray(luts["label"], np.int32)).to(DEV)
+    assert torch.equal(y, lab_lut[raw[:, schema.offsets["label"] // 4].long()])
+    del x
+    full = kdd_plan(schema, luts, ordered, onehot=True, label=False)
+    xo, _, _ = full.run(rec, torch.float32, want_valid=False)
+    col = 38
+    for c in synth.KDD_CATEGORICAL:
+        K = len(ordered[c]); blk = xo[:, col:col + K - 1]
+        rank = torch.from_numpy(np.asarray(luts[c], np.int32)).to(DEV)[raw[:, schema.offsets[c] // 4].long()]
+        assert torch.equal(blk.sum(1), (rank < K - 1).to(torch.float32))
+        hot = torch.where(rank < K - 1, rank, torch.zeros_like(rank)).long()
+        assert torch.equal(blk.gather(1, hot[:, None])[:, 0], (rank < K - 1).to(torch.float32))
+        col += K - 1
+    mean, std = enc.column_moments(xo)
+    m, sd = mean.cpu().numpy(), std.cpu().numpy()
+    full.set_scaling(m, np.where(sd != 0, 1.0 / np.where(sd != 0, sd, 1.0), 0.0))
+    del xo
+    xs, _, _ = full.run(rec, torch.float64, want_valid=False)
+    live = torch.from_numpy(sd != 0).to(DEV)
+    assert xs.mean(0).abs().max().item() < 1e-9
+    assert ((xs.var(0, unbiased=True) - 1.0).abs()[live]).max().item() < 1e-9 and (xs[:, ~live] == 0).all()
+
+
 def test_category_counts_multi_equals_single_columns():
     rec, dicts, schema = _kdd(50021)
     cols = synth.KDD_CATEGORICAL + ["label"]
