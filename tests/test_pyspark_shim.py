@@ -211,3 +211,35 @@ def test_onehot_standardscaler_pipeline_is_fused_and_matches_oracle(tmp_path):
     d3 = spark.createDataFrame([("a",), ("b",), ("c",), ("a",), ("a",), ("c",)], ["x"])
     d3 = StringIndexer(inputCol="x", outputCol="i").fit(d3).transform(d3)
     assert d3._cols["i"].data.cpu().numpy().tolist() == [0.0, 2.0, 1.0, 0.0, 0.0, 1.0]
+
+
+def test_indexer_columns_are_lazy_and_fused_but_identical():
+    """StringIndexerModel.transform defers its kernel when the record buffer's own category counts prove that no label is
+    unseen; VectorAssembler fuses the lookup.  The deferred column, once read, and the fused vector hold the same values as
+    the eager path; a model applied to OTHER data still checks for unseen labels."""
+    from b200flow import synth
+    from pyspark.ml import Pipeline
+    from pyspark.ml.feature import SparkException, StringIndexer, VectorAssembler
+    from pyspark.sql import DataFrame
+    rec, dicts = synth.make_kdd(30011, 23, seed=8, device="cuda")
+    df = DataFrame.fromRecords(rec, synth.kdd_schema(), dicts)
+    cats = synth.KDD_CATEGORICAL
+    stages = [StringIndexer(inputCol=c, outputCol=c + "_num") for c in cats + ["label"]]
+    model = Pipeline(stages=stages).fit(df)
+    out = model.transform(df)
+    assert all(out._cols[c + "_num"]._data is None for c in cats + ["label"])          # nothing launched yet
+    numerical = [c for c in out.columns if c not in cats + ["label", "label_num"]]
+    feats = VectorAssembler(inputCols=numerical, outputCol="features").transform(out)._cols["features"].data
+    raw = rec.view(torch.int32)
+    schema = synth.kdd_schema()
+    for j, c in enumerate(cats):
+        lazy = out._cols[c + "_num"].data                                             # materialised on first read
+        rank_of = {s: i for i, s in enumerate(model.stages[j].labels)}
+        lut = torch.tensor([rank_of.get(s, -1) for s in dicts[c]], dtype=torch.float64, device="cuda")
+        want = lut[raw[:, schema.offsets[c] // 4].long()]
+        assert torch.equal(lazy, want) and torch.equal(feats[:, 38 + j].to(torch.float64), want)
+    # other data with a label the model has not seen: the eager, checking path runs and raises
+    few = rec[rec.view(torch.int32)[:, schema.offsets["service"] // 4] == 0]
+    m_few = StringIndexer(inputCol="service", outputCol="s_num").fit(DataFrame.fromRecords(few.contiguous(), schema, dicts))
+    with pytest.raises(SparkException):
+        m_few.transform(df)
