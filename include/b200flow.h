@@ -131,7 +131,7 @@ int b200flow_bin_rows(const void* x, int32_t dtype, int64_t n_rows, int32_t F, i
                       int32_t max_bins, const int32_t* labels,
                       uint8_t* tp, int32_t tp_stride, int32_t* bad_rows, void* stream);
 
-/* Row de-duplication (flow records repeat massively: KDD99 has 4.9 M rows but ~1.07 M distinct ones).  Rows whose TreePoint
+/* helper of R5-R7 inside RandomForestClassifier.fit (kdd99.py:79, cicids17.py:83) and of R9 (kdd99.py:82); no MLlib counterpart — exact because the histograms are integer sums.  Row de-duplication (flow records repeat massively: KDD99 has 4.9 M rows but ~1.07 M distinct ones).  Rows whose TreePoint
  * records (first key_bytes bytes: bins + label) are identical are interchangeable for the trees: uid[row] = index of the
  * row's unique record (numbered in order of each group's first row), tp_unique[U][tp_stride] = the unique records,
  * *n_unique = U (device scalar).  Scratch (caller-owned): table/minrow int32[table_cap] (power of two >= 2*n_rows),
@@ -150,20 +150,20 @@ int b200flow_bag_weights(uint64_t seed, int32_t T, int64_t row_offset, int64_t n
                          const uint32_t* poisson_cdf, const uint32_t* poisson_cdf_host,
                          const int32_t* uid, const int32_t* perm, int64_t n_unique, uint32_t* W, void* stream);
 
-/* counting sort of the rows by unique id: perm[p] = row, uperm[p] = uid[perm[p]] (non-decreasing).  Scratch: gsize/cursor
+/* R6 helper (BaggedPoint.convertToBaggedRDD, inside fit: kdd99.py:79, cicids17.py:83): counting sort of the rows by unique id: perm[p] = row, uperm[p] = uid[perm[p]] (non-decreasing).  Scratch: gsize/cursor
  * int32[n_unique], goff int64[n_unique+1]. */
 int b200flow_group_rows(const int32_t* uid, int64_t n_rows, int64_t n_unique, int32_t* gsize, int64_t* goff,
                         int32_t* cursor, int32_t* perm, int32_t* uperm, void* stream);
 
-/* entries of every tree = its non-zero (unique record, summed weight) pairs in unique-id order.  Pass 1: non-zeros per
+/* R6 (BaggedPoint.convertToBaggedRDD, inside fit: kdd99.py:79, cicids17.py:83): entries of every tree = its non-zero (unique record, summed weight) pairs in unique-id order.  Pass 1: non-zeros per
  * (tree, block of 1024 uniques) -> blk_cnt[T][n_blocks]. */
 int b200flow_bag_count(const uint32_t* W, int32_t T, int64_t n_unique, int32_t* blk_cnt, void* stream);
 
-/* pass 2: given blk_off = exclusive scan of blk_cnt (int64, tree-major) write the entries; one entry = 8 bytes
+/* R6, pass 2: given blk_off = exclusive scan of blk_cnt (int64, tree-major) write the entries; one entry = 8 bytes
  * {uint32 unique record index, uint32 weight}. */
 int b200flow_bag_fill(const uint32_t* W, int32_t T, int64_t n_unique, const int64_t* blk_off, void* ent, void* stream);
 
-/* exclusive prefix sum utilities used by the trainer (single launch, any n) */
+/* (no MLlib counterpart; inside fit: kdd99.py:79, cicids17.py:83) exclusive prefix sum utilities used by the trainer (single launch, any n) */
 int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* out,
                                        int64_t* total, void* stream);
 
@@ -223,7 +223,8 @@ typedef struct b200flow_node {
     uint32_t nid;      /* MLlib node id                                  */
 } b200flow_node;       /* 16 bytes */
 
-/* grows the pool by one level: for each slot writes its node record (+ mask, counts), creates
+/* R8 driver side (LearningNode growth in RandomForest.findBestSplits, ml/tree/impl/RandomForest.scala [MLlib]; inside fit:
+ * kdd99.py:79, cicids17.py:83).  Grows the pool by one level: for each slot writes its node record (+ mask, counts), creates
  * two children per split (counts from left/right_counts), and emits the next level's slots for
  * the non-leaf children (next_* arrays, capacity 2*n_slots; next_parent = parent slot*2+side;
  * child_slot[2*s+side] = index of that child among the next slots, -1 when it is a leaf; may be NULL).
@@ -239,7 +240,7 @@ int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, const uint32_
                         int32_t* next_tree, uint32_t* next_nid, int32_t* next_node,
                         int32_t* next_parent, int32_t* child_slot, int64_t* counters, void* stream);
 
-/* routes every entry of every split slot to its child: left entries grow up from seg_begin,
+/* R7 unfused fallback (the row -> node relation MLlib recomputes with predictImpl in findBestSplits; inside fit: kdd99.py:79, cicids17.py:83): routes every entry of every split slot to its child: left entries grow up from seg_begin,
  * right entries grow down from seg_end inside the same range of the destination buffers;
  * cursors[s*2+{0,1}] (int32, caller zeroes) end as (#left, #right).  Entries of children
  * that are leaves are dropped. */
@@ -275,14 +276,14 @@ int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
 int b200flow_plan_route(int32_t n_slots, const b200flow_split* split, const int64_t* seg_begin, const int64_t* seg_end,
                         int32_t chunk_rows, const int32_t* slot_node, double* node_gain, int32_t* n_chunks, void* stream);
 
-/* segment table of the next level from the parents' ranges and the partition cursors */
+/* R7/R8 bookkeeping (inside fit: kdd99.py:79, cicids17.py:83): segment table of the next level from the parents' ranges and the partition cursors */
 int b200flow_next_segments(int32_t n_next /* or an upper bound */, const int64_t* n_next_dev /* NULL or the device-side count */,
                            const int32_t* next_parent,
                            const int64_t* seg_begin, const int64_t* seg_end,
                            const int32_t* cursors, int64_t* next_begin, int64_t* next_end,
                            void* stream);
 
-/* leaf payloads: prob[node][k] = counts[k] / Σcounts (fp64 true division), 0 if Σ == 0 */
+/* R9 preparation (LeafNode / ImpurityCalculator.prob in ml/tree/Node.scala [MLlib]; fit at kdd99.py:79): leaf payloads: prob[node][k] = counts[k] / Σcounts (fp64 true division), 0 if Σ == 0 */
 int b200flow_finalize_forest(int64_t n_nodes, const uint32_t* pool_counts, int32_t C,
                              double* leaf_prob, void* stream);
 
@@ -303,7 +304,7 @@ int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_rows,
 int b200flow_build_top_nodes(const b200flow_node* nodes, const int32_t* node_tree, int64_t n_nodes, int32_t T,
                              int32_t top_levels, void* top, void* stream);
 
-/* out[i] = src[idx[i]] for rows of row_bytes (multiple of 4): spreads the predictions computed once per UNIQUE test record
+/* R9 helper (model.transform, kdd99.py:82, cicids17.py:86): out[i] = src[idx[i]] for rows of row_bytes (multiple of 4): spreads the predictions computed once per UNIQUE test record
  * (b200flow_dedup_rows) back to the rows. */
 int b200flow_gather_rows(const void* src, int32_t row_bytes, const int32_t* idx, int64_t n_rows, void* out, void* stream);
 
@@ -319,7 +320,7 @@ int b200flow_random_split(uint64_t seed, int64_t row_offset, int64_t n_rows,
                           const double* cum_bounds_host, int32_t n_splits, uint8_t* split_id,
                           void* stream);
 
-/* stable row compaction (where / handleInvalid="skip" / one randomSplit part):
+/* SURVEY 8f rank 1 (Dataset.randomSplit kdd99.py:52, where cicids17.py:30-35, handleInvalid=skip cicids17.py:41): stable row compaction (where / handleInvalid="skip" / one randomSplit part):
  * keeps rows with flag[i] == want; out_rows gets the kept rows' row_bytes-sized records in
  * order.  Counting per block and the scan happen inside; scratch: (n_blocks+1) int64 followed by
  * n_blocks int32, n_blocks = ceil(n/1024); *n_kept (device int64) receives the count. */
