@@ -95,7 +95,7 @@ int b200flow_encode(const void* records, int64_t n_rows, int32_t row_bytes,
                     void* out, int32_t out_dtype, int32_t* label_out, uint8_t* valid_out,
                     void* stream);
 
-/* R3c  StandardScaler.fit: per-column shifted power sums of a dense [n, D] matrix
+/* R3c  StandardScaler.fit (ml/feature/StandardScaler.scala [MLlib]; north_star encode, not called by kdd99.py/cicids17.py): per-column shifted power sums of a dense [n, D] matrix
  * (leading dimension ld elements): sum[d] += Σ(x-shift[d]), sumsq[d] += Σ(x-shift[d])².
  * shift may be NULL (=0).  Two calls (shift = 0, then shift = mean) give the
  * corrected two-pass variance; multi-GPU: allreduce the 2·D doubles between them. */
@@ -103,7 +103,7 @@ int b200flow_column_moments(const void* x, int32_t dtype, int64_t n_rows, int32_
                             const double* shift, double* sum, double* sumsq, void* stream);
 
 /* --------------------------------------------------------------- tree prep ---
- * R4  RandomForest.findSplits, sampling half: Bernoulli(keep_threshold / 2^32) row
+ * R4  RandomForest.findSplits (inside fit: kdd99.py:79, cicids17.py:83), sampling half: Bernoulli(keep_threshold / 2^32) row
  * sample keyed by (seed, global row); gathers the sampled rows of the dense feature
  * matrix into a COLUMN-major fp64 buffer sample[F][cap]; *n_sampled is advanced
  * atomically (caller zeroes; rows beyond cap are counted but not stored). */
@@ -140,7 +140,7 @@ int b200flow_dedup_rows(const uint8_t* tp, int64_t n_rows, int32_t tp_stride, in
                         int32_t* table, int32_t* minrow, int64_t table_cap, int32_t* slot_of, int32_t* rep,
                         int32_t* flag, int64_t* pos, int64_t* n_unique, int32_t* uid, uint8_t* tp_unique, void* stream);
 
-/* R6  BaggedPoint.convertToBaggedRDD: W[tree][uid[row]] += Poisson weight of (tree, global row).  poisson_cdf: 32 increasing
+/* R6  BaggedPoint.convertToBaggedRDD (inside fit: kdd99.py:79, cicids17.py:83): W[tree][uid[row]] += Poisson weight of (tree, global row).  poisson_cdf: 32 increasing
  * uint32 thresholds, weight = #{k: cdf[k] != 2^32-1 && r >= cdf[k]} with r = word tree%4 of Philox(seed,'BAGG', row, tree/4);
  * NULL = no bagging (weight 1 per row, numTrees==1); poisson_cdf_host = the same 32 values in host memory (the first
  * thresholds travel as kernel arguments).  uid NULL = identity.  perm (optional) = the rows grouped by unique id
@@ -159,7 +159,7 @@ int b200flow_group_rows(const int32_t* uid, int64_t n_rows, int64_t n_unique, in
  * (tree, block of 1024 uniques) -> blk_cnt[T][n_blocks]. */
 int b200flow_bag_count(const uint32_t* W, int32_t T, int64_t n_unique, int32_t* blk_cnt, void* stream);
 
-/* R6, pass 2: given blk_off = exclusive scan of blk_cnt (int64, tree-major) write the entries; one entry = 8 bytes
+/* R6 (inside fit: kdd99.py:79), pass 2: given blk_off = exclusive scan of blk_cnt (int64, tree-major) write the entries; one entry = 8 bytes
  * {uint32 unique record index, uint32 weight}. */
 int b200flow_bag_fill(const uint32_t* W, int32_t T, int64_t n_unique, const int64_t* blk_off, void* ent, void* stream);
 
@@ -173,14 +173,14 @@ int b200flow_exclusive_scan_i32_to_i64(const int32_t* in, int64_t n, int64_t* ou
  *   slot_node[s]  index of the node in the forest node pool,
  *   seg_begin/seg_end[s]  its bagged entries inside ent (8-byte {record index, weight} pairs).  */
 
-/* per-node feature subsets (RandomForest.selectNodesToSplit): m of F features by a
+/* per-node feature subsets (RandomForest.selectNodesToSplit [MLlib]; inside fit: kdd99.py:79, cicids17.py:83): m of F features by a
  * partial Fisher-Yates keyed by (seed, tree, nid), sorted ascending -> subset[s*m..].
  * m == F gives the identity. */
 int b200flow_feature_subsets(uint64_t seed, int32_t n_slots, const int32_t* slot_tree,
                              const uint32_t* slot_nid, int32_t F, int32_t m,
                              uint16_t* subset, void* stream);
 
-/* R7  findBestSplits/binSeqOp — HOT LOOP A.  hist[s][j][bin][class] += w for every entry
+/* R7  findBestSplits/binSeqOp (ml/tree/impl/RandomForest.scala [MLlib]; inside fit: kdd99.py:79, cicids17.py:83) — HOT LOOP A.  hist[s][j][bin][class] += w for every entry
  * of slot s and every j < m (feature subset[s*m+j]).  hist (uint32) must be zeroed by
  * the caller; layout stride = m * n_bins * C.  chunk_off = exclusive scan over slots of
  * ceil(len/chunk_rows) (int64[n_slots+1]); the grid is one CTA per chunk. */
@@ -250,7 +250,7 @@ int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
                              const int64_t* chunk_off, int64_t n_chunks, int32_t chunk_rows,
                              const b200flow_split* split, int32_t* cursors, void* stream);
 
-/* R7 fused with the row routing: partition_level(L) + hist_level(L+1) in ONE pass — every entry's TreePoint
+/* R7 (inside fit: kdd99.py:79, cicids17.py:83) fused with the row routing: partition_level(L) + hist_level(L+1) in ONE pass — every entry's TreePoint
  * record is gathered once, routed by its parent's split and accumulated into its CHILD's histogram
  * (hist_next[child_slot][j][bin][class], child feature subsets in subset_next, caller zeroes hist_next and
  * cursors).  chunk_off counts chunks of chunk_rows = 512 entries (8 warps x 64) per parent slot; leaf
@@ -288,7 +288,7 @@ int b200flow_finalize_forest(int64_t n_nodes, const uint32_t* pool_counts, int32
                              double* leaf_prob, void* stream);
 
 /* ----------------------------------------------------------------- predict ---
- * R9  RandomForestClassificationModel.transform — HOT LOOP C.  Walks all T trees for every
+ * R9  RandomForestClassificationModel.transform (kdd99.py:82, cicids17.py:86) — HOT LOOP C.  Walks all T trees for every
  * binned row; raw[n][C] = Σ_t leaf_prob (tree order, fp64), prob = raw/Σraw, pred = first argmax.
  * dt_mode != 0 (DecisionTreeClassifier): raw = leaf class counts.  raw/prob may be NULL. */
 int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_rows,
@@ -308,7 +308,7 @@ int b200flow_build_top_nodes(const b200flow_node* nodes, const int32_t* node_tre
  * (b200flow_dedup_rows) back to the rows. */
 int b200flow_gather_rows(const void* src, int32_t row_bytes, const int32_t* idx, int64_t n_rows, void* out, void* stream);
 
-/* R10 MulticlassMetrics: confusion matrix cm[label*C + pred] += 1 (int64, caller zeroes).
+/* R10 MulticlassMetrics (evaluator.evaluate: kdd99.py:86-91, cicids17.py:90-95): confusion matrix cm[label*C + pred] += 1 (int64, caller zeroes).
  * pred / label are fp64 columns (as in the prediction DataFrame). */
 int b200flow_confusion(const double* pred, const double* label, int64_t n_rows, int32_t C,
                        int64_t* cm, void* stream);
