@@ -95,6 +95,28 @@ int b200flow_encode(const void* records, int64_t n_rows, int32_t row_bytes,
                     void* out, int32_t out_dtype, int32_t* label_out, uint8_t* valid_out,
                     void* stream);
 
+/* R2+R3 feeding R4/R5 without the dense matrix (SURVEY.md 8d "Encode -> bins"; the vector VectorAssembler builds at
+ * kdd99.py:45-46 / cicids17.py:41-46 is consumed by RandomForest.run at kdd99.py:79 / cicids17.py:83 only through
+ * findSplits and TreePoint.convertToTreeRDD):
+ * sample_records = b200flow_sample_rows on raw records: the Bernoulli row sample of findSplits, every sampled row
+ * evaluated through the encode plan (F slots) in fp64; round_f32 != 0 rounds each value to float first (the value an
+ * f32 feature matrix would have held).  sample is COLUMN-major [F][cap] fp64 as for sample_rows. */
+int b200flow_sample_records(const void* records, int64_t n_rows, int32_t row_bytes,
+                            const b200flow_slot* plan, int32_t F, const int32_t* lut, int32_t round_f32,
+                            uint64_t seed, uint64_t keep_threshold, int64_t row_offset,
+                            double* sample, int64_t cap, int32_t* n_sampled, void* stream);
+
+/* encode_bins = b200flow_encode + b200flow_bin_rows in one pass: raw records -> uint8 TreePoint records
+ * tp[n_rows][tp_stride] (bin per plan slot, the label's StringIndexer rank at byte F, zero padding), 16-byte words out.
+ * bad (int32[2], caller zeroes): bad[0] += categorical cells outside [0, arity) / non-integral (binned to a value no
+ * left-set contains), bad[1] += NaN numeric cells (when check_nan) + unseen dictionary codes.  label_out optional. */
+int b200flow_encode_bins(const void* records, int64_t n_rows, int32_t row_bytes,
+                         const b200flow_slot* plan, int32_t F, const int32_t* lut, int32_t lut_total,
+                         int32_t label_off, int32_t label_lut_off, int32_t label_lut_len,
+                         int32_t check_nan, int32_t round_f32,
+                         const double* thresholds, const int32_t* n_thr, const int32_t* arity, int32_t max_bins,
+                         uint8_t* tp, int32_t tp_stride, int32_t* label_out, int32_t* bad, void* stream);
+
 /* R3c  StandardScaler.fit (ml/feature/StandardScaler.scala [MLlib]; north_star encode, not called by kdd99.py/cicids17.py): per-column shifted power sums of a dense [n, D] matrix
  * (leading dimension ld elements): sum[d] += Σ(x-shift[d]), sumsq[d] += Σ(x-shift[d])².
  * shift may be NULL (=0).  Two calls (shift = 0, then shift = mean) give the
@@ -253,12 +275,19 @@ int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
 /* R7 (inside fit: kdd99.py:79, cicids17.py:83) fused with the row routing: partition_level(L) + hist_level(L+1) in ONE pass — every entry's TreePoint
  * record is gathered once, routed by its parent's split and accumulated into its CHILD's histogram
  * (hist_next[child_slot][j][bin][class], child feature subsets in subset_next, caller zeroes hist_next and
- * cursors).  chunk_off counts chunks of chunk_rows = 512 entries (8 warps x 64) per parent slot; leaf
- * parents must have 0 chunks.  The kernel is persistent (148 x k CTAs); each warp gathers the records of
- * its 64 entries with asynchronous copies into a private shared-memory tile and there is no CTA barrier
- * except when the parent slot changes.  b200flow_route_hist_fits() tells whether the shapes fit shared memory; when
- * they do not, use partition_level followed by hist_level. */
-int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows);
+ * cursors).  The kernel is persistent (148 x k CTAs); each warp gathers the records of its entries with
+ * asynchronous copies into a private shared-memory tile and there is no CTA barrier except when the parent slot
+ * changes.
+ * b200flow_route_hist_config() picks the launch shape for a level shape (host-only, no device needed): it returns
+ * 1 and writes chunk_rows (entries per routing chunk = warps x entries per warp step; pass it to plan_route and to
+ * route_hist_level) and m_pass (subset features whose two child histograms share shared memory; m_pass < m means
+ * ceil(m / m_pass) feature passes over the entries, only the first of which routes — DecisionTree nodes, whose
+ * histograms cover every feature), or returns 0 when even one feature's pair of child histograms does not fit
+ * (then use partition_level followed by hist_level).
+ * flags bit 0: route — write the kept entries to ent_out and count them in cursors; without it only the child
+ * histograms are built (ent_out / cursors may be NULL): the level-0 pass, whose segments do not change, and the
+ * pass that builds the deepest scored level, whose entries are never read again. */
+int b200flow_route_hist_config(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t* chunk_rows, int32_t* m_pass);
 int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
                               const void* ent, void* ent_out,
                               int32_t n_slots, const int64_t* seg_begin, const int64_t* seg_end,
@@ -268,7 +297,7 @@ int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
                               const b200flow_split* split, const int32_t* child_slot, int32_t* cursors,
                               void* chunk_scratch /* 16 bytes per chunk (n_chunks_max), 16-byte aligned */,
                               const uint16_t* subset_next, int32_t m, int32_t n_bins, int32_t C,
-                              uint32_t* hist_next, void* stream);
+                              uint32_t* hist_next, int32_t flags, void* stream);
 
 /* routing plan of a scored level: n_chunks[s] = ceil(len(s) / chunk_rows) for a split parent with at least one non-leaf
  * child, else 0 (its exclusive scan is route_hist_level's chunk_off); also scatters split[s].gain into node_gain[slot_node[s]]

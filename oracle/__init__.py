@@ -48,6 +48,15 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n=None):
+    """use n OpenMP threads (default: every core this process may run on), whatever OMP_NUM_THREADS says —
+    torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def philox(seed, purpose, c0, c1=0, c2=0, c3=0):
     out = np.zeros(4, np.uint32)
     lib().orc_philox(C.c_uint64(seed), C.c_uint32(purpose), C.c_uint32(c0), C.c_uint32(c1),

@@ -264,6 +264,15 @@ void orc_philox(uint64_t seed, uint32_t purpose, uint32_t c0, uint32_t c1, uint3
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
 }
 
+// explicit thread count: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently serialise the CPU arm
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -381,7 +390,7 @@ void orc_bin_rows(const double* x, int64_t n, int32_t F, const double* threshold
             double v = x[i * F + f];
             if (arity[f] > 0) {
                 int b = (int)v;
-                if (!((double)b == v) || b < 0 || b >= arity[f]) { rowbad = true; b = 0; }
+                if (!((double)b == v) || b < 0 || b >= arity[f]) { rowbad = true; b = arity[f] < 255 ? arity[f] : 255; }   // not in any left set: goes right (Node.scala CategoricalSplit.shouldGoLeft)
                 r[f] = (uint8_t)b;
             } else {
                 const double* thr = thresholds + (size_t)f * (max_bins - 1);

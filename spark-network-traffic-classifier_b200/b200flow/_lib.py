@@ -27,6 +27,11 @@ class B200FlowError(RuntimeError):
     pass
 
 
+class UnsupportedParamError(B200FlowError, ValueError):
+    """a parameter value MLlib accepts but the B200 path does not implement (entropy impurity, maxBins > 256, ...): a
+    ValueError, so the pyspark shim reports it as IllegalArgumentException; CUDA/runtime failures stay B200FlowError."""
+
+
 _P, _I32, _I64, _U64, _F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
 
 # name -> argtypes, exactly the prototypes of include/b200flow.h
@@ -34,6 +39,8 @@ _SIGNATURES = {
     "b200flow_category_counts": [_P, _I64, _I32, _I32, _I32, _P, _P],
     "b200flow_category_counts_multi": [_P, _I64, _I32, _I32, _P, _P, _P, _P],
     "b200flow_encode": [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P],
+    "b200flow_sample_records": [_P, _I64, _I32, _P, _I32, _P, _I32, _U64, _U64, _I64, _P, _I64, _P, _P],
+    "b200flow_encode_bins": [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _I32, _P, _P, _P],
     "b200flow_column_moments": [_P, _I32, _I64, _I32, _I64, _P, _P, _P, _P],
     "b200flow_sample_rows": [_P, _I32, _I64, _I32, _I64, _U64, _U64, _I64, _P, _I64, _P, _P],
     "b200flow_find_splits": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P],
@@ -49,7 +56,7 @@ _SIGNATURES = {
     "b200flow_score_level": [_P, _I32, _P, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _F64, _P, _P, _P, _P, _P],
     "b200flow_grow_level": [_I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P],
     "b200flow_route_hist_level": [_P, _I32, _I32, _P, _P, _I32, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _I32, _I32,
-                                  _I32, _P, _P],
+                                  _I32, _P, _I32, _P],
     "b200flow_partition_level": [_P, _I32, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P],
     "b200flow_plan_route": [_I32, _P, _P, _P, _I32, _P, _P, _P, _P],
     "b200flow_next_segments": [_I32, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -61,7 +68,7 @@ _SIGNATURES = {
     "b200flow_random_split": [_U64, _I64, _I64, _P, _I32, _P, _P],
     "b200flow_compact_rows": [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version", "b200flow_route_hist_fits"])
+EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version", "b200flow_route_hist_config"])
 
 _lib = None
 launches = 0   # kernels of OURS launched so far (counted per C-ABI call); bench.py reads the delta over the timed region
@@ -83,10 +90,17 @@ def load():
             fn.restype = C.c_int
         lib.b200flow_last_error.restype = C.c_char_p
         lib.b200flow_version.restype = C.c_int
-        lib.b200flow_route_hist_fits.argtypes = [_I32] * 5
-        lib.b200flow_route_hist_fits.restype = C.c_int
+        lib.b200flow_route_hist_config.argtypes = [_I32] * 4 + [C.POINTER(_I32), C.POINTER(_I32)]
+        lib.b200flow_route_hist_config.restype = C.c_int
         _lib = lib
     return _lib
+
+
+def route_hist_config(F, m, n_bins, n_classes):
+    """launch shape of the fused route + histogram kernel: (chunk_rows, m_pass) or None when it cannot run (host-only call)."""
+    ch, mp = _I32(0), _I32(0)
+    ok = load().b200flow_route_hist_config(int(F), int(m), int(n_bins), int(n_classes), C.byref(ch), C.byref(mp))
+    return (int(ch.value), int(mp.value)) if ok else None
 
 
 def ptr(t):

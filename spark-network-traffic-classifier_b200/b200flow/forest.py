@@ -16,11 +16,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import NODE_DTYPE, SPLIT_DTYPE, B200FlowError, call, ptr
+from ._lib import NODE_DTYPE, SPLIT_DTYPE, B200FlowError, UnsupportedParamError, call, ptr
 
 CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_level (<= 2048)
 import os as _os
-ROUTE_CHUNK_ROWS = int(_os.environ.get("B200FLOW_ROUTE_CHUNK", "512"))   # entries per CTA in the fused route_hist_level kernel
 FUSED = True                       # use route_hist_level (partition + next-level histogram in one pass) when it fits
 TOP_LEVELS = int(_os.environ.get("B200FLOW_TOP_LEVELS", "8"))   # tree levels the predict kernel walks in shared memory (0 = none)
 DEDUP = True                       # run the level loop on unique binned records (flow records repeat massively)
@@ -83,7 +82,7 @@ def poisson_cdf_table(rate=1.0):
         out[k] = min(int(math.floor(cdf * 4294967296.0)), 0xFFFFFFFF)
         term = term * rate / (k + 1)
     if out[30] != 0xFFFFFFFF:
-        raise B200FlowError("subsamplingRate %.3f too large: bag weights must stay below 31" % rate)
+        raise UnsupportedParamError("subsamplingRate %.3f too large: bag weights must stay below 31" % rate)
     return out
 
 
@@ -92,7 +91,7 @@ def build_metadata(n_rows, F, num_classes, arity, max_bins, num_trees, strategy=
     arity = np.asarray(arity, np.int32)
     mpb = int(min(max_bins, n_rows))
     if mpb > 256:
-        raise B200FlowError("maxBins > 256 is not supported (bins are stored as uint8)")
+        raise UnsupportedParamError("maxBins > 256 is not supported (bins are stored as uint8)")
     if arity.size and int(arity.max()) > mpb:
         raise ValueError("DecisionTree requires maxBins (= %d) to be at least as large as the number of values in each "
                          "categorical feature, but a categorical feature has %d values. Consider removing this and other "
@@ -146,6 +145,63 @@ def _i32(a, dev):
     return _lib.h2d(np.ascontiguousarray(a, np.int32), dev)
 
 
+class InvalidRowsError(ValueError):
+    """NaN / null numeric cells or unseen dictionary codes met while assembling rows (VectorAssembler / StringIndexerModel
+    handleInvalid="error"); raised when the fused record path meets them — Spark raises at the same point: the action."""
+
+
+class _DenseSource:
+    """training / test rows as a dense CUDA feature matrix x [n, F] (f32/f64) + int32 labels: the materialised
+    VectorAssembler output (kdd99.py:46)."""
+
+    def __init__(self, x, labels=None):
+        self.x, self.labels = x, (labels.to(torch.int32).contiguous() if labels is not None else None)
+        self.n, self.F = x.shape
+        self.device = x.device
+
+    def sample(self, seed, keep, row_offset, sample, cap, n_s_dev):
+        call("b200flow_sample_rows", ptr(self.x), _lib.dtype_code(self.x), self.n, self.F, self.x.stride(0), seed, keep, int(row_offset),
+             ptr(sample), cap, ptr(n_s_dev))
+
+    def bin(self, thresholds, n_thr, arity_dev, mpb, bad, want_label_out=False):
+        stride = tp_stride(self.F)
+        tp = torch.empty((self.n, stride), dtype=torch.uint8, device=self.device)
+        _timed("bin_rows", "b200flow_bin_rows", ptr(self.x), _lib.dtype_code(self.x), self.n, self.F, self.x.stride(0), ptr(thresholds), ptr(n_thr),
+               ptr(arity_dev), mpb, ptr(self.labels), ptr(tp), stride, ptr(bad[0:1]))
+        return tp, self.labels
+
+
+class _RecordSource:
+    """rows as raw AoS flow records + the encode plan that would assemble their feature vector: sampled and binned
+    straight from the records by the fused kernels (SURVEY.md 8d "Encode -> bins"), the dense matrix never exists.
+    round_f32: the plan's vector would have been an f32 matrix (only matters for scaled slots, whose f32 rounding the
+    bins must see)."""
+
+    def __init__(self, rec, plan, round_f32=False, with_label=True):
+        if rec.dtype != torch.uint8 or rec.dim() != 2 or rec.shape[1] != plan.schema.row_bytes:
+            raise ValueError("records must be uint8 [n, %d]" % plan.schema.row_bytes)
+        self.rec, self.plan, self.round_f32 = rec, plan, 1 if round_f32 else 0
+        self.n, self.F = rec.shape[0], plan.n_out
+        self.device = rec.device
+        self.with_label = with_label and plan.label is not None
+
+    def sample(self, seed, keep, row_offset, sample, cap, n_s_dev):
+        _, slots, lut_t, _ = self.plan._device_tables(self.device)
+        call("b200flow_sample_records", ptr(self.rec), self.n, self.plan.schema.row_bytes, ptr(slots), self.F, ptr(lut_t), self.round_f32,
+             seed, keep, int(row_offset), ptr(sample), cap, ptr(n_s_dev))
+
+    def bin(self, thresholds, n_thr, arity_dev, mpb, bad, want_label_out=False):
+        _, slots, lut_t, lut_total = self.plan._device_tables(self.device)
+        stride = tp_stride(self.F)
+        tp = torch.empty((self.n, stride), dtype=torch.uint8, device=self.device)
+        loff, llo, lln = self.plan.label if self.with_label else (-1, 0, 0)
+        lab = torch.empty(self.n, dtype=torch.int32, device=self.device) if (want_label_out and self.with_label) else None
+        _timed("encode_bins", "b200flow_encode_bins", ptr(self.rec), self.n, self.plan.schema.row_bytes, ptr(slots), self.F, ptr(lut_t), lut_total,
+               loff, llo, lln, int(self.plan.check_nan), self.round_f32, ptr(thresholds), ptr(n_thr), ptr(arity_dev), mpb, ptr(tp), stride,
+               ptr(lab), ptr(bad))
+        return tp, lab
+
+
 class ForestModel:
     """Device-resident forest: one node pool for all trees (roots = nodes 0..T-1)."""
 
@@ -163,12 +219,9 @@ class ForestModel:
         n, F = x.shape
         if F != self.F:
             raise ValueError("expected %d features, got %d" % (self.F, F))
-        stride = tp_stride(F)
-        tp = torch.empty((n, stride), dtype=torch.uint8, device=x.device)
-        bad = torch.zeros(1, dtype=torch.int32, device=x.device)
-        call("b200flow_bin_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), ptr(self.thresholds), ptr(self.n_thr),
-             ptr(self._arity_dev), self.max_bins, ptr(labels), ptr(tp), stride, ptr(bad))
-        return tp, bad
+        bad = torch.zeros(2, dtype=torch.int32, device=x.device)
+        tp, _ = _DenseSource(x, labels).bin(self.thresholds, self.n_thr, self._arity_dev, self.max_bins, bad)
+        return tp, bad[0:1]
 
     def _top_table(self):
         """the first TOP_LEVELS levels of every tree, heap-indexed by node id, for the predict kernel's shared-memory stage
@@ -193,13 +246,35 @@ class ForestModel:
 
     def predict(self, x, want_raw=True, want_prob=True):
         """RandomForestClassificationModel.transform (R9): rawPrediction, probability, prediction.  The trees are walked
-        once per UNIQUE binned record; the results are then spread back to the rows."""
+        once per UNIQUE binned record; the results are then spread back to the rows.  A categorical value outside
+        [0, arity) is binned to a value no left-set contains, so it goes right at every split on that feature — what
+        MLlib's CategoricalSplit.shouldGoLeft does with an unseen category."""
         tp, _ = self.bin(x)
+        return self._predict_tp(tp, want_raw, want_prob)
+
+    def predict_records(self, rec, plan, want_raw=True, want_prob=True, round_f32=False, want_label=False, on_invalid="ignore"):
+        """the same from raw flow records + the encode plan of the feature vector (fused encode -> bins, no dense matrix).
+        -> (raw, prob, pred, label int32 | None).  on_invalid="error": NaN cells (plan.check_nan) / unseen codes raise."""
+        src = _RecordSource(rec, plan, round_f32, with_label=want_label)
+        if src.F != self.F:
+            raise ValueError("expected %d features, got %d" % (self.F, src.F))
+        bad = torch.zeros(2, dtype=torch.int32, device=rec.device)
+        tp, lab = src.bin(self.thresholds, self.n_thr, self._arity_dev, self.max_bins, bad, want_label_out=want_label)
+        out = self._predict_tp(tp, want_raw, want_prob, bad if on_invalid == "error" else None)
+        return out + (lab,)
+
+    def _predict_tp(self, tp, want_raw=True, want_prob=True, bad=None):
         n = tp.shape[0]
         if not DEDUP or n == 0:
+            if bad is not None and int(bad[1].item()):
+                raise InvalidRowsError("%d NaN/null cells or unseen labels in the rows to transform" % int(bad[1].item()))
             return self.predict_binned(tp, want_raw, want_prob)
-        tpu, uid, U = dedup_rows(tp, self.F)                 # the label byte is not part of a test record's identity
-        raw_u, prob_u, pred_u = self.predict_binned(tpu, want_raw, want_prob)
+        tpu, uid, u_dev = dedup_rows(tp, self.F, sync=False)  # the label byte is not part of a test record's identity
+        head = (torch.cat([u_dev, bad.to(torch.int64)]) if bad is not None else u_dev).cpu()    # ONE host read
+        if bad is not None and int(head[2]):
+            raise InvalidRowsError("%d NaN/null cells or unseen labels in the rows to transform" % int(head[2]))
+        U = int(head[0])
+        raw_u, prob_u, pred_u = self.predict_binned(tpu[:U], want_raw, want_prob)
 
         def spread(src, width):
             if src is None:
@@ -242,14 +317,17 @@ class ForestModel:
 
 
 def _gather_sample(sample, n_s, cap, F, group):
-    """all-gather the per-rank findSplits samples (column-major [F, cap]) into one buffer."""
+    """all-gather the per-rank findSplits samples (column-major [F, cap]) into one buffer.  The ranks agree on the widest
+    sample first and exchange (F, mx) blocks padded to that width — local capacities differ when the shards are uneven."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     counts = [torch.zeros(1, dtype=torch.int64, device=sample.device) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([n_s], dtype=torch.int64, device=sample.device), group=group)
     counts = [int(c.item()) for c in counts]
     mx = max(max(counts), 1)
-    mine = sample.view(F, cap)[:, :mx].contiguous()
+    mine = torch.zeros((F, mx), dtype=torch.float64, device=sample.device)
+    if n_s > 0:
+        mine[:, :n_s] = sample.view(F, cap)[:, :n_s]
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
     tot = sum(counts)
@@ -269,16 +347,30 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     arity[f] = 0 for a continuous feature, else the number of categories (from the StringIndexer's
     nominal metadata).  With `group`, x/labels are this rank's row shard starting at
     global row `row_offset`.  Returns a ForestModel."""
+    return _fit(_DenseSource(x, labels), num_classes, arity, params, row_offset, group)
+
+
+def fit_forest_records(rec, plan, num_classes, arity, params, row_offset=0, group=None, round_f32=False):
+    """the same on raw flow records [n, row_bytes] + the encode plan of their feature vector (plan.label = the label
+    column): findSplits samples and TreePoint bins come straight from the records (fused encode -> bins)."""
+    if plan.label is None:
+        raise ValueError("fit_forest_records: the encode plan has no label column (EncodePlan.set_label)")
+    return _fit(_RecordSource(rec, plan, round_f32), num_classes, arity, params, row_offset, group)
+
+
+def _fit(src, num_classes, arity, params, row_offset=0, group=None):
     import torch.distributed as dist
     _lib.require_cuda()
     p = params
     if p.impurity != "gini":
-        raise B200FlowError("impurity=%r: only 'gini' is implemented on the B200 path" % p.impurity)
+        raise UnsupportedParamError("impurity=%r: only 'gini' is implemented on the B200 path" % p.impurity)
     if not (0 <= p.max_depth <= 30):
         raise ValueError("maxDepth must be in [0, 30], got %d" % p.max_depth)
-    dev = x.device
-    n, F = x.shape
+    dev = src.device
+    n, F = src.n, src.F
     C = int(num_classes)
+    if not (1 <= C <= 256):
+        raise ValueError("numClasses must be in [1, 256] (labels are stored as one byte), got %d" % C)
     T = int(p.num_trees)
     seed = int(p.seed) & 0xFFFFFFFFFFFFFFFF
     n_global = n
@@ -289,11 +381,10 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     mpb, kind, m = build_metadata(n_global, F, C, arity, p.max_bins, T, p.feature_subset_strategy)
     arity = np.asarray(arity, np.int32)
     arity_dev = _i32(arity, dev)
-    labels = labels.to(torch.int32).contiguous()
 
     # ---- R4 findSplits: Bernoulli row sample keyed by global row, sort + stride walk on device
     has_cont = bool((arity == 0).any())
-    frac = min(1.0, max(mpb * mpb, 10000) / float(n_global)) if has_cont else 1.0
+    frac = min(1.0, max(mpb * mpb, 10000) / float(max(n_global, 1))) if has_cont else 1.0
     keep = int(frac * 4294967296.0)
     expect = n if frac >= 1.0 else int(n * frac + 6.0 * math.sqrt(max(n * frac, 1.0)) + 64)
     cap = 1
@@ -304,8 +395,7 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     thresholds = torch.zeros((F, mpb - 1), dtype=torch.float64, device=dev)
     n_thr = torch.zeros(F, dtype=torch.int32, device=dev)
     if has_cont:
-        call("b200flow_sample_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), seed, keep, int(row_offset),
-             ptr(sample), cap, ptr(n_s_dev))
+        src.sample(seed, keep, row_offset, sample, cap, n_s_dev)
         if group is not None:
             n_s = int(n_s_dev.item())
             if n_s > cap:
@@ -316,16 +406,14 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
             call("b200flow_find_splits", ptr(sample), cap, cap, F, ptr(arity_dev), mpb, ptr(thresholds), ptr(n_thr), ptr(n_s_dev))
     del sample
 
-    # ---- R5 binning
+    # ---- R5 binning (dense matrix: bin_rows; raw records: the fused encode -> bins kernel)
     stride = tp_stride(F)
-    tp = torch.empty((n, stride), dtype=torch.uint8, device=dev)
-    bad = torch.zeros(1, dtype=torch.int32, device=dev)
-    _timed("bin_rows", "b200flow_bin_rows", ptr(x), _lib.dtype_code(x), n, F, x.stride(0), ptr(thresholds), ptr(n_thr),
-           ptr(arity_dev), mpb, ptr(labels), ptr(tp), stride, ptr(bad))
+    bad = torch.zeros(2, dtype=torch.int32, device=dev)
+    tp, _ = src.bin(thresholds, n_thr, arity_dev, mpb, bad)
     feat_bins = torch.where(arity_dev > 0, arity_dev, n_thr + 1).to(torch.int32).contiguous()
     feat_kind = _i32(kind, dev)
     # ---- de-duplicate the binned rows: the level loop runs on UNIQUE TreePoint records carrying summed bag weights.
-    # Everything is enqueued first; ONE host read then fetches the bad-cell count, the bin count, the sample count and U.
+    # Everything is enqueued first; ONE host read then fetches the bad-cell counts, the bin count, the sample count and U.
     total = torch.zeros(1, dtype=torch.int64, device=dev)
     dedup = n > 0 and DEDUP
     if dedup:
@@ -333,11 +421,13 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     else:
         uid, u_dev = None, torch.full((1,), n, dtype=torch.int64, device=dev)
     head = torch.cat([bad.to(torch.int64), feat_bins.max().reshape(1).to(torch.int64), n_s_dev.to(torch.int64), u_dev]).cpu()
+    if int(head[1]) != 0:
+        raise InvalidRowsError("%d NaN/null cells or unseen labels in the training rows" % int(head[1]))
     if int(head[0]) != 0:
         raise ValueError("categorical feature value outside [0, arity) or non-integral in %d cells" % int(head[0]))
-    if has_cont and group is None and int(head[2]) > cap:
-        raise B200FlowError("findSplits sample overflow (%d > %d)" % (int(head[2]), cap))
-    n_bins, U = int(head[1]), int(head[3])
+    if has_cont and group is None and int(head[3]) > cap:
+        raise B200FlowError("findSplits sample overflow (%d > %d)" % (int(head[3]), cap))
+    n_bins, U = int(head[2]), int(head[4])
     if dedup:
         tp = tp[:U]
     # ---- R6 bagging: W[tree][unique] = summed Poisson weights; entries = non-zero (unique, weight) pairs per tree
@@ -410,11 +500,14 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
     group_slots = max(1, HIST_BUDGET_BYTES // per_slot_hist)
     stats = dict(levels=0, slots=0, entries=E, hist_launches=0, rows=n, unique_rows=U)
 
-    route_ch = ROUTE_CHUNK_ROWS
-    while route_ch > 128 and not _lib.load().b200flow_route_hist_fits(F, m, n_bins, C, route_ch):
-        route_ch //= 2
-    fused = FUSED and bool(_lib.load().b200flow_route_hist_fits(F, m, n_bins, C, route_ch))
+    # launch shape of the fused kernel: entries per routing chunk and subset features per pass (wide nodes — many classes,
+    # or a DecisionTree's all-feature histograms — are accumulated in several feature passes, the first of which routes)
+    cfg = _lib.route_hist_config(F, m, n_bins, C) if FUSED else None
+    fused = cfg is not None
+    route_ch, m_pass = cfg if fused else (CHUNK_ROWS, m)
+    route_passes = -(-m // m_pass)
     hsz = m * n_bins * C
+    stats["route_chunk"], stats["route_passes"] = route_ch if fused else 0, route_passes if fused else 0
 
     def chunk_table(nch):
         off = torch.empty(nch.shape[0] + 1, dtype=torch.int64, device=dev)
@@ -463,24 +556,26 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
             dst.view(-1)[:world * per * width].view(world, per * width).copy_(gathered[:, o:o + per * width])
             o += per * width
 
-    def run_route(roff, rch_dev, n_parents, split_, child_slot_, cursors_, next_subset_, n_next_cap):
+    def run_route(roff, rch_dev, n_parents, split_, child_slot_, cursors_, next_subset_, n_next_cap, route=True):
         """fused pass: route the entries of the planned parent slots to their children and build the children's histograms
         (returns the zero-initialised, now filled, histogram buffer of the next level).  The chunk count stays on the device
-        (rch_dev), so the pass can be enqueued before the host knows how many children were created."""
+        (rch_dev), so the pass can be enqueued before the host knows how many children were created.  route=False builds
+        the histograms only (level 0, whose segments do not change; the deepest scored level, whose entries nobody reads)."""
         hist_next = torch.zeros((n_next_cap + world - 1) * hsz, dtype=torch.int32, device=dev)   # + padding for the node-block scatter
         cmax = route_chunks_max + n_parents
         scratch = torch.empty(cmax * 4, dtype=torch.int32, device=dev)
         _timed("route_hist_level", "b200flow_route_hist_level", ptr(tp), stride, F, ptr(ent), ptr(ent2), n_parents,
                ptr(seg_begin), ptr(seg_end), ptr(roff), ptr(rch_dev), cmax, route_ch, ptr(split_), ptr(child_slot_), ptr(cursors_),
-               ptr(scratch), ptr(next_subset_), m, n_bins, C, ptr(hist_next))
-        stats["hist_launches"] += 1
+               ptr(scratch), ptr(next_subset_), m, n_bins, C, ptr(hist_next), 1 if route else 0)
+        _lib.launches += route_passes - 1
+        stats["hist_launches"] += route_passes
         return hist_next
 
     side_stream = torch.cuda.Stream(device=dev)
     host_cnt = torch.empty(5, dtype=torch.int64).pin_memory() if _PIN else None
     subset = level_subsets(n_slots, slot_tree, slot_nid)
     hist_ready = None                  # histogram of the CURRENT level when the fused kernel already built it
-    if fused and n_slots * hsz * 4 <= HIST_BUDGET_BYTES and E > 0:
+    if fused and n_slots * hsz * 4 <= HIST_BUDGET_BYTES:        # (not on E: every rank must take the same collective path)
         # level 0 through the same kernel: T pseudo-parents whose split sends every entry "left" into the tree's root
         pseudo = np.zeros(T, SPLIT_DTYPE); pseudo["bin_thr"] = 255; pseudo["flags"] = 4
         pseudo_t = _lib.h2d(pseudo.view(np.uint8).reshape(T, 64), dev)
@@ -488,9 +583,8 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                               torch.full((T,), -1, dtype=torch.int32, device=dev)], 1).contiguous().view(-1)
         cursors0 = torch.zeros(2 * T, dtype=torch.int32, device=dev)
         roff0 = plan_route(T, pseudo_t, seg_begin, seg_end, total)
-        hist_full = run_route(roff0, total, T, pseudo_t, child0, cursors0, subset, T)
+        hist_full = run_route(roff0, total, T, pseudo_t, child0, cursors0, subset, T, route=False)
         hist_ready = hist_full[:T * hsz]
-        ent, ent2 = ent2, ent          # the pass copied every entry into the other buffer, same segments
     while n_slots > 0:
         grow_pool(pool_size + 2 * n_slots)
         lens = (seg_end - seg_begin) if hist_ready is None else None   # only the unfused kernels need the lengths on the host side
@@ -548,7 +642,8 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                ptr(left_counts), ptr(right_counts), C, ptr(nodes), ptr(node_mask), ptr(pool_counts), ptr(node_tree),
                cap_nodes, ptr(next_tree), ptr(next_nid), ptr(next_node), ptr(next_parent), ptr(child_slot), ptr(counters))
         n_cap = 2 * n_slots                              # upper bound on the number of next-level slots
-        speculative = fused and n_cap * hsz * 4 <= HIST_BUDGET_BYTES
+        # (the deepest level has only leaf children: nothing to route, nothing to enqueue ahead)
+        speculative = fused and n_cap * hsz * 4 <= HIST_BUDGET_BYTES and level + 1 < p.max_depth
         if not speculative:
             node_gain[slot_node.long()] = split.view(torch.float64)[:, 2]
         if speculative:
@@ -562,7 +657,9 @@ def fit_forest(x, labels, num_classes, arity, params, row_offset=0, group=None):
                 ev_read = torch.cuda.Event(); ev_read.record(side_stream)
             next_subset = level_subsets(n_cap, next_tree, next_nid)
             cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
-            hist_next = run_route(roff, counters[4:5], n_slots, split, child_slot, cursors, next_subset, n_cap)
+            # children at level + 1 == maxDepth - 1 are scored but never split further into routed nodes: their entries are not written
+            hist_next = run_route(roff, counters[4:5], n_slots, split, child_slot, cursors, next_subset, n_cap,
+                                  route=level + 2 < p.max_depth)
             next_begin = torch.empty(n_cap, dtype=torch.int64, device=dev)
             next_end = torch.empty(n_cap, dtype=torch.int64, device=dev)
             call("b200flow_next_segments", n_cap, ptr(counters[1:2]), ptr(next_parent), ptr(seg_begin), ptr(seg_end), ptr(cursors),

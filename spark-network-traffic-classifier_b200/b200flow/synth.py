@@ -126,32 +126,39 @@ CICIDS_LABELS = ["BENIGN", "DoS Hulk", "PortScan", "DDoS", "DoS GoldenEye", "FTP
 CICIDS_COUNTS = [2273097, 231073, 158930, 128027, 10293, 7938, 5897, 5796, 5499, 1966, 1507, 652, 36, 21, 11]
 
 
-def cicids_schema(n_features=78):
-    return RecordSchema([("f%02d" % i, "f32") for i in range(n_features)] + [("Label", "code")])
+def cicids_schema(n_features=78, dtype="f32"):
+    """dtype="f64": the layout Spark's inferSchema gives the CICIDS2017 CSVs (cicids17.py:19-20 -> DoubleType columns):
+    78 x 8 + 4 = 628 B per record."""
+    return RecordSchema([("f%02d" % i, dtype) for i in range(n_features)] + [("Label", "code")])
 
 
-def make_cicids(n, n_classes=15, seed=2019, device="cpu", label_noise=0.01, nan_fraction=0.0, n_features=78):
-    """-> (records uint8 [n, 4*n_features+4], dictionaries {"Label": [...]}).  Mix of integer counters, µs durations,
-    many-digit rates, 8 constant-zero columns; optional NaN in two rate columns (handleInvalid='skip')."""
+def make_cicids(n, n_classes=15, seed=2019, device="cpu", label_noise=0.01, nan_fraction=0.0, n_features=78, dtype="f32",
+                row_offset=0):
+    """-> (records uint8 [n, row_bytes], dictionaries {"Label": [...]}).  Mix of integer counters, µs durations,
+    many-digit rates, 8 constant-zero columns; optional NaN in two rate columns (handleInvalid='skip').  dtype="f64" keeps
+    the rate columns' full double precision (more than 7 significant digits: an f32 copy of the same record can land on the
+    other side of a split threshold)."""
     dev = torch.device(device)
-    g = torch.Generator(device=dev); g.manual_seed(int(seed))
+    g = torch.Generator(device=dev); g.manual_seed(int(seed) + 7919 * int(row_offset))
     pg = np.random.default_rng(54321)
     L = n_classes
+    real = torch.float64 if dtype == "f64" else torch.float32
     pri = np.asarray(CICIDS_COUNTS[:L], np.float64); pri /= pri.sum()
     z = torch.multinomial(torch.tensor(pri, device=dev), n, replacement=True, generator=g)
     flip = torch.rand(n, device=dev, generator=g) < label_noise
     y = torch.where(flip, torch.randint(0, L, (n,), device=dev, generator=g), z)
-    loc = torch.tensor(pg.uniform(0.0, 1.0, (L, n_features)), device=dev, dtype=torch.float32)
+    loc = torch.tensor(pg.uniform(0.0, 1.0, (L, n_features)), device=dev, dtype=real)
     informative = set(pg.choice(n_features, min(14, n_features // 2), replace=False).tolist())
     zero_cols = set(pg.choice([i for i in range(n_features) if i not in informative], min(8, n_features // 5), replace=False).tolist())
-    schema = cicids_schema(n_features)
+    schema = cicids_schema(n_features, dtype)
     rec = torch.empty((n, schema.row_bytes), dtype=torch.uint8, device=dev)
     rec32 = rec.view(torch.int32)
+    wpf = 2 if dtype == "f64" else 1                                          # 32-bit words per feature field
     for j in range(n_features):
-        u = torch.rand(n, device=dev, generator=g)
-        m = loc[:, j][z] if j in informative else torch.full((n,), 0.5, device=dev)
+        u = torch.rand(n, device=dev, generator=g, dtype=real)
+        m = loc[:, j][z] if j in informative else torch.full((n,), 0.5, device=dev, dtype=real)
         if j in zero_cols:
-            v = torch.zeros(n, device=dev)
+            v = torch.zeros(n, device=dev, dtype=real)
         elif j % 3 == 0:
             v = torch.floor(torch.exp(u * (3.0 + 15.0 * m)))                  # counters / µs durations up to ~1e8
         elif j % 3 == 1:
@@ -160,8 +167,11 @@ def make_cicids(n, n_classes=15, seed=2019, device="cpu", label_noise=0.01, nan_
             v = torch.floor(u * (40.0 * m + 2.0))
         if nan_fraction > 0 and j in (14, 15):
             v = torch.where(torch.rand(n, device=dev, generator=g) < nan_fraction, torch.full_like(v, float("nan")), v)
-        rec32[:, j] = v.to(torch.float32).view(torch.int32)
+        if dtype == "f64":
+            rec32[:, 2 * j:2 * j + 2] = v.to(torch.float64).view(torch.int32).reshape(n, 2)
+        else:
+            rec32[:, j] = v.to(torch.float32).view(torch.int32)
     scramble = pg.permutation(L)
-    rec32[:, n_features] = torch.tensor(scramble, device=dev, dtype=torch.int32)[y]
+    rec32[:, wpf * n_features] = torch.tensor(scramble, device=dev, dtype=torch.int32)[y]
     names = CICIDS_LABELS[:L]
     return rec, {"Label": [names[np.argsort(scramble)[c]] for c in range(L)]}

@@ -177,40 +177,9 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
     const int dstep = fixed ? n_out : bd;
     const bool active = fixed ? (tid < rp * n_out) : true;
 
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % kEncStages, o = it % kEncOutBufs, ob = it & 1;
-        const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
-        const int64_t row_base = tile * R;
-        const int rows = (int)min((int64_t)R, a.n_rows - row_base);
-        const bool full = rows == R;
-        uint8_t* in_t = in_base + (size_t)s * a.in_stride;
-        OUT* out_t = (OUT*)(out_base + (size_t)o * a.out_stride);
-        int32_t* bad = badtag + ob * R;
-        const int tag = it + 1;
-
-        mbar_wait(&mbar[s], ph);
-        if (!full) {
-            const uint32_t* src = (const uint32_t*)(a.records + row_base * row_bytes);
-            for (int i = tid; i < rows * row_bytes / 4; i += bd) ((uint32_t*)in_t)[i] = __ldg(src + i);
-            __syncthreads();
-        }
-
-        if (nsrc > 0) {
-            for (int idx = tid; idx < rows * nsrc; idx += bd) {
-                const int r = idx / nsrc, c = idx - r * nsrc;
-                const int code = *(const int32_t*)(in_t + r * row_bytes + cat_tab[c]);
-                const int rank = (code >= 0 && code < cat_tab[2 * (kEncMaxCat + 1) + c]) ? lut[cat_tab[(kEncMaxCat + 1) + c] + code] : -1;
-                if (rank < 0) bad[r] = tag;
-                if (c < ncat) rank_sh[r * kEncMaxCat + c] = rank;
-                else if (a.label_out) a.label_out[row_base + r] = rank;
-            }
-            if (ncat > 0) __syncthreads();          // ranks visible to the slot loops (label-only: nothing to wait for)
-        }
-        if (active) {
-            // one tight loop per source kind: the slot (and so the kind) is fixed per thread, rows are strided by rp
-            for (int d = d0; d < n_out; d += dstep) {
-                const b200flow_slot sl = plan_sh[d];
+    // one tight loop per source kind: the slot (and so the kind) is fixed per thread, rows are strided by rp
+    auto do_slot = [&](const b200flow_slot& sl, const int cat, const int d, const uint8_t* in_t, OUT* out_t, int32_t* bad, const int tag,
+                       const int rows) {
                 const uint8_t* p = in_t + r0 * row_bytes + sl.src_off;
                 OUT* op = out_t + r0 * n_out + d;
                 const int pstep = rp * row_bytes, ostep = rp * n_out;
@@ -245,7 +214,6 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
                 } else {
                     const bool index = sl.kind == B200FLOW_SRC_INDEX;
                     const OUT hot = (OUT)((1.0 - mean) * scale), cold = (OUT)((0.0 - mean) * scale);
-                    const int cat = slot_cat[d];
                     if (cat >= 0) {                  // rank looked up once per (row, source) by the pre-pass
                         const int32_t* rk = rank_sh + r0 * kEncMaxCat + cat;
                         const int rstep = rp * kEncMaxCat;
@@ -267,7 +235,43 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
                         }
                     }
                 }
+    };
+    b200flow_slot my_sl = plan_sh[0]; int my_cat = -2;
+    if (fixed && active) { my_sl = plan_sh[d0]; my_cat = slot_cat[d0]; }
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kEncStages, o = it % kEncOutBufs, ob = it & 1;
+        const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
+        const int64_t row_base = tile * R;
+        const int rows = (int)min((int64_t)R, a.n_rows - row_base);
+        const bool full = rows == R;
+        uint8_t* in_t = in_base + (size_t)s * a.in_stride;
+        OUT* out_t = (OUT*)(out_base + (size_t)o * a.out_stride);
+        int32_t* bad = badtag + ob * R;
+        const int tag = it + 1;
+
+        mbar_wait(&mbar[s], ph);
+        if (!full) {
+            const uint32_t* src = (const uint32_t*)(a.records + row_base * row_bytes);
+            for (int i = tid; i < rows * row_bytes / 4; i += bd) ((uint32_t*)in_t)[i] = __ldg(src + i);
+            __syncthreads();
+        }
+
+        if (nsrc > 0) {
+            for (int idx = tid; idx < rows * nsrc; idx += bd) {
+                const int r = idx / nsrc, c = idx - r * nsrc;
+                const int code = *(const int32_t*)(in_t + r * row_bytes + cat_tab[c]);
+                const int rank = (code >= 0 && code < cat_tab[2 * (kEncMaxCat + 1) + c]) ? lut[cat_tab[(kEncMaxCat + 1) + c] + code] : -1;
+                if (rank < 0) bad[r] = tag;
+                if (c < ncat) rank_sh[r * kEncMaxCat + c] = rank;
+                else if (a.label_out) a.label_out[row_base + r] = rank;
             }
+            if (ncat > 0) __syncthreads();          // ranks visible to the slot loops (label-only: nothing to wait for)
+        }
+        if (active) {
+            if (fixed) do_slot(my_sl, my_cat, d0, in_t, out_t, bad, tag, rows);     // one slot per thread, hoisted out of the tile loop
+            else for (int d = d0; d < n_out; d += dstep) do_slot(plan_sh[d], slot_cat[d], d, in_t, out_t, bad, tag, rows);
         }
         if (tid == 0) bulk_wait_read<1>();           // all but the latest store have drained: the next tile's out buffer is free
         fence_proxy_async();
@@ -284,6 +288,174 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
         if (a.valid_out) for (int r = tid; r < rows; r += bd) a.valid_out[row_base + r] = (bad[r] != tag) ? 1 : 0;
     }
     if (tid == 0) bulk_wait_all<0>();
+}
+
+// ------------------------------------------------------------------ fused encode -> TreePoint bins (R2+R3 feeding R5)
+// The tree trainer never needs the dense feature matrix: it needs TreePoint bins.  These two kernels go from the raw AoS
+// records straight to (a) the findSplits row sample and (b) the binned uint8 records, evaluating every slot of the encode
+// plan in fp64 exactly like encode_kernel does (SURVEY.md 8d "Encode -> bins": KDD 168 + 41 + 1 = 210 B/row instead of
+// writing, compacting and re-reading a 164 B/row f32 matrix).
+__device__ __forceinline__ double slot_value(const uint8_t* row, const b200flow_slot& sl, const int32_t* __restrict__ lut,
+                                             int round_f32, bool* invalid, bool* is_nan) {
+    double v;
+    if (sl.kind == B200FLOW_SRC_F32) { v = (double)(*(const float*)(row + sl.src_off)); *is_nan = v != v; }
+    else if (sl.kind == B200FLOW_SRC_F64) { const uint32_t* q = (const uint32_t*)(row + sl.src_off); v = __hiloint2double((int)q[1], (int)q[0]); *is_nan = v != v; }
+    else if (sl.kind == B200FLOW_SRC_I32) v = (double)(*(const int32_t*)(row + sl.src_off));
+    else {
+        const int code = *(const int32_t*)(row + sl.src_off);
+        const int rank = (code >= 0 && code < sl.lut_len) ? lut[sl.lut_off + code] : -1;
+        if (rank < 0) *invalid = true;
+        v = sl.kind == B200FLOW_SRC_INDEX ? (double)rank : (rank == sl.hot ? 1.0 : 0.0);
+    }
+    if (!(sl.mean == 0.0 && sl.scale == 1.0)) v = (v - sl.mean) * sl.scale;
+    if (round_f32) v = (double)(float)v;                   // the value an f32 feature matrix would have held
+    return v;
+}
+
+// R4 on raw records: Bernoulli row sample keyed by the GLOBAL row, every sampled row encoded through the plan
+__global__ void __launch_bounds__(256) sample_records_kernel(const uint8_t* __restrict__ rec, int64_t n, int row_bytes,
+                                                             const b200flow_slot* __restrict__ plan, int F,
+                                                             const int32_t* __restrict__ lut, int round_f32, uint64_t seed,
+                                                             uint64_t keep_thr, int64_t row_offset, double* sample, int64_t cap,
+                                                             int32_t* n_sampled) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = (uint64_t)(row_offset + i);
+        const uint4 r = philox_keyed(seed, PURPOSE_SAMPLE, (uint32_t)g, (uint32_t)(g >> 32), 0u, 0u);
+        if ((uint64_t)r.x < keep_thr) {
+            const int slot = atomicAdd(n_sampled, 1);
+            if (slot < cap) {
+                const uint8_t* row = rec + i * row_bytes;
+                for (int f = 0; f < F; ++f) {
+                    bool inv = false, nan = false;
+                    const b200flow_slot sl = plan[f];
+                    sample[(int64_t)f * cap + slot] = slot_value(row, sl, lut, round_f32, &inv, &nan);
+                }
+            }
+        }
+    }
+}
+
+struct EncodeBinsArgs {
+    const uint8_t* records; int64_t n_rows; int row_bytes;
+    const b200flow_slot* plan; int F;
+    const int32_t* lut; int lut_total; int lut_in_smem;
+    int label_off, label_lut_off, label_lut_len, check_nan, round_f32;
+    const double* thresholds; const int32_t* n_thr; const int32_t* arity; int max_bins; int thr_in_smem;
+    uint8_t* tp; int stride; int32_t* label_out; int32_t* bad;    // bad[0]: categorical cells outside [0, arity); bad[1]: NaN cells + unseen codes
+    int R; int in_stride;
+};
+
+constexpr int kBinThreads = 256;
+
+// Persistent CTAs; per tile of R records (one TMA bulk load, 3-deep ring): a WARP owns a feature for 32 rows at a time, so
+// the slot descriptor, the arity and the threshold array are warp-uniform — the lower_bound search of the first steps hits
+// one or two shared-memory words per step (broadcast) instead of 32 different arrays — and feature trip counts do not
+// diverge.  Bins land in a padded byte tile (row pitch = stride + 4 bytes: conflict-free byte stores across rows), which
+// the whole CTA then streams out as 16-byte words; the tile is double-buffered, so there is ONE barrier per tile.
+__global__ void __launch_bounds__(kBinThreads) encode_bins_kernel(const EncodeBinsArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id(), nw = kBinThreads / 32;
+    const int R = a.R, F = a.F, row_bytes = a.row_bytes, ns = a.max_bins - 1, stride = a.stride, pitch = stride + 4;
+    uint8_t* in_base = smem;
+    uint8_t* out_base = in_base + (size_t)kEncStages * a.in_stride;                 // [2][R][pitch]
+    uint64_t* mbar = (uint64_t*)(out_base + (((size_t)2 * R * pitch + 7) & ~(size_t)7));
+    b200flow_slot* plan_sh = (b200flow_slot*)(mbar + kEncStages);
+    int32_t* nthr_sh = (int32_t*)(plan_sh + F);
+    int32_t* arity_sh = nthr_sh + F;
+    int32_t* lut_sh = arity_sh + F;
+    double* thr_sh = (double*)(((uintptr_t)(lut_sh + (a.lut_in_smem ? a.lut_total : 0)) + 7) & ~(uintptr_t)7);
+    const int64_t n_tiles = (a.n_rows + R - 1) / R;
+    const uint32_t tile_in_bytes = (uint32_t)R * row_bytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < kEncStages; ++s) mbar_init(&mbar[s], 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < F * (int)(sizeof(b200flow_slot) / 4); i += kBinThreads) ((uint32_t*)plan_sh)[i] = ((const uint32_t*)a.plan)[i];
+    for (int i = tid; i < F; i += kBinThreads) { nthr_sh[i] = a.n_thr[i]; arity_sh[i] = a.arity[i]; }
+    if (a.lut_in_smem) for (int i = tid; i < a.lut_total; i += kBinThreads) lut_sh[i] = a.lut[i];
+    if (a.thr_in_smem) for (int i = tid; i < F * ns; i += kBinThreads) thr_sh[i] = a.thresholds[i];
+    for (int i = tid; i < 2 * R * pitch / 4; i += kBinThreads) ((uint32_t*)out_base)[i] = 0;      // pad bytes stay zero for ever
+    __syncthreads();
+    const int32_t* lut = a.lut_in_smem ? lut_sh : a.lut;
+    const double* thr_all = a.thr_in_smem ? thr_sh : a.thresholds;
+
+    auto issue_load = [&](int64_t tile, int s) {
+        if (a.n_rows - tile * R >= R) {
+            mbar_arrive_expect_tx(&mbar[s], tile_in_bytes);
+            bulk_g2s(in_base + (size_t)s * a.in_stride, a.records + tile * (int64_t)tile_in_bytes, tile_in_bytes, &mbar[s]);
+        } else mbar_arrive(&mbar[s]);                       // ragged last tile: loaded cooperatively below
+    };
+    if (tid == 0)
+        for (int s = 0; s < kEncStages; ++s) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+            if (t < n_tiles) issue_load(t, s);
+        }
+    int n_bad = 0, n_inv = 0;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kEncStages;
+        const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
+        const int64_t row_base = tile * R;
+        const int rows = (int)min((int64_t)R, a.n_rows - row_base);
+        const uint8_t* in_t = in_base + (size_t)s * a.in_stride;
+        uint8_t* out_t = out_base + (size_t)(it & 1) * R * pitch;
+        mbar_wait(&mbar[s], ph);
+        if (rows < R) {
+            const uint32_t* src = (const uint32_t*)(a.records + row_base * row_bytes);
+            for (int i = tid; i < rows * row_bytes / 4; i += kBinThreads) ((uint32_t*)in_t)[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        for (int f = wid; f <= F; f += nw) {                // task F = the label column
+            if (f == F) {
+                if (a.label_off < 0) continue;
+                for (int r = lane; r < rows; r += 32) {
+                    const int code = *(const int32_t*)(in_t + r * row_bytes + a.label_off);
+                    const int rank = (code >= 0 && code < a.label_lut_len) ? lut[a.label_lut_off + code] : -1;
+                    if (rank < 0) ++n_inv;
+                    out_t[r * pitch + F] = (uint8_t)rank;
+                    if (a.label_out) a.label_out[row_base + r] = rank;
+                }
+                continue;
+            }
+            const b200flow_slot sl = plan_sh[f];
+            const int ar = arity_sh[f], nt = nthr_sh[f];
+            const double* thr = thr_all + (int64_t)f * ns;
+            const int steps = 32 - __clz(nt);              // ceil(log2(nt + 1)) iterations settle lower_bound over nt thresholds
+            for (int r = lane; r < rows; r += 32) {
+                bool inv = false, nan = false;
+                const double v = slot_value(in_t + r * row_bytes, sl, lut, a.round_f32, &inv, &nan);
+                if (inv || (a.check_nan && nan)) ++n_inv;
+                int b;
+                if (ar > 0) {
+                    b = (int)v;
+                    if (!((double)b == v) || b < 0 || b >= ar) { b = ar < 255 ? ar : 255; ++n_bad; }   // never inside a left-set mask
+                } else {
+                    int lo = 0, hi = nt;                    // lower_bound: first b with v <= thr[b] (branch-free, uniform trip count)
+                    for (int k = 0; k < steps; ++k) {
+                        const int mid = (lo + hi) >> 1;
+                        const bool open = lo < hi;
+                        const bool le = open && v <= thr[open ? mid : 0];
+                        hi = le ? mid : hi;
+                        lo = (open && !le) ? mid + 1 : lo;
+                    }
+                    b = lo;
+                }
+                out_t[r * pitch + f] = (uint8_t)b;
+            }
+        }
+        __syncthreads();                                    // tile binned; input stage s consumed
+        if (tid == 0) { const int64_t next = tile + (int64_t)kEncStages * gridDim.x; if (next < n_tiles) issue_load(next, s); }
+        const int q16 = stride / 16;
+        uint4* dst = (uint4*)(a.tp + row_base * stride);
+        for (int i = tid; i < rows * q16; i += kBinThreads) {
+            const int r = i / q16, q = i - r * q16;
+            const uint32_t* w = (const uint32_t*)(out_t + r * pitch + q * 16);
+            st_stream_u4(dst + i, make_uint4(w[0], w[1], w[2], w[3]));
+        }
+    }
+    n_bad = warp_sum(n_bad); n_inv = warp_sum(n_inv);
+    if (lane == 0) { if (n_bad) atomicAdd(&a.bad[0], n_bad); if (n_inv) atomicAdd(&a.bad[1], n_inv); }
 }
 
 // ------------------------------------------------------------------ R3c column moments
@@ -418,4 +590,59 @@ extern "C" int b200flow_column_moments(const void* x, int32_t dtype, int64_t n_r
     else
         column_moments_kernel<double><<<grid, 256, smem, (cudaStream_t)stream>>>((const double*)x, n_rows, D, ld, shift, sum, sumsq);
     return check_launch("column_moments");
+}
+
+extern "C" int b200flow_sample_records(const void* records, int64_t n_rows, int32_t row_bytes, const b200flow_slot* plan, int32_t F,
+                                       const int32_t* lut, int32_t round_f32, uint64_t seed, uint64_t keep_threshold,
+                                       int64_t row_offset, double* sample, int64_t cap, int32_t* n_sampled, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(records && plan && sample && n_sampled && F > 0 && cap > 0 && row_bytes >= 4 && (row_bytes & 3) == 0, "sample_records: bad arguments");
+    const int grid = grid_for(n_rows, 256 * 4, kNumSMs * 8);
+    sample_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)records, n_rows, row_bytes, plan, F, lut, round_f32, seed,
+                                                                 keep_threshold, row_offset, sample, cap, n_sampled);
+    return check_launch("sample_records");
+}
+
+extern "C" int b200flow_encode_bins(const void* records, int64_t n_rows, int32_t row_bytes, const b200flow_slot* plan, int32_t F,
+                                    const int32_t* lut, int32_t lut_total, int32_t label_off, int32_t label_lut_off,
+                                    int32_t label_lut_len, int32_t check_nan, int32_t round_f32, const double* thresholds,
+                                    const int32_t* n_thr, const int32_t* arity, int32_t max_bins, uint8_t* tp, int32_t tp_stride,
+                                    int32_t* label_out, int32_t* bad, void* stream) {
+    if (n_rows <= 0) return B200FLOW_OK;
+    B2F_REQUIRE(records && plan && thresholds && n_thr && arity && tp && bad, "encode_bins: null pointer");
+    B2F_REQUIRE(F > 0 && F < 4096 && row_bytes >= 4 && (row_bytes & 3) == 0 && max_bins >= 2 && max_bins <= 256, "encode_bins: bad shape");
+    B2F_REQUIRE(tp_stride >= F + 1 && (tp_stride & 15) == 0 && ((uintptr_t)tp & 15) == 0 && ((uintptr_t)records & 15) == 0,
+                "encode_bins: records/tp must be 16-byte aligned, tp_stride a multiple of 16 >= F + 1");
+    B2F_REQUIRE(label_off < 0 || (label_off + 4 <= row_bytes && (label_off & 3) == 0 && lut), "encode_bins: bad label_off");
+    EncodeBinsArgs a;
+    a.records = (const uint8_t*)records; a.n_rows = n_rows; a.row_bytes = row_bytes; a.plan = plan; a.F = F;
+    a.lut = lut; a.lut_total = lut ? lut_total : 0; a.lut_in_smem = (lut && lut_total > 0 && lut_total <= 4096) ? 1 : 0;
+    a.label_off = label_off; a.label_lut_off = label_lut_off; a.label_lut_len = label_lut_len; a.check_nan = check_nan; a.round_f32 = round_f32;
+    a.thresholds = thresholds; a.n_thr = n_thr; a.arity = arity; a.max_bins = max_bins;
+    const size_t thr_bytes = (size_t)F * (max_bins - 1) * 8;
+    a.thr_in_smem = thr_bytes <= 96 * 1024 ? 1 : 0;
+    a.tp = tp; a.stride = tp_stride; a.label_out = label_out; a.bad = bad;
+    const size_t fixed_bytes = kEncStages * 8 + (size_t)F * sizeof(b200flow_slot) + 8 * (size_t)F + (a.lut_in_smem ? (size_t)a.lut_total * 4 : 0) + 16 +
+                               (a.thr_in_smem ? thr_bytes : 0) + 256;
+    const size_t per_row = (size_t)row_bytes * kEncStages + 2 * (size_t)(tp_stride + 4);
+    static int budget_kb = -1;                             // tuning knob: per-CTA shared memory target (2 CTAs per SM at ~100 KB)
+    if (budget_kb < 0) { const char* e = getenv("B200FLOW_BINS_SMEM_KB"); budget_kb = e ? atoi(e) : 100; }
+    B2F_REQUIRE(fixed_bytes + 32 * per_row <= 224 * 1024, "encode_bins: record too wide for shared memory (row_bytes=%d F=%d)", row_bytes, F);
+    int R = (int)(((size_t)budget_kb * 1024 > fixed_bytes ? (size_t)budget_kb * 1024 - fixed_bytes : 0) / per_row);
+    R &= ~31;
+    if (R < 32) R = 32;
+    if (R > 1024) R = 1024;
+    a.R = R;
+    a.in_stride = (R * row_bytes + 127) & ~127;
+    const size_t smem = (size_t)kEncStages * a.in_stride + (((size_t)2 * R * (tp_stride + 4) + 7) & ~(size_t)7) + fixed_bytes;
+    B2F_REQUIRE(smem <= 227 * 1024, "encode_bins: shared memory budget exceeded");
+    const int64_t n_tiles = (n_rows + R - 1) / R;
+    int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    const int grid = (int)(n_tiles < (int64_t)kNumSMs * ctas_per_sm ? n_tiles : (int64_t)kNumSMs * ctas_per_sm);
+    cudaError_t e = cudaFuncSetAttribute(encode_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("encode_bins: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
+    encode_bins_kernel<<<grid, kBinThreads, smem, (cudaStream_t)stream>>>(a);
+    return check_launch("encode_bins");
 }

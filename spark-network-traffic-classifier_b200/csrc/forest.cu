@@ -506,18 +506,21 @@ __global__ void __launch_bounds__(256) partition_level_kernel(
 
 // ------------------------------------------------------------------ fused row routing + next-level histogram
 // Persistent CTAs (a multiple of 148), each owning a contiguous range of chunks (<= CH entries of one SPLIT parent).
-// Software pipeline per CTA, all copies asynchronous (LDGSTS, no register staging):
+// Software pipeline per WARP, all copies asynchronous (LDGSTS, no register staging):
 //     entries(t+2)  -->  record gather(t+1)  -->  route + histogram(t)
 //   * the gather brings each entry's 64-byte-aligned TreePoint record (one HBM burst) into a shared-memory tile,
 //     ONCE per entry per level — partition_level + hist_level gathered it twice and were bound by exactly that;
 //   * every entry is routed by the parent's split and accumulated into its CHILD's histogram (child feature subset)
-//     in shared memory; lanes with identical (child, bins, label) keys — the duplicate-heavy smurf/neptune flows —
-//     are merged with match.any + ballots so that one lane issues the shared atomics;
+//     in shared memory; the lanes that hit the same counter as the first active lane are merged (top-group merge);
 //   * kept entries go to the child's range (left grows up from seg_begin, right grows down from seg_end; one cursor
-//     reservation per chunk and side); the two child histograms stay in shared memory while consecutive chunks belong
-//     to the same parent and are flushed with sparse global REDs when the parent changes.
-constexpr int kRouteThreads = 256;
-
+//     reservation per warp step and side); the two child histograms stay in shared memory while consecutive chunks
+//     belong to the same parent and are flushed with sparse global REDs when the parent changes.
+// Launch shapes (route_cfg below): NW warps per CTA x KS entries per lane and step; a chunk is NW * KS * 32 entries.
+// Narrow nodes (KDD 5-class: 2 x 9.8 KB of child histograms) run 4 CTAs x 8 warps x 64 entries per SM; wide nodes
+// (KDD 23-class: 2 x 45 KB, CICIDS 15-class: 2 x 42 KB) trade tile bytes for histogram bytes — 2 CTAs x 16 warps x 32
+// entries, or 1 CTA x 32 warps — so that the SM still holds 32 warps.  Nodes whose two child histograms exceed shared
+// memory altogether (DecisionTree: every feature of every node) are processed in FEATURE PASSES: pass p accumulates
+// subset positions [j0, j0 + m_pass) and only pass 0 routes.
 struct RouteChunk { int32_t slot; int32_t n; long long begin; };   // 16 bytes, one per chunk
 
 __global__ void route_chunks_kernel(const int64_t* __restrict__ chunk_off, int n_slots, const int64_t* __restrict__ n_chunks_dev,
@@ -534,33 +537,33 @@ __global__ void route_chunks_kernel(const int64_t* __restrict__ chunk_off, int n
 struct RouteArgs {
     const uint8_t* tp; int stride; int F;
     const b2f_entry* ent; b2f_entry* ent_out;
-    const RouteChunk* chunks; const int64_t* n_chunks_dev; int CH;
+    const RouteChunk* chunks; const int64_t* n_chunks_dev;
     const int64_t* seg_begin; const int64_t* seg_end;
     const b200flow_split* split; const int32_t* child_slot; int32_t* cursors;
-    const uint16_t* subset_next; int m; int n_bins; int C; uint32_t* hist_next;
+    const uint16_t* subset_next; int m_total;   // subset width of a slot (stride of subset_next and of a slot's histogram)
+    int j0; int m;                              // this pass accumulates subset positions [j0, j0 + m)
+    int n_bins; int C; uint32_t* hist_next;
+    int route;                                  // 1: write the routed entries + cursors (first pass of a routed level)
 };
 
-// M = compile-time size of the per-node feature subset (merged shared atomics); M = 0: generic path.
-// Barrier-free inner loop: a chunk is kRouteWarps sub-chunks of 64 entries, one per warp.  Per warp and step t:
-//     entries(t+2) -> registers (prefetch) | record gather(t+1) -> private tile[(t+1)&1] (LDGSTS, asynchronous)
+// M = compile-time number of subset features of the pass (merged shared atomics); M = 0: generic path.
+// Barrier-free inner loop: a chunk is NW sub-chunks of KS * 32 entries, one per warp.  Per warp and step t:
+//     entries(t+2) -> registers (prefetch) | record gather(t) -> private tile (LDGSTS; hidden by the other resident warps)
 //     write-out of step t-1 (its cursor reservation, a global atomic issued one step earlier, has landed by now)
-//     route + histogram of step t from tile[t&1]
-// so every warp always has one gather (64 x 64-byte HBM bursts) in flight.  CTA-wide barriers happen only when the
-// parent slot changes (flush + re-zero of the two child histograms).
-constexpr int kRouteWarps = kRouteThreads / 32;
-constexpr int kSub = 64;                                    // entries per warp step (2 per lane)
-
-template <int M, int NBUF, int MERGE>   // MERGE: 0 plain shared atomics, 1 top-group merge
-__global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_level_kernel(const RouteArgs a) {
+//     route + histogram of step t from the tile
+// CTA-wide barriers happen only when the parent slot changes (flush + re-zero of the two child histograms).
+template <int M, int NW, int KS, int MERGE>   // MERGE: 0 plain shared atomics, 1 top-group merge
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) route_hist_level_kernel(const RouteArgs a) {
     extern __shared__ __align__(16) uint32_t sm_u32[];
+    constexpr int kThreads = NW * 32, kSub = KS * 32;
     const int m = M > 0 ? M : a.m;
     const int F = a.F;
     const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     const int nq = (F + 1 + 15) / 16;                        // staged 16-byte quads per record
     const int nbC = a.n_bins * a.C, hsz = m * nbC;
     const int tile_words = nq * kSub * 4;
-    uint32_t* tiles = sm_u32 + (size_t)wid * NBUF * tile_words; // this warp's NBUF [64][nq] quad tiles (entry-major)
-    uint32_t* sh_hist = sm_u32 + (size_t)kRouteWarps * NBUF * tile_words;   // [2][hsz]
+    uint32_t* tile = sm_u32 + (size_t)wid * tile_words;      // this warp's [kSub][nq] quad tile (entry-major)
+    uint32_t* sh_hist = sm_u32 + (size_t)NW * tile_words;    // [2][hsz]
     int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: byte offset of the feature inside a staged record
     __shared__ b200flow_split sh_split;
     __shared__ int sh_child[2];
@@ -572,72 +575,68 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
         for (int side = 0; side < 2; ++side) {
             const int cs = sh_child[side];
             if (cs < 0) continue;
-            uint32_t* gh = a.hist_next + (int64_t)cs * hsz;
+            uint32_t* gh = a.hist_next + ((int64_t)cs * a.m_total + a.j0) * nbC;
             uint32_t* sh = sh_hist + side * hsz;
-            for (int i = tid; i < hsz; i += kRouteThreads) { const uint32_t v = sh[i]; if (v) { atomicAdd(gh + i, v); sh[i] = 0; } }   // flush + re-zero
+            for (int i = tid; i < hsz; i += kThreads) { const uint32_t v = sh[i]; if (v) { atomicAdd(gh + i, v); sh[i] = 0; } }   // flush + re-zero
         }
     };
-    for (int i = tid; i < 2 * hsz; i += kRouteThreads) sh_hist[i] = 0;     // zero once; every flush leaves the histograms zeroed
+    for (int i = tid; i < 2 * hsz; i += kThreads) sh_hist[i] = 0;     // zero once; every flush leaves the histograms zeroed
     auto desc_at = [&](int64_t c) { return c < c1 ? __ldg((const int4*)(a.chunks + c)) : make_int4(-1, 0, 0, 0); };
     auto count_of = [&](const int4& d) { return min(kSub, d.y - wid * kSub); };
-    auto entries_of = [&](const int4& d, b2f_entry* x0, b2f_entry* x1) {
+    auto entries_of = [&](const int4& d, b2f_entry* x) {
         const int cn = count_of(d);
         const b2f_entry* ep = a.ent + (((long long)(uint32_t)d.z) | ((long long)d.w << 32)) + wid * kSub;
-        *x0 = lane < cn ? __ldg(ep + lane) : make_uint2(0u, 0u);
-        *x1 = lane + 32 < cn ? __ldg(ep + 32 + lane) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) x[k] = lane + 32 * k < cn ? __ldg(ep + 32 * k + lane) : make_uint2(0u, 0u);
     };
-    // The tile is entry-major ([64 entries][nq quads]) and its 64 * nq 16-byte chunks are copied in linear order, lane after
-    // lane: neighbouring lanes fetch neighbouring quads of the SAME record (same 32-byte sector) into neighbouring shared
-    // addresses, which the L1 fills with fewer wavefronts than one scattered 16-byte fill per lane (ncu source page: the
-    // LDGSTS fills were 45 % of the kernel's shared-memory wavefronts with a quad-major tile; 23 instead of 31 per LDGSTS now).
-    // It costs two shuffles per chunk for the record index, so it only pays once the kernel is LSU-bound, not issue-bound:
-    // same time before the predicated merge, 19.0 -> 17.7 ms per fit after it.
+    // The tile is entry-major ([kSub entries][nq quads]) and its kSub * nq 16-byte chunks are copied in linear order, lane
+    // after lane: neighbouring lanes fetch neighbouring quads of the SAME record (same 32-byte sector) into neighbouring
+    // shared addresses, which the L1 fills with fewer wavefronts than one scattered 16-byte fill per lane (ncu source page:
+    // 23 instead of 31 wavefronts per LDGSTS).
     const uint32_t inv_nq = 65536u / (uint32_t)nq + 1u;         // c / nq == (c * inv_nq) >> 16 for c < 1024
-    auto issue_gather = [&](const int4& d, const b2f_entry& x0, const b2f_entry& x1, uint32_t* tile) {
+    auto issue_gather = [&](const int4& d, const b2f_entry* x) {
         const int cn = count_of(d);
-        for (int c = lane; c < kSub * nq; c += 32) {           // uniform trip count (2 * nq)
+        for (int c = lane; c < kSub * nq; c += 32) {           // uniform trip count (KS * nq)
             const int e = (int)(((uint32_t)c * inv_nq) >> 16), q = c - e * nq;
-            const uint32_t r0 = __shfl_sync(0xffffffffu, x0.x, e & 31), r1 = __shfl_sync(0xffffffffu, x1.x, e & 31);
-            if (e < cn) cp_async16(tile + c * 4, a.tp + (int64_t)(e < 32 ? r0 : r1) * a.stride + q * 16);
+            uint32_t r = __shfl_sync(0xffffffffu, x[0].x, e & 31);
+            if (KS == 2) { const uint32_t r1 = __shfl_sync(0xffffffffu, x[KS - 1].x, e & 31); r = e < 32 ? r : r1; }
+            if (e < cn) cp_async16(tile + c * 4, a.tp + (int64_t)r * a.stride + q * 16);
         }
         cp_async_commit();
     };
     // pending write of the previous step (registers only)
     bool pending = false;
-    b2f_entry p_e0 = make_uint2(0u, 0u), p_e1 = p_e0; uint32_t p_dec = 0; int p_bl = 0, p_br = 0; int64_t p_sb = 0, p_se = 0;
+    b2f_entry p_e[KS]; uint32_t p_dec = 0; int p_bl = 0, p_br = 0; int64_t p_sb = 0, p_se = 0;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) p_e[k] = make_uint2(0u, 0u);
     const uint32_t lt = (1u << lane) - 1u;
     auto write_pending = [&]() {
         int baseL = __shfl_sync(0xffffffffu, p_bl, 0), baseR = __shfl_sync(0xffffffffu, p_br, 0);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < KS; ++k) {
             const int d = (p_dec >> (2 * k)) & 3;
-            const b2f_entry e = k ? p_e1 : p_e0;
             const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
-            if (d == 1) a.ent_out[p_sb + baseL + __popc(mL & lt)] = e;
-            else if (d == 2) a.ent_out[p_se - 1 - (baseR + __popc(mR & lt))] = e;
+            if (d == 1) a.ent_out[p_sb + baseL + __popc(mL & lt)] = p_e[k];
+            else if (d == 2) a.ent_out[p_se - 1 - (baseR + __popc(mR & lt))] = p_e[k];
             baseL += __popc(mL); baseR += __popc(mR);
         }
         pending = false;
     };
 
     int4 d0 = desc_at(c0), d1 = desc_at(c0 + 1), d2 = desc_at(c0 + 2);
-    b2f_entry e0, e1, f0, f1, g0 = make_uint2(0u, 0u), g1 = g0;   // entries of steps t, t+1, t+2
-    entries_of(d0, &e0, &e1);
-    entries_of(d1, &f0, &f1);
-    if (NBUF == 2) issue_gather(d0, e0, e1, tiles);
+    b2f_entry e[KS], f[KS], g[KS];                             // entries of steps t, t+1, t+2
+    entries_of(d0, e);
+    entries_of(d1, f);
     int cur_slot = -1;
-    const int rs = nq * 16;                                      // bytes per staged record
-    const int lab_pos = F;         // byte of the label inside a tile (entry 0; + 16 per entry)
+    const int rs = nq * 16;                                    // bytes per staged record
+    const int lab_pos = F;                                     // byte of the label inside a staged record
+    const uint8_t* tile8 = (const uint8_t*)tile;               // [kSub entries][nq * 16 bytes]
     for (int64_t c = c0; c < c1; ++c) {
-        const int par = NBUF == 2 ? (int)((c - c0) & 1) : 0;
-        const uint8_t* tile8 = (const uint8_t*)(tiles + par * tile_words);   // [64 entries][nq * 16 bytes]
-        entries_of(d2, &g0, &g1);                              // prefetch, consumed two steps later
+        entries_of(d2, g);                                     // prefetch, consumed two steps later
         const int4 d3 = desc_at(c + 3);
-        if (NBUF == 2) issue_gather(d1, f0, f1, tiles + (par ^ 1) * tile_words);   // in flight during this step's compute
-        else issue_gather(d0, e0, e1, tiles);                  // single tile: latency hidden by the other resident warps
+        issue_gather(d0, e);                                   // single tile: latency hidden by the other resident warps
         if (pending) write_pending();
-        if (NBUF == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");  // this step's gather has landed
-        else cp_async_wait_all();
+        cp_async_wait_all();
         __syncwarp();
         const int s = d0.x;
         if (s != cur_slot) {                                   // same decision in every warp: all iterate the same chunks
@@ -646,10 +645,10 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
             __syncthreads();
             if (tid < 16) ((uint32_t*)&sh_split)[tid] = ((const uint32_t*)(a.split + s))[tid];
             if (tid < 2) sh_child[tid] = a.child_slot[2 * s + tid];
-            for (int j = tid; j < 2 * m; j += kRouteThreads) {
+            for (int j = tid; j < 2 * m; j += kThreads) {
                 const int cs = a.child_slot[2 * s + (j >= m)];
-                const int f = cs >= 0 ? a.subset_next[(int64_t)cs * m + (j < m ? j : j - m)] : 0;
-                sh_fpos[j] = f;
+                const int fidx = cs >= 0 ? a.subset_next[(int64_t)cs * a.m_total + a.j0 + (j < m ? j : j - m)] : 0;
+                sh_fpos[j] = fidx;
             }
             cur_slot = s;
             __syncthreads();
@@ -658,15 +657,14 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
         if (cnt > 0) {
             const int cl = sh_child[0], cr = sh_child[1];
             const int fs = sh_split.feat, kind = sh_split.kind, thr = sh_split.bin_thr;
-            const int fs_pos = fs;
             int nL = 0, nR = 0;
             uint32_t dec = 0;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < KS; ++k) {
                 const int i = k * 32 + lane;
                 int d = 0;
                 if (i < cnt) {
-                    const int bin = tile8[fs_pos + i * rs];
+                    const int bin = tile8[fs + i * rs];
                     const bool left = kind == 0 ? (bin <= thr) : ((sh_split.mask[bin >> 6] >> (bin & 63)) & 1ull);
                     d = left ? (cl >= 0 ? 1 : 0) : (cr >= 0 ? 2 : 0);
                 }
@@ -679,7 +677,7 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
                     const int* fpos = sh_fpos + side * m;
                     uint32_t* hist = sh_hist + side * hsz;
                     const uint32_t lab = tile8[lab_pos + i * rs];
-                    const uint32_t w = k ? e1.y : e0.y;
+                    const uint32_t w = e[k].y;
                     if (M > 0 && MERGE) {
                         // top-group merge: per feature, the lanes that share the first active lane's (bin, label, child) counter are
                         // summed with ONE redux over the whole active mask (the others contribute 0: no divergence) and issue one
@@ -709,13 +707,17 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
             }
             __syncwarp();
             // reserve output positions (one atomic pair per warp step); the result is consumed one step later
-            if (nL | nR) {
+            if (a.route && (nL | nR)) {
                 if (lane == 0) { p_bl = nL ? atomicAdd(&a.cursors[2 * s], nL) : 0; p_br = nR ? atomicAdd(&a.cursors[2 * s + 1], nR) : 0; }
-                p_e0 = e0; p_e1 = e1; p_dec = dec; p_sb = a.seg_begin[s]; p_se = a.seg_end[s];
+#pragma unroll
+                for (int k = 0; k < KS; ++k) p_e[k] = e[k];
+                p_dec = dec; p_sb = a.seg_begin[s]; p_se = a.seg_end[s];
                 pending = true;
             }
         }
-        d0 = d1; d1 = d2; d2 = d3; e0 = f0; e1 = f1; f0 = g0; f1 = g1;
+        d0 = d1; d1 = d2; d2 = d3;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) { e[k] = f[k]; f[k] = g[k]; }
     }
     if (pending) write_pending();
     cp_async_wait_all();
@@ -723,17 +725,86 @@ __global__ void __launch_bounds__(kRouteThreads, NBUF == 1 ? 4 : 3) route_hist_l
     flush();
 }
 
-static int route_variant() {                                // tuning knob: bit0 = 2 tiles per warp, bit1 = plain atomics (no merge)
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? atoi(e) & 3 : 0; }
-    return v;        // default 0 = one tile per warp + top-group merge (per KDD-full fit: 19.0 ms; plain atomics 26 ms)
+// ---- launch shape of the fused kernel
+struct RouteCfg { int nw, ks, m_pass, per_sm; size_t smem; };
+constexpr size_t kSmemPerSM = 227 * 1024;                  // 232,448 B usable per SM on sm_100
+constexpr size_t kSmemCtaOverhead = 1024 + 128;            // driver reservation per CTA + the kernel's static shared memory
+
+static size_t route_hist_smem(int F, int mp, int n_bins, int C, int nw, int ks) {
+    const size_t nq = (size_t)(F + 1 + 15) / 16;
+    return (size_t)nw * ks * 32 * nq * 16 + 2 * (size_t)mp * n_bins * C * 4 + 2 * (size_t)mp * 4 + 64;
+}
+static int route_max_ctas(int nw) { return nw == 8 ? 4 : (nw == 16 ? 2 : 1); }   // __launch_bounds__
+
+// Picks (warps per CTA, entries per lane, features per pass): the fewest passes first (every extra pass gathers the
+// records again), then the most resident warps per SM (<= 32 matter), then the most entries in flight, then the smallest chunk.
+static bool route_cfg(int F, int m, int n_bins, int C, RouteCfg* out) {
+    static const int cand[5][2] = {{8, 2}, {8, 1}, {16, 2}, {16, 1}, {32, 1}};
+    int force_nw = 0, force_ks = 0;                         // tuning / test knob, read per call: B200FLOW_ROUTE_SHAPE=<warps>x<entries per lane>
+    { const char* e = getenv("B200FLOW_ROUTE_SHAPE"); if (e && sscanf(e, "%dx%d", &force_nw, &force_ks) != 2) force_nw = force_ks = 0; }
+    if (F <= 0 || F > 255 || m <= 0 || n_bins <= 0 || C <= 0) return false;
+    auto fits = [&](int mp, int nw, int ks) { return route_hist_smem(F, mp, n_bins, C, nw, ks) + kSmemCtaOverhead <= kSmemPerSM; };
+    int mp = m;
+    while (mp >= 1 && !fits(mp, 8, 1)) --mp;                // (8, 1) has the smallest tiles
+    if (mp < 1) return false;
+    const int passes = (m + mp - 1) / mp;
+    mp = (m + passes - 1) / passes;                          // balanced passes
+    int best = -1; long best_key = -1;
+    for (int i = 0; i < 5; ++i) {
+        const int nw = cand[i][0], ks = cand[i][1];
+        if (force_nw > 0 && (nw != force_nw || ks != force_ks)) continue;
+        if (!fits(mp, nw, ks)) continue;
+        const size_t smem = route_hist_smem(F, mp, n_bins, C, nw, ks);
+        int per_sm = (int)(kSmemPerSM / (smem + kSmemCtaOverhead));
+        if (per_sm > route_max_ctas(nw)) per_sm = route_max_ctas(nw);
+        const int warps = per_sm * nw > 32 ? 32 : per_sm * nw;
+        const long key = ((long)warps << 20) + ((long)(warps * ks) << 10) + (1023 - nw * ks);
+        if (key > best_key) { best_key = key; best = i; }
+    }
+    if (best < 0) return false;
+    out->nw = cand[best][0]; out->ks = cand[best][1]; out->m_pass = mp;
+    out->smem = route_hist_smem(F, mp, n_bins, C, out->nw, out->ks);
+    out->per_sm = (int)(kSmemPerSM / (out->smem + kSmemCtaOverhead));
+    if (out->per_sm > route_max_ctas(out->nw)) out->per_sm = route_max_ctas(out->nw);
+    return true;
 }
 
-static size_t route_hist_smem(int F, int m, int n_bins, int C, int CH) {
-    const size_t nq = (size_t)(F + 1 + 15) / 16;
-    (void)CH;                                               // a chunk is always kRouteWarps * kSub entries
-    const size_t nbuf = (route_variant() & 1) ? 2 : 1;
-    return (size_t)kRouteWarps * nbuf * nq * kSub * 16 + 2 * (size_t)m * n_bins * C * 4 + 2 * (size_t)m * 4 + 64;
+static int route_plain_atomics() {                          // tuning knob: B200FLOW_ROUTE_VARIANT bit1 = plain atomics (no merge)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? (atoi(e) >> 1) & 1 : 0; }
+    return v;        // default 0 = top-group merge (per KDD-full fit: 19.0 ms; plain atomics 26 ms)
+}
+
+template <int NW, int KS>
+static cudaError_t route_launch(int M, bool merge, unsigned grid_cap, size_t smem, int per_sm_hint, int waves, int64_t n_chunks_max,
+                                const RouteArgs& a, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+#define B2F_ROUTE_GO(KERNEL)                                                                                                   \
+    {                                                                                                                          \
+        e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
+        if (e != cudaSuccess) return e;                                                                                        \
+        int per_sm = 0;                                                                                                        \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KERNEL, NW * 32, smem);                                    \
+        if (e != cudaSuccess) return e;                                                                                        \
+        if (per_sm < 1) per_sm = per_sm_hint > 0 ? per_sm_hint : 1;                                                            \
+        const int64_t want = (int64_t)kNumSMs * per_sm * waves;                                                                \
+        unsigned grid = (unsigned)(n_chunks_max < want ? n_chunks_max : want);                                                 \
+        if (grid_cap && grid > grid_cap) grid = grid_cap;                                                                      \
+        KERNEL<<<grid, NW * 32, smem, st>>>(a);                                                                                \
+    }
+#define B2F_ROUTE_CASE(MM)                                                                                                     \
+    case MM:                                                                                                                   \
+        if (merge) B2F_ROUTE_GO((route_hist_level_kernel<MM, NW, KS, 1>))                                                      \
+        else B2F_ROUTE_GO((route_hist_level_kernel<0, NW, KS, 0>))                                                             \
+        break;
+    switch (M) {
+        B2F_ROUTE_CASE(1) B2F_ROUTE_CASE(2) B2F_ROUTE_CASE(3) B2F_ROUTE_CASE(4) B2F_ROUTE_CASE(5) B2F_ROUTE_CASE(6)
+        B2F_ROUTE_CASE(7) B2F_ROUTE_CASE(8) B2F_ROUTE_CASE(9) B2F_ROUTE_CASE(10) B2F_ROUTE_CASE(11) B2F_ROUTE_CASE(12)
+        default: B2F_ROUTE_GO((route_hist_level_kernel<0, NW, KS, 0>)) break;
+    }
+#undef B2F_ROUTE_CASE
+#undef B2F_ROUTE_GO
+    return cudaGetLastError();
 }
 
 __global__ void next_segments_kernel(int n_next, const int64_t* __restrict__ n_next_dev, const int32_t* __restrict__ next_parent,
@@ -866,9 +937,12 @@ extern "C" int b200flow_finalize_forest(int64_t n_nodes, const uint32_t* pool_co
     return check_launch("finalize_forest");
 }
 
-extern "C" int b200flow_route_hist_fits(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t chunk_rows) {
-    if (F <= 0 || m <= 0 || n_bins <= 0 || C <= 0 || chunk_rows != kRouteWarps * kSub) return 0;
-    return route_hist_smem(F, m, n_bins, C, chunk_rows) <= 110 * 1024 ? 1 : 0;    // >= 2 CTAs per SM
+extern "C" int b200flow_route_hist_config(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t* chunk_rows, int32_t* m_pass) {
+    RouteCfg cfg;
+    if (!route_cfg(F, m, n_bins, C, &cfg)) return 0;
+    if (chunk_rows) *chunk_rows = cfg.nw * cfg.ks * 32;
+    if (m_pass) *m_pass = cfg.m_pass;
+    return 1;
 }
 
 extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F, const void* ent, void* ent_out,
@@ -876,50 +950,39 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
                                          const int64_t* n_chunks_dev, int64_t n_chunks_max, int32_t chunk_rows,
                                          const b200flow_split* split, const int32_t* child_slot,
                                          int32_t* cursors, void* chunk_scratch, const uint16_t* subset_next, int32_t m, int32_t n_bins,
-                                         int32_t C, uint32_t* hist_next, void* stream) {
-    B2F_REQUIRE(tp && ent && ent_out && seg_begin && seg_end && chunk_off && n_chunks_dev && split && child_slot && cursors && chunk_scratch &&
+                                         int32_t C, uint32_t* hist_next, int32_t flags, void* stream) {
+    B2F_REQUIRE(tp && ent && seg_begin && seg_end && chunk_off && n_chunks_dev && split && child_slot && chunk_scratch &&
                     subset_next && hist_next, "route_hist_level: null pointer");
+    const bool route = (flags & 1) != 0;
+    B2F_REQUIRE(!route || (ent_out && cursors), "route_hist_level: routing needs ent_out and cursors");
     B2F_REQUIRE((tp_stride & 15) == 0 && tp_stride >= (F + 1 + 15) / 16 * 16 && ((uintptr_t)tp & 15) == 0, "route_hist_level: bad TreePoint stride/alignment");
     B2F_REQUIRE(((uintptr_t)chunk_scratch & 15) == 0, "route_hist_level: chunk_scratch must be 16-byte aligned");
-    B2F_REQUIRE(b200flow_route_hist_fits(F, m, n_bins, C, chunk_rows), "route_hist_level: does not fit shared memory (use partition_level + hist_level)");
+    RouteCfg cfg;
+    B2F_REQUIRE(route_cfg(F, m, n_bins, C, &cfg), "route_hist_level: one feature's child histograms exceed shared memory (use partition_level + hist_level)");
+    B2F_REQUIRE(chunk_rows == cfg.nw * cfg.ks * 32, "route_hist_level: chunk_rows must be the value of b200flow_route_hist_config (%d)", cfg.nw * cfg.ks * 32);
     if (n_slots <= 0 || n_chunks_max <= 0) return B200FLOW_OK;
-    const size_t smem = route_hist_smem(F, m, n_bins, C, chunk_rows);
+    cudaStream_t st = (cudaStream_t)stream;
     RouteChunk* chunks = (RouteChunk*)chunk_scratch;
-    route_chunks_kernel<<<(unsigned)((n_chunks_max + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chunk_off, n_slots, n_chunks_dev, seg_begin,
-                                                                                                seg_end, chunk_rows, chunks);
+    route_chunks_kernel<<<(unsigned)((n_chunks_max + 255) / 256), 256, 0, st>>>(chunk_off, n_slots, n_chunks_dev, seg_begin,
+                                                                             seg_end, chunk_rows, chunks);
     RouteArgs a;
-    a.tp = tp; a.stride = tp_stride; a.F = F; a.ent = (const b2f_entry*)ent; a.ent_out = (b2f_entry*)ent_out; a.chunks = chunks; a.n_chunks_dev = n_chunks_dev; a.CH = chunk_rows;
+    a.tp = tp; a.stride = tp_stride; a.F = F; a.ent = (const b2f_entry*)ent; a.ent_out = (b2f_entry*)ent_out; a.chunks = chunks; a.n_chunks_dev = n_chunks_dev;
     a.seg_begin = seg_begin; a.seg_end = seg_end; a.split = split; a.child_slot = child_slot; a.cursors = cursors;
-    a.subset_next = subset_next; a.m = m; a.n_bins = n_bins; a.C = C; a.hist_next = hist_next;
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    const int max_per_sm = (route_variant() & 1) ? 3 : 4;   // __launch_bounds__
-    if (per_sm > max_per_sm) per_sm = max_per_sm;
-    if (per_sm < 1) per_sm = 1;
+    a.subset_next = subset_next; a.m_total = m; a.n_bins = n_bins; a.C = C; a.hist_next = hist_next;
     static int waves = -1;                                    // CTAs per resident slot: > 1 lets the block scheduler even out the tail
     if (waves < 0) { const char* e = getenv("B200FLOW_ROUTE_WAVES"); waves = e ? atoi(e) : 2; if (waves < 1) waves = 1; }   // measured per fit: 17.7 (1), 17.4 (2-6), 17.6 ms (8)
-    const int64_t want = (int64_t)kNumSMs * per_sm * waves;
-    const unsigned grid = (unsigned)(n_chunks_max < want ? n_chunks_max : want);
-#define B2F_ROUTE_LAUNCH(KERNEL)                                                                                               \
-    {                                                                                                                          \
-        cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
-        if (e != cudaSuccess) { set_error("route_hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }       \
-        KERNEL<<<grid, kRouteThreads, smem, (cudaStream_t)stream>>>(a);                                                        \
+    const bool merge = !route_plain_atomics() && C <= 128;
+    for (int j0 = 0, pass = 0; j0 < m; j0 += cfg.m_pass, ++pass) {
+        a.j0 = j0; a.m = m - j0 < cfg.m_pass ? m - j0 : cfg.m_pass; a.route = (route && pass == 0) ? 1 : 0;
+        const int M = a.m <= 12 ? a.m : 0;
+        const size_t smem = route_hist_smem(F, a.m, n_bins, C, cfg.nw, cfg.ks);
+        cudaError_t e;
+        if (cfg.nw == 8 && cfg.ks == 2) e = route_launch<8, 2>(M, merge, 0, smem, cfg.per_sm, waves, n_chunks_max, a, st);
+        else if (cfg.nw == 8) e = route_launch<8, 1>(M, merge, 0, smem, cfg.per_sm, waves, n_chunks_max, a, st);
+        else if (cfg.nw == 16 && cfg.ks == 2) e = route_launch<16, 2>(M, merge, 0, smem, cfg.per_sm, waves, n_chunks_max, a, st);
+        else if (cfg.nw == 16) e = route_launch<16, 1>(M, merge, 0, smem, cfg.per_sm, waves, n_chunks_max, a, st);
+        else e = route_launch<32, 1>(M, merge, 0, smem, cfg.per_sm, waves, n_chunks_max, a, st);
+        if (e != cudaSuccess) { set_error("route_hist_level: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
     }
-#define B2F_ROUTE_CASE(MM)                                                                                                     \
-    case MM:                                                                                                                   \
-        switch (route_variant()) {                                                                                             \
-            case 0: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 1>)) break;                                               \
-            case 1: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 1>)) break;                                               \
-            case 2: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 1, 0>)) break;                                               \
-            default: B2F_ROUTE_LAUNCH((route_hist_level_kernel<MM, 2, 0>)) break;                                              \
-        }                                                                                                                      \
-        break;
-    switch ((m <= 12 && C <= 128) ? m : 0) {
-        B2F_ROUTE_CASE(1) B2F_ROUTE_CASE(2) B2F_ROUTE_CASE(3) B2F_ROUTE_CASE(4) B2F_ROUTE_CASE(5) B2F_ROUTE_CASE(6)
-        B2F_ROUTE_CASE(7) B2F_ROUTE_CASE(8) B2F_ROUTE_CASE(9) B2F_ROUTE_CASE(10) B2F_ROUTE_CASE(11) B2F_ROUTE_CASE(12)
-        default: B2F_ROUTE_CASE(0)
-    }
-#undef B2F_ROUTE_CASE
-#undef B2F_ROUTE_LAUNCH
     return check_launch("route_hist_level");
 }

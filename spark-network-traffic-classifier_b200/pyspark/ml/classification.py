@@ -61,6 +61,9 @@ class _TreeClassifierBase(Estimator, _TreeParams):
         imp = str(self.getOrDefault("impurity")).lower()
         if imp not in ("gini", "entropy"):
             raise IllegalArgumentException("impurity must be gini or entropy, got %r" % imp)
+        if imp == "entropy":       # log is not bit-reproducible between libm and CUDA: not offered on the B200 path
+            raise IllegalArgumentException("impurity='entropy' is not supported by the b200flow tree trainer; use 'gini' "
+                                           "(the reference scripts take the default, kdd99.py:64 / cicids17.py:68)")
         seed = self.getOrDefault("seed")
         return fr.ForestParams(num_trees=int(num_trees), max_depth=int(self.getOrDefault("maxDepth")),
                                max_bins=int(self.getOrDefault("maxBins")),
@@ -78,7 +81,7 @@ class _TreeClassifierBase(Estimator, _TreeParams):
             off, _ = bdist.global_offset(x.shape[0], x.device, grp)
             forest = fr.fit_forest(x, y.to(torch.int32), C, _arity_from_attrs(attrs, x.shape[1]), params,
                                    row_offset=off, group=grp)
-        except ValueError as e:
+        except ValueError as e:        # includes b200flow's UnsupportedParamError; CUDA failures propagate as they are
             raise IllegalArgumentException(str(e))
         return forest
 

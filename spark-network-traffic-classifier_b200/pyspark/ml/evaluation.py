@@ -18,9 +18,8 @@ class MulticlassClassificationEvaluator(Params):
     def confusionMatrix(self, dataset):
         pred = dataset._column_tensor(self.getOrDefault("predictionCol")).to(torch.float64).contiguous()
         lab = dataset._column_tensor(self.getOrDefault("labelCol")).to(torch.float64).contiguous()
-        if pred.numel() == 0:
-            return torch.zeros((1, 1), dtype=torch.int64)
-        mx = torch.maximum(pred.max(), lab.max()).reshape(1)
+        # an empty local shard still takes part in both collectives (every rank issues the same sequence)
+        mx = (torch.maximum(pred.max(), lab.max()) if pred.numel() else torch.zeros((), dtype=torch.float64, device=pred.device)).reshape(1)
         if bdist.group() is not None:
             import torch.distributed as dist
             dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=bdist.group())

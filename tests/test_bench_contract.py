@@ -24,6 +24,19 @@ def test_reference_arm_prints_the_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 
+def test_reference_arm_sets_its_thread_count_and_honours_warmup():
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not inherit it (SCALE_r01: the N>1 arms timed out)
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "cicids_script",
+                          "--cpu-rows", "3000", "--trees", "3", "--depth", "3", "--steps", "1", "--warmup", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    assert d["cpu_baseline"]["cores"] == cores and d["warmup"] == 2 and d["n_gpus"] == 2
+    assert d["config"]["name"] == "cicids_script" and d["config"]["sample_rows"] == 3000 and d["config"]["classes"] == 14
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
@@ -33,5 +46,6 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 def test_gpu_arm_keys_are_emitted_by_bench_source():
     src = open(os.path.join(ROOT, "bench.py")).read()
-    for k in GPU_ARM_KEYS | {"traffic", "frac", "peak", "achieved", "bound", "h2d_bytes_per_step", "d2h_bytes_per_step", "sm_mhz"}:
+    for k in GPU_ARM_KEYS | {"traffic", "frac", "peak", "achieved", "bound", "h2d_bytes_per_step", "d2h_bytes_per_step", "sm_mhz",
+                             "dram_frac", "lsu_pct", "labels_equal", "forest_equal", "forest_hash"}:
         assert '"%s"' % k in src, k
