@@ -275,16 +275,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def fit_tables(wl, rec, dicts, grp):
-    """R1 StringIndexer.fit for every code column (one pass, one D2H) -> (luts, ordered)."""
+def count_tables(wl, rec, dicts, grp):
+    """R1 StringIndexer.fit, counting half: enqueue the category counts of every code column (one pass) -> device tensors."""
     from b200flow import dist as bdist, encode as enc
     cols = wl.count_cols()
-    counts = [bdist.all_reduce_sum_(t, grp) for t in enc.category_counts_multi(rec, wl.schema, cols, [len(dicts[c]) for c in cols])]
-    host_counts = torch.cat(counts).cpu().numpy()
-    luts, ordered, o = {}, {}, 0
-    for c, cnt in zip(cols, counts):
-        ordered[c], luts[c] = enc.string_index_order(host_counts[o:o + cnt.numel()], dicts[c]); o += cnt.numel()
+    return [bdist.all_reduce_sum_(t, grp) for t in enc.category_counts_multi(rec, wl.schema, cols, [len(dicts[c]) for c in cols])]
+
+
+def order_tables(wl, dicts, host_counts):
+    """R1, ordering half (host, <= 70 entries per column): frequencyDesc ranks -> (luts, ordered)."""
+    from b200flow import encode as enc
+    luts, ordered = {}, {}
+    for c, cnt in zip(wl.count_cols(), host_counts):
+        ordered[c], luts[c] = enc.string_index_order(np.asarray(cnt), dicts[c])
     return luts, ordered
+
+
+def fit_tables(wl, rec, dicts, grp):
+    return order_tables(wl, dicts, [t.cpu().numpy() for t in count_tables(wl, rec, dicts, grp)])
 
 
 def step_resident(wl, rec, dicts, a, grp, keep=None):
@@ -292,19 +300,21 @@ def step_resident(wl, rec, dicts, a, grp, keep=None):
     from b200flow import dist as bdist, forest as fr, rows
     dev = rec.device
     n = rec.shape[0]
-    luts, ordered = fit_tables(wl, rec, dicts, grp)                                 # R1
-    plan = wl.plan(luts)
-    arity = wl.arity(ordered)
-    C = len(ordered[wl.label_col])
+    counts = count_tables(wl, rec, dicts, grp)                                      # R1 (enqueued; read below)
     p = fr.ForestParams(num_trees=a.trees, max_depth=a.depth, max_bins=a.max_bins, seed=2019)
     off, _ = bdist.global_offset(n, dev, grp)
     sid = rows.random_split_ids(n, [0.75, 0.25], 2019, off, dev)                    # randomSplit (kdd99.py:52)
     if a.path == "records":
-        (([rtr], ntr), ([rte], nte)) = rows.split_many([rec], sid, 2)               # raw records only: 75/25 compaction
+        # raw records only: 75/25 compaction; the category counts travel in the same device->host copy as the split sizes
+        (([rtr], ntr), ([rte], nte)), host_counts = rows.split_many([rec], sid, 2, fetch=counts)
+        luts, ordered = order_tables(wl, dicts, [h.numpy() for h in host_counts])
+        plan, arity, C = wl.plan(luts), wl.arity(ordered), len(ordered[wl.label_col])
         toff, _ = bdist.global_offset(ntr, dev, grp)
         model = fr.fit_forest_records(rtr, plan, C, arity, p, row_offset=toff, group=grp)       # R2-R8, fused encode->bins
         raw, prob, pred, yte = model.predict_records(rte, plan, want_label=True)                # R9
     else:
+        luts, ordered = order_tables(wl, dicts, [t.cpu().numpy() for t in counts])
+        plan, arity, C = wl.plan(luts), wl.arity(ordered), len(ordered[wl.label_col])
         x, y, _ = plan.run(rec, torch.float32 if a.dtype == "f32" else torch.float64, want_valid=False)   # R2+R3 fused encode
         ((xtr, ytr), ntr), ((xte, yte), nte) = rows.split_many([x, y], sid, 2)
         del x, y
@@ -533,7 +543,7 @@ def main():
             "train_levels": stats["levels"], "bagged_entries": stats["entries"],
             "train_rows": stats.get("rows"), "unique_binned_rows": stats.get("unique_rows"),
             "route_chunk": stats.get("route_chunk"), "route_passes": stats.get("route_passes"),
-            "level_exchange_ms": stats.get("exchange_ms"),
+            "level_exchange_ms": kern.get("level_exchange", {}).get("ms_per_step"),   # collectives of the level loop (the sharded scoring of the reduce-scatter path runs inside this window)
             "clocks": sampler.summary() if sampler else None, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "kernels": kern, "cpu_baseline": cpu}
     print(json.dumps(line))

@@ -114,6 +114,8 @@ int b200flow_encode_bins(const void* records, int64_t n_rows, int32_t row_bytes,
                          const b200flow_slot* plan, int32_t F, const int32_t* lut, int32_t lut_total,
                          int32_t label_off, int32_t label_lut_off, int32_t label_lut_len,
                          int32_t check_nan, int32_t round_f32,
+                         int32_t thr_f32 /* != 0: every continuous slot's value is exactly a float (f32 field with mean 0 / scale 1, or
+                                            round_f32): the search then runs on thresholds rounded DOWN to float — the same bins */,
                          const double* thresholds, const int32_t* n_thr, const int32_t* arity, int32_t max_bins,
                          uint8_t* tp, int32_t tp_stride, int32_t* label_out, int32_t* bad, void* stream);
 

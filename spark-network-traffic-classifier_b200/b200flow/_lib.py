@@ -40,7 +40,7 @@ _SIGNATURES = {
     "b200flow_category_counts_multi": [_P, _I64, _I32, _I32, _P, _P, _P, _P],
     "b200flow_encode": [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P],
     "b200flow_sample_records": [_P, _I64, _I32, _P, _I32, _P, _I32, _U64, _U64, _I64, _P, _I64, _P, _P],
-    "b200flow_encode_bins": [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _I32, _P, _P, _P],
+    "b200flow_encode_bins": [_P, _I64, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _I32, _P, _P, _P],
     "b200flow_column_moments": [_P, _I32, _I64, _I32, _I64, _P, _P, _P, _P],
     "b200flow_sample_rows": [_P, _I32, _I64, _I32, _I64, _U64, _U64, _I64, _P, _I64, _P, _P],
     "b200flow_find_splits": [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P],

@@ -18,8 +18,8 @@ import torch
 from . import _lib
 from ._lib import NODE_DTYPE, SPLIT_DTYPE, B200FlowError, UnsupportedParamError, call, ptr
 
-CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_level (<= 2048)
 import os as _os
+CHUNK_ROWS = 2048                  # entries per CTA in hist_level / partition_level (<= 2048)
 FUSED = True                       # use route_hist_level (partition + next-level histogram in one pass) when it fits
 TOP_LEVELS = int(_os.environ.get("B200FLOW_TOP_LEVELS", "8"))   # tree levels the predict kernel walks in shared memory (0 = none)
 DEDUP = True                       # run the level loop on unique binned records (flow records repeat massively)
@@ -45,11 +45,12 @@ def profile_totals():
             if not k.startswith("_")}
 
 
-HIST_BUDGET_BYTES = 4 << 30        # node-group cap for the histogram buffer (MLlib: maxMemoryInMB)
+HIST_BUDGET_BYTES = int(_os.environ.get("B200FLOW_HIST_BUDGET_GB", "24")) << 30   # cap of one level's histogram buffer (MLlib: maxMemoryInMB); beyond it the level is processed in node groups by the unfused kernels
 # Multi-GPU: level histograms of at least this many bytes are REDUCE-SCATTERED by node (each rank then scores only its own
 # nodes and the 64-byte split records are all-gathered) instead of all-reduced: half the NVLink bytes, 1/world of the scoring.
 # Smaller levels are latency-bound and keep the single all-reduce.
 RS_MIN_BYTES = int(_os.environ.get("B200FLOW_RS_MIN_BYTES", str(8 << 20)))
+RS_CHUNKS = int(_os.environ.get("B200FLOW_RS_CHUNKS", "4"))   # slot ranges per level whose reduce-scatter overlaps the scoring of the previous range
 
 
 @dataclass
@@ -185,6 +186,13 @@ class _RecordSource:
         self.device = rec.device
         self.with_label = with_label and plan.label is not None
 
+    def _thr_f32(self, arity_dev):
+        """1 when every slot's value is exactly a float (f32 fields / ranks / one-hot flags unscaled, or an f32 matrix being
+        emulated): the fused kernel may then search float thresholds (rounded down) — the same bins, half the bytes."""
+        if self.round_f32:
+            return 1
+        return 1 if all(s[0] in (_lib.SRC_F32, _lib.SRC_INDEX, _lib.SRC_ONEHOT) and s[5] == 0.0 and s[6] == 1.0 for s in self.plan.slots) else 0
+
     def sample(self, seed, keep, row_offset, sample, cap, n_s_dev):
         _, slots, lut_t, _ = self.plan._device_tables(self.device)
         call("b200flow_sample_records", ptr(self.rec), self.n, self.plan.schema.row_bytes, ptr(slots), self.F, ptr(lut_t), self.round_f32,
@@ -197,7 +205,7 @@ class _RecordSource:
         loff, llo, lln = self.plan.label if self.with_label else (-1, 0, 0)
         lab = torch.empty(self.n, dtype=torch.int32, device=self.device) if (want_label_out and self.with_label) else None
         _timed("encode_bins", "b200flow_encode_bins", ptr(self.rec), self.n, self.plan.schema.row_bytes, ptr(slots), self.F, ptr(lut_t), lut_total,
-               loff, llo, lln, int(self.plan.check_nan), self.round_f32, ptr(thresholds), ptr(n_thr), ptr(arity_dev), mpb, ptr(tp), stride,
+               loff, llo, lln, int(self.plan.check_nan), self.round_f32, self._thr_f32(arity_dev), ptr(thresholds), ptr(n_thr), ptr(arity_dev), mpb, ptr(tp), stride,
                ptr(lab), ptr(bad))
         return tp, lab
 
@@ -420,45 +428,12 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
         tp, uid, u_dev = dedup_rows(tp, F + 1, sync=False)
     else:
         uid, u_dev = None, torch.full((1,), n, dtype=torch.int64, device=dev)
-    head = torch.cat([bad.to(torch.int64), feat_bins.max().reshape(1).to(torch.int64), n_s_dev.to(torch.int64), u_dev]).cpu()
-    if int(head[1]) != 0:
-        raise InvalidRowsError("%d NaN/null cells or unseen labels in the training rows" % int(head[1]))
-    if int(head[0]) != 0:
-        raise ValueError("categorical feature value outside [0, arity) or non-integral in %d cells" % int(head[0]))
-    if has_cont and group is None and int(head[3]) > cap:
-        raise B200FlowError("findSplits sample overflow (%d > %d)" % (int(head[3]), cap))
-    n_bins, U = int(head[2]), int(head[4])
-    if dedup:
-        tp = tp[:U]
-    # ---- R6 bagging: W[tree][unique] = summed Poisson weights; entries = non-zero (unique, weight) pairs per tree
+    # host-side preparation that does not depend on the counts runs BEFORE the read, while the GPU works through the queue
     bagging = p.bootstrap and T > 1
     cdf_host = np.ascontiguousarray(poisson_cdf_table(p.subsampling_rate)) if bagging else None
     cdf = _lib.h2d(cdf_host.view(np.int32), dev) if bagging else None
-    nb = (U + 1023) // 1024
-    W = torch.zeros(max(T * U, 1), dtype=torch.int32, device=dev)
-    if n > 0:
-        perm = uperm = None
-        if uid is not None and bagging and U < n:           # group the rows by unique id: one RED per (warp run, tree)
-            gsize = torch.empty(U, dtype=torch.int32, device=dev); cursor = torch.empty(U, dtype=torch.int32, device=dev)
-            goff = torch.empty(U + 1, dtype=torch.int64, device=dev)
-            perm = torch.empty(n, dtype=torch.int32, device=dev); uperm = torch.empty(n, dtype=torch.int32, device=dev)
-            _timed("group_rows", "b200flow_group_rows", ptr(uid), n, U, ptr(gsize), ptr(goff), ptr(cursor), ptr(perm), ptr(uperm))
-        _timed("bag_weights", "b200flow_bag_weights", seed, T, int(row_offset), n, ptr(cdf),
-               cdf_host.ctypes.data if bagging else None, ptr(uperm if perm is not None else uid), ptr(perm), U, ptr(W))
-    blk_cnt = torch.zeros(max(T * nb, 1), dtype=torch.int32, device=dev)
-    blk_off = torch.zeros(T * nb + 1, dtype=torch.int64, device=dev)
-    if U > 0:
-        call("b200flow_bag_count", ptr(W), T, U, ptr(blk_cnt))
-    call("b200flow_exclusive_scan_i32_to_i64", ptr(blk_cnt), T * nb, ptr(blk_off), ptr(total))
-    E = int(total.item())
-    ent = torch.empty((max(E, 1), 2), dtype=torch.int32, device=dev)     # {unique record index, weight}
-    ent2 = torch.empty_like(ent)
-    if U > 0:
-        call("b200flow_bag_fill", ptr(W), T, U, ptr(blk_off), ptr(ent))
-    del W, uid
-
-    # ---- node pool
-    cap_nodes = max(4096, 4 * T)
+    # node pool
+    cap_nodes = max(4096, 4 * T, min(T << (min(p.max_depth, 18) + 1), 1 << 20))   # sized so that typical forests never re-allocate
     nodes = torch.zeros((cap_nodes, 16), dtype=torch.uint8, device=dev)
     use_mask = bool((kind > 0).any())
     node_mask = torch.zeros((cap_nodes, 4), dtype=torch.int64, device=dev) if use_mask else None
@@ -486,6 +461,40 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
         if node_mask is not None:
             node_mask = ext(node_mask, (4,))
         cap_nodes = new_cap
+
+    head = torch.cat([bad.to(torch.int64), feat_bins.max().reshape(1).to(torch.int64), n_s_dev.to(torch.int64), u_dev]).cpu()
+    if int(head[1]) != 0:
+        raise InvalidRowsError("%d NaN/null cells or unseen labels in the training rows" % int(head[1]))
+    if int(head[0]) != 0:
+        raise ValueError("categorical feature value outside [0, arity) or non-integral in %d cells" % int(head[0]))
+    if has_cont and group is None and int(head[3]) > cap:
+        raise B200FlowError("findSplits sample overflow (%d > %d)" % (int(head[3]), cap))
+    n_bins, U = int(head[2]), int(head[4])
+    if dedup:
+        tp = tp[:U]
+    # ---- R6 bagging: W[tree][unique] = summed Poisson weights; entries = non-zero (unique, weight) pairs per tree
+    nb = (U + 1023) // 1024
+    W = torch.zeros(max(T * U, 1), dtype=torch.int32, device=dev)
+    if n > 0:
+        perm = uperm = None
+        if uid is not None and bagging and U < n:           # group the rows by unique id: one RED per (warp run, tree)
+            gsize = torch.empty(U, dtype=torch.int32, device=dev); cursor = torch.empty(U, dtype=torch.int32, device=dev)
+            goff = torch.empty(U + 1, dtype=torch.int64, device=dev)
+            perm = torch.empty(n, dtype=torch.int32, device=dev); uperm = torch.empty(n, dtype=torch.int32, device=dev)
+            _timed("group_rows", "b200flow_group_rows", ptr(uid), n, U, ptr(gsize), ptr(goff), ptr(cursor), ptr(perm), ptr(uperm))
+        _timed("bag_weights", "b200flow_bag_weights", seed, T, int(row_offset), n, ptr(cdf),
+               cdf_host.ctypes.data if bagging else None, ptr(uperm if perm is not None else uid), ptr(perm), U, ptr(W))
+    blk_cnt = torch.zeros(max(T * nb, 1), dtype=torch.int32, device=dev)
+    blk_off = torch.zeros(T * nb + 1, dtype=torch.int64, device=dev)
+    if U > 0:
+        call("b200flow_bag_count", ptr(W), T, U, ptr(blk_cnt))
+    call("b200flow_exclusive_scan_i32_to_i64", ptr(blk_cnt), T * nb, ptr(blk_off), ptr(total))
+    E = int(total.item())
+    ent = torch.empty((max(E, 1), 2), dtype=torch.int32, device=dev)     # {unique record index, weight}
+    ent2 = torch.empty_like(ent)
+    if U > 0:
+        call("b200flow_bag_fill", ptr(W), T, U, ptr(blk_off), ptr(ent))
+    del W, uid
 
     # ---- level 0 slots: one per tree
     slot_tree = torch.arange(T, dtype=torch.int32, device=dev)
@@ -538,23 +547,45 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
 
     def score_sharded(h_full, gs, sub, lvl, split_, nc_, lc_, rc_):
         """R7r + R8 over `world` ranks: reduce-scatter the level histograms by node block, score this rank's block, all-gather
-        the results.  h_full holds world * per slots (the tail beyond gs is zero padding)."""
-        per = -(-gs // world)
-        mine = torch.empty(per * hsz, dtype=torch.int32, device=dev)
-        dist.reduce_scatter_tensor(mine, h_full[:world * per * hsz], group=group)
-        lo = rank * per
-        cnt = max(0, min(per, gs - lo))
-        local = torch.empty(per * REC, dtype=torch.uint8, device=dev)
-        sec = [local[:per * 64], local[per * 64:per * (64 + 4 * C)], local[per * (64 + 4 * C):per * (64 + 8 * C)], local[per * (64 + 8 * C):]]
-        if cnt > 0:
-            _timed("score_level", "b200flow_score_level", ptr(mine), cnt, ptr(sub[lo:lo + cnt]), m, n_bins, C, ptr(feat_bins), ptr(feat_kind),
-                   lvl, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(sec[0]), ptr(sec[1]), ptr(sec[2]), ptr(sec[3]))
-        gathered = torch.empty((world, per * REC), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(gathered, local, group=group)
-        o = 0
-        for dst, width in ((split_, 64), (nc_.view(torch.uint8), 4 * C), (lc_.view(torch.uint8), 4 * C), (rc_.view(torch.uint8), 4 * C)):
-            dst.view(-1)[:world * per * width].view(world, per * width).copy_(gathered[:, o:o + per * width])
-            o += per * width
+        the results.  The level is cut into RS_CHUNKS slot ranges whose reduce-scatters are all enqueued first (NCCL's own
+        stream), so chunk k is scored while chunk k+1 is still on the wire; the 64 + 12 C byte results travel back in one
+        asynchronous all-gather per chunk.  h_full holds the level's slots + world - 1 slots of zero padding."""
+        K = int(max(1, min(RS_CHUNKS, gs, (gs * hsz * 4) // max(RS_MIN_BYTES, 1))))
+        bounds = [gs * i // K for i in range(K + 1)]
+        ev0 = None
+        if PROFILE is not None:
+            ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
+        jobs = []
+        for k in range(K):
+            s0, g = bounds[k], bounds[k + 1] - bounds[k]
+            per = -(-g // world)
+            mine = torch.empty(per * hsz, dtype=torch.int32, device=dev)
+            # rank r reduces slots [s0 + r * per, s0 + (r + 1) * per); whatever lies beyond the chunk's g slots is ignored
+            w = dist.reduce_scatter_tensor(mine, h_full[s0 * hsz:(s0 + world * per) * hsz], group=group, async_op=True)
+            jobs.append((s0, g, per, mine, w))
+        gathers = []
+        for s0, g, per, mine, w in jobs:
+            w.wait()
+            lo = rank * per
+            cnt = max(0, min(per, g - lo))
+            local = torch.empty(per * REC, dtype=torch.uint8, device=dev)
+            sec = [local[:per * 64], local[per * 64:per * (64 + 4 * C)], local[per * (64 + 4 * C):per * (64 + 8 * C)], local[per * (64 + 8 * C):]]
+            if cnt > 0:
+                _timed("score_level", "b200flow_score_level", ptr(mine), cnt, ptr(sub[s0 + lo:s0 + lo + cnt]), m, n_bins, C, ptr(feat_bins),
+                       ptr(feat_kind), lvl, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(sec[0]), ptr(sec[1]),
+                       ptr(sec[2]), ptr(sec[3]))
+            gathered = torch.empty((world, per * REC), dtype=torch.uint8, device=dev)
+            gw = dist.all_gather_into_tensor(gathered, local, group=group, async_op=True)
+            gathers.append((s0, per, gathered, gw))
+        for s0, per, gathered, gw in gathers:               # in chunk order: a chunk's padded tail is overwritten by its successor
+            gw.wait()
+            o = 0
+            for dst, width in ((split_, 64), (nc_.view(torch.uint8), 4 * C), (lc_.view(torch.uint8), 4 * C), (rc_.view(torch.uint8), 4 * C)):
+                dst.view(-1)[s0 * width:(s0 + world * per) * width].view(world, per * width).copy_(gathered[:, o:o + per * width])
+                o += per * width
+        if ev0 is not None:
+            ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+            PROFILE.setdefault("level_exchange", []).append((ev0, ev1))
 
     def run_route(roff, rch_dev, n_parents, split_, child_slot_, cursors_, next_subset_, n_next_cap, route=True):
         """fused pass: route the entries of the planned parent slots to their children and build the children's histograms
@@ -621,7 +652,12 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
                 del h
                 continue
             if group is not None:                       # R7r: the one data-path collective
+                if PROFILE is not None:
+                    ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
                 dist.all_reduce(h, group=group)
+                if PROFILE is not None:
+                    ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+                    PROFILE.setdefault("level_exchange", []).append((ev0, ev1))
             # R8 HOT LOOP B
             _timed("score_level", "b200flow_score_level", ptr(h), gs, ptr(subset[g0:g1]), m, n_bins, C, ptr(feat_bins), ptr(feat_kind),
                    level, p.max_depth, int(p.min_instances_per_node), float(p.min_info_gain), ptr(split[g0:g1]),

@@ -50,12 +50,22 @@ def compact_many(bufs, flag):
     return [o[:k] for o in outs], k
 
 
-def split_many(bufs, split_id, n_splits):
+def split_many(bufs, split_id, n_splits, fetch=None):
     """randomSplit's row movement: the rows of every split, for every buffer, with ONE host sync for all the kept counts.
-    -> [(list of compacted tensors, count)] per split."""
+    -> [(list of compacted tensors, count)] per split.  `fetch`: extra device tensors read in the SAME device->host copy
+    (e.g. pending category counts): -> (splits, [host tensors])."""
     n = split_id.shape[0]
     if n == 0 or not bufs:
-        return [compact_many(bufs, split_id == k) for k in range(n_splits)]
+        out = [compact_many(bufs, split_id == k) for k in range(n_splits)]
+        return out if fetch is None else (out, [t.cpu() for t in fetch])
     parts = [_compact_enqueue(bufs, split_id == k) for k in range(n_splits)]
-    counts = torch.cat([kept for _, kept in parts]).cpu().tolist()
-    return [([o[:int(c)] for o in outs], int(c)) for (outs, _), c in zip(parts, counts)]
+    flat = [kept for _, kept in parts] + [t.reshape(-1).to(torch.int64) for t in (fetch or [])]
+    host = torch.cat(flat).cpu()
+    counts = host[:n_splits].tolist()
+    out = [([o[:int(c)] for o in outs], int(c)) for (outs, _), c in zip(parts, counts)]
+    if fetch is None:
+        return out
+    extra, o = [], n_splits
+    for t in fetch:
+        extra.append(host[o:o + t.numel()]); o += t.numel()
+    return out, extra

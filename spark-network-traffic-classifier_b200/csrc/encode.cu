@@ -345,17 +345,24 @@ struct EncodeBinsArgs {
     int R; int in_stride;
 };
 
-constexpr int kBinThreads = 256;
+constexpr int kBinMaxThreads = 512;
 
-// Persistent CTAs; per tile of R records (one TMA bulk load, 3-deep ring): a WARP owns a feature for 32 rows at a time, so
-// the slot descriptor, the arity and the threshold array are warp-uniform — the lower_bound search of the first steps hits
-// one or two shared-memory words per step (broadcast) instead of 32 different arrays — and feature trip counts do not
-// diverge.  Bins land in a padded byte tile (row pitch = stride + 4 bytes: conflict-free byte stores across rows), which
-// the whole CTA then streams out as 16-byte words; the tile is double-buffered, so there is ONE barrier per tile.
-__global__ void __launch_bounds__(kBinThreads) encode_bins_kernel(const EncodeBinsArgs a) {
+// Persistent CTAs; per tile of R = 32 * RPL records (one TMA bulk load, 3-deep ring): a WARP owns a feature for the whole
+// tile, so the slot descriptor, the arity and the threshold array are warp-uniform — the first steps of the search hit one
+// or two shared-memory words per step (broadcast) instead of 32 different arrays — and trip counts do not diverge; every lane
+// runs RPL independent searches side by side (ILP hides the dependent shared-memory loads).
+// lower_bound (first b with v <= thr[b]) is the branch-free power-of-two descent  pos += st  while  !(v <= thr[pos + st - 1]):
+// four instructions per step.  TT = float when every continuous value is exactly a float (f32 fields, identity scaling, or
+// an f32 feature matrix being emulated): thresholds are rounded DOWN to float once, and  v <= thr  <=>  v <= rd(thr)  for
+// every float v — the same bins as the fp64 compare, at half the shared-memory bytes; TT = double otherwise.
+// Bins land in a padded byte tile (row pitch = stride + 4 bytes: conflict-free byte stores across rows), which the whole CTA
+// then streams out as 16-byte words; the tile is double-buffered, so there is ONE barrier per tile.
+template <int RPL, typename TT>
+__global__ void __launch_bounds__(kBinMaxThreads) encode_bins_kernel(const EncodeBinsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, lane = lane_id(), wid = warp_id(), nw = kBinThreads / 32;
-    const int R = a.R, F = a.F, row_bytes = a.row_bytes, ns = a.max_bins - 1, stride = a.stride, pitch = stride + 4;
+    constexpr int R = 32 * RPL;
+    const int tid = threadIdx.x, bd = blockDim.x, lane = lane_id(), wid = warp_id(), nw = bd / 32;
+    const int F = a.F, row_bytes = a.row_bytes, ns = a.max_bins - 1, stride = a.stride, pitch = stride + 4;
     uint8_t* in_base = smem;
     uint8_t* out_base = in_base + (size_t)kEncStages * a.in_stride;                 // [2][R][pitch]
     uint64_t* mbar = (uint64_t*)(out_base + (((size_t)2 * R * pitch + 7) & ~(size_t)7));
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(kBinThreads) encode_bins_kernel(const EncodeBi
     int32_t* nthr_sh = (int32_t*)(plan_sh + F);
     int32_t* arity_sh = nthr_sh + F;
     int32_t* lut_sh = arity_sh + F;
-    double* thr_sh = (double*)(((uintptr_t)(lut_sh + (a.lut_in_smem ? a.lut_total : 0)) + 7) & ~(uintptr_t)7);
+    TT* thr_sh = (TT*)(((uintptr_t)(lut_sh + (a.lut_in_smem ? a.lut_total : 0)) + 7) & ~(uintptr_t)7);
     const int64_t n_tiles = (a.n_rows + R - 1) / R;
     const uint32_t tile_in_bytes = (uint32_t)R * row_bytes;
 
@@ -371,14 +378,17 @@ __global__ void __launch_bounds__(kBinThreads) encode_bins_kernel(const EncodeBi
         for (int s = 0; s < kEncStages; ++s) mbar_init(&mbar[s], 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < F * (int)(sizeof(b200flow_slot) / 4); i += kBinThreads) ((uint32_t*)plan_sh)[i] = ((const uint32_t*)a.plan)[i];
-    for (int i = tid; i < F; i += kBinThreads) { nthr_sh[i] = a.n_thr[i]; arity_sh[i] = a.arity[i]; }
-    if (a.lut_in_smem) for (int i = tid; i < a.lut_total; i += kBinThreads) lut_sh[i] = a.lut[i];
-    if (a.thr_in_smem) for (int i = tid; i < F * ns; i += kBinThreads) thr_sh[i] = a.thresholds[i];
-    for (int i = tid; i < 2 * R * pitch / 4; i += kBinThreads) ((uint32_t*)out_base)[i] = 0;      // pad bytes stay zero for ever
+    for (int i = tid; i < F * (int)(sizeof(b200flow_slot) / 4); i += bd) ((uint32_t*)plan_sh)[i] = ((const uint32_t*)a.plan)[i];
+    for (int i = tid; i < F; i += bd) { nthr_sh[i] = a.n_thr[i]; arity_sh[i] = a.arity[i]; }
+    if (a.lut_in_smem) for (int i = tid; i < a.lut_total; i += bd) lut_sh[i] = a.lut[i];
+    if (a.thr_in_smem)
+        for (int i = tid; i < F * ns; i += bd) {
+            if (sizeof(TT) == 4) ((float*)thr_sh)[i] = __double2float_rd(a.thresholds[i]);
+            else ((double*)thr_sh)[i] = a.thresholds[i];
+        }
+    for (int i = tid; i < 2 * R * pitch / 4; i += bd) ((uint32_t*)out_base)[i] = 0;      // pad bytes stay zero for ever
     __syncthreads();
     const int32_t* lut = a.lut_in_smem ? lut_sh : a.lut;
-    const double* thr_all = a.thr_in_smem ? thr_sh : a.thresholds;
 
     auto issue_load = [&](int64_t tile, int s) {
         if (a.n_rows - tile * R >= R) {
@@ -398,18 +408,22 @@ __global__ void __launch_bounds__(kBinThreads) encode_bins_kernel(const EncodeBi
         const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
         const int64_t row_base = tile * R;
         const int rows = (int)min((int64_t)R, a.n_rows - row_base);
-        const uint8_t* in_t = in_base + (size_t)s * a.in_stride;
+        uint8_t* in_t = in_base + (size_t)s * a.in_stride;
         uint8_t* out_t = out_base + (size_t)(it & 1) * R * pitch;
         mbar_wait(&mbar[s], ph);
         if (rows < R) {
             const uint32_t* src = (const uint32_t*)(a.records + row_base * row_bytes);
-            for (int i = tid; i < rows * row_bytes / 4; i += kBinThreads) ((uint32_t*)in_t)[i] = __ldg(src + i);
+            for (int i = tid; i < rows * row_bytes / 4; i += bd) ((uint32_t*)in_t)[i] = __ldg(src + i);
+            for (int i = rows * row_bytes / 4 + tid; i < R * row_bytes / 4; i += bd) ((uint32_t*)in_t)[i] = 0;   // rows past the end: defined, never stored
             __syncthreads();
         }
         for (int f = wid; f <= F; f += nw) {                // task F = the label column
             if (f == F) {
                 if (a.label_off < 0) continue;
-                for (int r = lane; r < rows; r += 32) {
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int r = lane + 32 * q;
+                    if (r >= rows) continue;
                     const int code = *(const int32_t*)(in_t + r * row_bytes + a.label_off);
                     const int rank = (code >= 0 && code < a.label_lut_len) ? lut[a.label_lut_off + code] : -1;
                     if (rank < 0) ++n_inv;
@@ -420,35 +434,64 @@ __global__ void __launch_bounds__(kBinThreads) encode_bins_kernel(const EncodeBi
             }
             const b200flow_slot sl = plan_sh[f];
             const int ar = arity_sh[f], nt = nthr_sh[f];
-            const double* thr = thr_all + (int64_t)f * ns;
-            const int steps = 32 - __clz(nt);              // ceil(log2(nt + 1)) iterations settle lower_bound over nt thresholds
-            for (int r = lane; r < rows; r += 32) {
-                bool inv = false, nan = false;
-                const double v = slot_value(in_t + r * row_bytes, sl, lut, a.round_f32, &inv, &nan);
-                if (inv || (a.check_nan && nan)) ++n_inv;
-                int b;
-                if (ar > 0) {
-                    b = (int)v;
-                    if (!((double)b == v) || b < 0 || b >= ar) { b = ar < 255 ? ar : 255; ++n_bad; }   // never inside a left-set mask
-                } else {
-                    int lo = 0, hi = nt;                    // lower_bound: first b with v <= thr[b] (branch-free, uniform trip count)
-                    for (int k = 0; k < steps; ++k) {
-                        const int mid = (lo + hi) >> 1;
-                        const bool open = lo < hi;
-                        const bool le = open && v <= thr[open ? mid : 0];
-                        hi = le ? mid : hi;
-                        lo = (open && !le) ? mid + 1 : lo;
-                    }
-                    b = lo;
+            int b[RPL];
+            if (ar > 0 || sizeof(TT) == 8 || sl.kind != B200FLOW_SRC_F32) {
+                double v[RPL];
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    bool inv = false, nan = false;
+                    const int r = lane + 32 * q;
+                    v[q] = slot_value(in_t + r * row_bytes, sl, lut, a.round_f32, &inv, &nan);
+                    if (r < rows && (inv || (a.check_nan && nan))) ++n_inv;
                 }
-                out_t[r * pitch + f] = (uint8_t)b;
+                if (ar > 0) {
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) {
+                        b[q] = (int)v[q];
+                        if (!((double)b[q] == v[q]) || b[q] < 0 || b[q] >= ar) { b[q] = ar < 255 ? ar : 255; if (lane + 32 * q < rows) ++n_bad; }   // never inside a left-set mask
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) b[q] = 0;
+                    if (sizeof(TT) == 8) {
+                        const double* thr = (a.thr_in_smem ? (const double*)thr_sh : a.thresholds) + (int64_t)f * ns;
+                        for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {
+#pragma unroll
+                            for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; if (i < nt && !(v[q] <= thr[i])) b[q] += st; }
+                        }
+                    } else {                                // float table, non-f32 source whose value an f32 matrix would have held
+                        const float* thr = (const float*)thr_sh + (int64_t)f * ns;
+                        for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {
+#pragma unroll
+                            for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; if (i < nt && !((float)v[q] <= thr[i])) b[q] += st; }
+                        }
+                    }
+                }
+            } else {                                        // f32 field, float thresholds: no fp64 at all
+                const float* thr = (const float*)thr_sh + (int64_t)f * ns;
+                const bool ident = sl.mean == 0.0 && sl.scale == 1.0;
+                float v[RPL];
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    const int r = lane + 32 * q;
+                    v[q] = *(const float*)(in_t + r * row_bytes + sl.src_off);
+                    if (a.check_nan && r < rows && v[q] != v[q]) ++n_inv;
+                    if (!ident) v[q] = (float)(((double)v[q] - sl.mean) * sl.scale);      // round_f32 mode: the f32 matrix value
+                    b[q] = 0;
+                }
+                for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; if (i < nt && !(v[q] <= thr[i])) b[q] += st; }
+                }
             }
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) out_t[(lane + 32 * q) * pitch + f] = (uint8_t)b[q];
         }
         __syncthreads();                                    // tile binned; input stage s consumed
         if (tid == 0) { const int64_t next = tile + (int64_t)kEncStages * gridDim.x; if (next < n_tiles) issue_load(next, s); }
         const int q16 = stride / 16;
         uint4* dst = (uint4*)(a.tp + row_base * stride);
-        for (int i = tid; i < rows * q16; i += kBinThreads) {
+        for (int i = tid; i < rows * q16; i += bd) {
             const int r = i / q16, q = i - r * q16;
             const uint32_t* w = (const uint32_t*)(out_t + r * pitch + q * 16);
             st_stream_u4(dst + i, make_uint4(w[0], w[1], w[2], w[3]));
@@ -605,7 +648,7 @@ extern "C" int b200flow_sample_records(const void* records, int64_t n_rows, int3
 
 extern "C" int b200flow_encode_bins(const void* records, int64_t n_rows, int32_t row_bytes, const b200flow_slot* plan, int32_t F,
                                     const int32_t* lut, int32_t lut_total, int32_t label_off, int32_t label_lut_off,
-                                    int32_t label_lut_len, int32_t check_nan, int32_t round_f32, const double* thresholds,
+                                    int32_t label_lut_len, int32_t check_nan, int32_t round_f32, int32_t thr_f32, const double* thresholds,
                                     const int32_t* n_thr, const int32_t* arity, int32_t max_bins, uint8_t* tp, int32_t tp_stride,
                                     int32_t* label_out, int32_t* bad, void* stream) {
     if (n_rows <= 0) return B200FLOW_OK;
@@ -620,29 +663,41 @@ extern "C" int b200flow_encode_bins(const void* records, int64_t n_rows, int32_t
     a.label_off = label_off; a.label_lut_off = label_lut_off; a.label_lut_len = label_lut_len; a.check_nan = check_nan; a.round_f32 = round_f32;
     a.thresholds = thresholds; a.n_thr = n_thr; a.arity = arity; a.max_bins = max_bins;
     const size_t thr_bytes = (size_t)F * (max_bins - 1) * 8;
-    a.thr_in_smem = thr_bytes <= 96 * 1024 ? 1 : 0;
     a.tp = tp; a.stride = tp_stride; a.label_out = label_out; a.bad = bad;
+    // float thresholds when every continuous value is exactly a float: f32 fields with identity scaling, or the f32 feature
+    // matrix being emulated (round_f32); the plan is a HOST-side fact of the caller, passed as thr_f32
+    const bool f32_table = thr_f32 != 0;
+    const size_t thr_smem = (size_t)F * (max_bins - 1) * (f32_table ? 4 : 8);
+    a.thr_in_smem = (f32_table || thr_smem <= 56 * 1024) ? 1 : 0;   // a double table beyond that stays in global memory (L1 keeps the top levels)
+    B2F_REQUIRE(!f32_table || thr_smem <= 100 * 1024, "encode_bins: float threshold table exceeds shared memory");
     const size_t fixed_bytes = kEncStages * 8 + (size_t)F * sizeof(b200flow_slot) + 8 * (size_t)F + (a.lut_in_smem ? (size_t)a.lut_total * 4 : 0) + 16 +
-                               (a.thr_in_smem ? thr_bytes : 0) + 256;
+                               (a.thr_in_smem ? thr_smem : 0) + 256;
     const size_t per_row = (size_t)row_bytes * kEncStages + 2 * (size_t)(tp_stride + 4);
-    static int budget_kb = -1;                             // tuning knob: per-CTA shared memory target (2 CTAs per SM at ~100 KB)
-    if (budget_kb < 0) { const char* e = getenv("B200FLOW_BINS_SMEM_KB"); budget_kb = e ? atoi(e) : 100; }
+    static int budget_kb = -1;                             // tuning knob: per-CTA shared memory target (2 CTAs per SM at ~110 KB)
+    if (budget_kb < 0) { const char* e = getenv("B200FLOW_BINS_SMEM_KB"); budget_kb = e ? atoi(e) : 110; }
     B2F_REQUIRE(fixed_bytes + 32 * per_row <= 224 * 1024, "encode_bins: record too wide for shared memory (row_bytes=%d F=%d)", row_bytes, F);
-    int R = (int)(((size_t)budget_kb * 1024 > fixed_bytes ? (size_t)budget_kb * 1024 - fixed_bytes : 0) / per_row);
-    R &= ~31;
-    if (R < 32) R = 32;
-    if (R > 1024) R = 1024;
+    int rpl = 4;                                            // rows per lane: the most that fits the budget
+    while (rpl > 1 && fixed_bytes + (size_t)32 * rpl * per_row > (size_t)budget_kb * 1024) rpl >>= 1;
+    const int R = 32 * rpl;
     a.R = R;
     a.in_stride = (R * row_bytes + 127) & ~127;
     const size_t smem = (size_t)kEncStages * a.in_stride + (((size_t)2 * R * (tp_stride + 4) + 7) & ~(size_t)7) + fixed_bytes;
     B2F_REQUIRE(smem <= 227 * 1024, "encode_bins: shared memory budget exceeded");
+    // warps per CTA: F + 1 warp tasks per tile (one per feature + the label); take the count in 12..16 that leaves the fewest idle
+    int nw = 16, best_idle = 1 << 30;
+    for (int w = 16; w >= 12; --w) { const int idle = (F + 1 + w - 1) / w * w - (F + 1); if (idle < best_idle) { best_idle = idle; nw = w; } }
     const int64_t n_tiles = (n_rows + R - 1) / R;
     int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    if (ctas_per_sm > 4) ctas_per_sm = 4;                   // 2048 threads per SM
     const int grid = (int)(n_tiles < (int64_t)kNumSMs * ctas_per_sm ? n_tiles : (int64_t)kNumSMs * ctas_per_sm);
-    cudaError_t e = cudaFuncSetAttribute(encode_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e;
+#define B2F_BINS_LAUNCH(RPL, TT)                                                                                          \
+    e = cudaFuncSetAttribute(encode_bins_kernel<RPL, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    if (e == cudaSuccess) encode_bins_kernel<RPL, TT><<<grid, nw * 32, smem, (cudaStream_t)stream>>>(a);
+    if (f32_table) { if (rpl == 4) { B2F_BINS_LAUNCH(4, float) } else if (rpl == 2) { B2F_BINS_LAUNCH(2, float) } else { B2F_BINS_LAUNCH(1, float) } }
+    else { if (rpl == 4) { B2F_BINS_LAUNCH(4, double) } else if (rpl == 2) { B2F_BINS_LAUNCH(2, double) } else { B2F_BINS_LAUNCH(1, double) } }
+#undef B2F_BINS_LAUNCH
     if (e != cudaSuccess) { set_error("encode_bins: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
-    encode_bins_kernel<<<grid, kBinThreads, smem, (cudaStream_t)stream>>>(a);
     return check_launch("encode_bins");
 }

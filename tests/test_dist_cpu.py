@@ -54,6 +54,34 @@ def test_two_rank_sharding_gloo(tmp_path):
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
 
 
+def _gather_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from b200flow import forest as fr
+        F = 3
+        n_s, cap = (1000, 1024) if rank == 0 else (1050, 2048)      # 1050 > the other rank's capacity
+        col = torch.arange(n_s, dtype=torch.float64) + 10000.0 * rank
+        sample = torch.zeros(F * cap, dtype=torch.float64)
+        for f in range(F):
+            sample.view(F, cap)[f, :n_s] = col + 0.25 * f
+        out, tot, new_cap = fr._gather_sample(sample, n_s, cap, F, dist.group.WORLD)
+        assert tot == 2050 and new_cap == 4096 and out.numel() == F * new_cap
+        got = out.view(F, new_cap)[:, :tot]
+        want0 = torch.cat([torch.arange(1000, dtype=torch.float64), torch.arange(1050, dtype=torch.float64) + 10000.0])
+        for f in range(F):
+            assert torch.equal(got[f], want0 + 0.25 * f)
+        open(os.path.join(out_dir, "g%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_sample_uneven_shards_gloo(tmp_path):
+    # the findSplits sample of every rank is exchanged in blocks of the agreed (widest) width, whatever the local capacity
+    mp.spawn(_gather_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "g0") and os.path.exists(tmp_path / "g1")
+
+
 def test_shard_bounds_cover_everything():
     for n in (0, 1, 7, 1000, 4898431):
         for world in (1, 2, 3, 8):

@@ -40,17 +40,32 @@ def _worker(rank, world, port, out_dir):
         plan.set_label("label", luts["label"])
         x, y, _ = plan.run(shard, torch.float64)
         arity = [0] * 38 + [len(ordered[c]) for c in synth.KDD_CATEGORICAL]
+        C = len(ordered["label"])
         p = fr.ForestParams(num_trees=8, max_bins=70, max_depth=10, seed=2019)
         off, _ = bdist.global_offset(hi - lo, dev)
-        model = fr.fit_forest(x, y, len(ordered["label"]), arity, p, row_offset=off, group=bdist.group())
+        model = fr.fit_forest(x, y, C, arity, p, row_offset=off, group=bdist.group())
         ex = model.export()
         fr.RS_MIN_BYTES = 0            # every level through reduce-scatter -> sharded scoring -> all-gather of the split records
-        ex_rs = fr.fit_forest(x, y, len(ordered["label"]), arity, p, row_offset=off, group=bdist.group()).export()
+        fr.RS_CHUNKS = 3               # ... in three pipelined slot ranges
+        ex_rs = fr.fit_forest(x, y, C, arity, p, row_offset=off, group=bdist.group()).export()
+        fr.RS_MIN_BYTES = 8 << 20
+        # uneven shards (21,000 / 39,000 rows: different findSplits sample capacities per rank) on the fused record path
+        cut = 21000
+        ulo, uhi = (0, cut) if rank == 0 else (cut, n)
+        ushard = rec[ulo:uhi].contiguous()
+        uoff, _ = bdist.global_offset(uhi - ulo, dev)
+        ex_uneven = fr.fit_forest_records(ushard, plan, C, arity, p, row_offset=uoff, group=bdist.group()).export()
+        # one rank without any row: it still takes part in every collective
+        eshard = rec if rank == 0 else rec[:0].contiguous()
+        eoff, _ = bdist.global_offset(eshard.shape[0], dev)
+        ex_empty = fr.fit_forest_records(eshard, plan, C, arity, p, row_offset=eoff, group=bdist.group()).export()
         if rank == 0:
             np.savez(os.path.join(out_dir, "sharded.npz"), **ex)
             np.savez(os.path.join(out_dir, "sharded_rs.npz"), **ex_rs)
+            np.savez(os.path.join(out_dir, "sharded_uneven.npz"), **ex_uneven)
+            np.savez(os.path.join(out_dir, "sharded_empty.npz"), **ex_empty)
             xf, yf, _ = plan.run(rec, torch.float64)
-            single = fr.fit_forest(xf, yf, len(ordered["label"]), arity, p).export()
+            single = fr.fit_forest(xf, yf, C, arity, p).export()
             np.savez(os.path.join(out_dir, "single.npz"), **single)
         dist.barrier()
     finally:
@@ -64,7 +79,12 @@ def test_two_gpu_forest_is_byte_identical_to_one_gpu(tmp_path):
     a, b = np.load(tmp_path / "sharded.npz"), np.load(tmp_path / "single.npz")
     assert sorted(a.files) == sorted(b.files)
     c = np.load(tmp_path / "sharded_rs.npz")
+    d, e = np.load(tmp_path / "sharded_uneven.npz"), np.load(tmp_path / "sharded_empty.npz")
     for k in a.files:
         assert np.array_equal(a[k], b[k]), k
         assert np.array_equal(c[k], b[k]), "reduce-scatter path: " + k
+        assert np.array_equal(d[k], b[k]), "uneven shards, record path: " + k
+        assert np.array_equal(e[k], b[k]), "empty shard: " + k
     assert len(a["nid"]) > 500
+    print("2-GPU forests (all-reduce, pipelined reduce-scatter, uneven shards on the record path, one empty shard) == 1-GPU forest: "
+          "%d nodes, byte-identical" % len(a["nid"]))

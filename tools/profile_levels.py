@@ -5,15 +5,16 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "spark-network-traffic-classifier_b200"))
 import torch, bench
-from b200flow import synth, forest
+from b200flow import forest
 a = bench.parse()
-rec, dicts = synth.make_kdd(a.rows, a.classes, seed=2019, device="cuda")
+wl = bench.Workload(a)
+rec, dicts = wl.make(a.rows, "cuda")
 for _ in range(2):
-    bench.step_resident(rec, dicts, a, None)
+    bench.step_resident(wl, rec, dicts, a, None)
 torch.cuda.synchronize()
 forest.PROFILE = {}
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-t0.record(); bench.step_resident(rec, dicts, a, None); t1.record()
+t0.record(); bench.step_resident(wl, rec, dicts, a, None); t1.record()
 torch.cuda.synchronize()
 P = forest.PROFILE
 print("step %.2f ms (with per-kernel events)" % t0.elapsed_time(t1))

@@ -5,17 +5,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "spark-network-traffic-classifier_b200"))
 import torch, bench
 from torch.profiler import profile, ProfilerActivity
-from b200flow import synth
 E2E = "--shim" in sys.argv
 if E2E:
     sys.argv.remove("--shim")
 a = bench.parse()
-rec, dicts = synth.make_kdd(a.rows, a.classes, seed=2019, device="cuda")
+wl = bench.Workload(a)
+rec, dicts = wl.make(a.rows, "cuda")
 if E2E:                                                  # the pyspark.ml-shaped path from pinned host records
     host = rec.cpu().pin_memory(); del rec
-    step = lambda: bench.step_e2e(host, dicts, a)
+    step = lambda: bench.step_e2e(wl, host, dicts, a)
 else:
-    step = lambda: bench.step_resident(rec, dicts, a, None)
+    step = lambda: bench.step_resident(wl, rec, dicts, a, None)
 for _ in range(3):
     step()
 torch.cuda.synchronize()
