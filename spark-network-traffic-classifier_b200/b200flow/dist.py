@@ -26,15 +26,48 @@ def global_offset(n_local, device, grp=None):
     if grp is None:
         return 0, int(n_local)
     world, rank = dist.get_world_size(grp), dist.get_rank(grp)
-    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([int(n_local)], dtype=torch.int64, device=device), group=grp)
-    counts = [int(c.item()) for c in counts]
+    counts = [int(c.item()) for c in all_gather_list(torch.tensor([int(n_local)], dtype=torch.int64, device=device), grp)]
     return sum(counts[:rank]), sum(counts)
+
+
+def _staged(t, grp):
+    """gloo moves CUDA tensors only for broadcast / all_reduce: everything else (and, for uniformity, those two) is staged
+    through host memory when the group is gloo — the 2-ranks-on-one-GPU tests run the real kernels over a gloo group."""
+    return t.is_cuda and dist.get_backend(grp) == "gloo"
+
+
+def is_nccl(grp):
+    return grp is not None and dist.get_backend(grp) == "nccl"
+
+
+def all_reduce_(t, grp, op=None):
+    """in-place all-reduce (sum by default) on whatever backend the group has."""
+    op = dist.ReduceOp.SUM if op is None else op
+    if _staged(t, grp):
+        c = t.cpu()
+        dist.all_reduce(c, op=op, group=grp)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t, op=op, group=grp)
+    return t
+
+
+def all_gather_list(t, grp):
+    """equal-shape all-gather -> list of tensors (one per rank) on t's device."""
+    world = dist.get_world_size(grp)
+    if _staged(t, grp):
+        c = t.cpu()
+        parts = [torch.empty_like(c) for _ in range(world)]
+        dist.all_gather(parts, c, group=grp)
+        return [p.to(t.device) for p in parts]
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=grp)
+    return parts
 
 
 def all_reduce_sum_(t, grp=None):
     """in-place sum over ranks (integer tensors stay exact -> bit-identical models for any world size)."""
     grp = grp if grp is not None else group()
     if grp is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=grp)
+        all_reduce_(t, grp)
     return t

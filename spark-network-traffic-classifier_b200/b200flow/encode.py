@@ -176,13 +176,14 @@ def column_moments(x, group=None):
     call("b200flow_column_moments", ptr(x), _lib.dtype_code(x), n, D, x.stride(0), None, ptr(buf[:D]), ptr(buf[D:2 * D]))
     buf[2 * D] = float(n)
     if group is not None:
-        dist.all_reduce(buf, group=group)
+        from .dist import all_reduce_
+        all_reduce_(buf, group)
     n_tot = buf[2 * D]
     mean = (buf[:D] / torch.clamp(n_tot, min=1.0)).contiguous()
     buf2 = torch.zeros(2 * D, dtype=torch.float64, device=dev)
     call("b200flow_column_moments", ptr(x), _lib.dtype_code(x), n, D, x.stride(0), ptr(mean), ptr(buf2[:D]), ptr(buf2[D:]))
     if group is not None:
-        dist.all_reduce(buf2, group=group)
+        all_reduce_(buf2, group)
     m2 = buf2[D:] - buf2[:D] * buf2[:D] / torch.clamp(n_tot, min=1.0)
     var = torch.where(n_tot > 1, m2 / torch.clamp(n_tot - 1.0, min=1.0), torch.zeros_like(m2))
     return mean, torch.sqrt(torch.clamp(var, min=0.0))

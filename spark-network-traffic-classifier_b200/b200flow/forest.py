@@ -50,7 +50,8 @@ HIST_BUDGET_BYTES = int(_os.environ.get("B200FLOW_HIST_BUDGET_GB", "24")) << 30 
 # nodes and the 64-byte split records are all-gathered) instead of all-reduced: half the NVLink bytes, 1/world of the scoring.
 # Smaller levels are latency-bound and keep the single all-reduce.
 RS_MIN_BYTES = int(_os.environ.get("B200FLOW_RS_MIN_BYTES", str(8 << 20)))
-RS_CHUNKS = int(_os.environ.get("B200FLOW_RS_CHUNKS", "4"))   # slot ranges per level whose reduce-scatter overlaps the scoring of the previous range
+RS_CHUNKS = int(_os.environ.get("B200FLOW_RS_CHUNKS", "1"))   # slot ranges per level whose reduce-scatter overlaps the scoring of the previous range
+# (measured on 2 x B200, KDD99-full weak scaling: 1 chunk 32.8 ms/step, 4 chunks 37.8 — the extra collectives cost more than the overlap hides)
 
 
 @dataclass
@@ -329,15 +330,13 @@ def _gather_sample(sample, n_s, cap, F, group):
     sample first and exchange (F, mx) blocks padded to that width — local capacities differ when the shards are uneven."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    counts = [torch.zeros(1, dtype=torch.int64, device=sample.device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([n_s], dtype=torch.int64, device=sample.device), group=group)
-    counts = [int(c.item()) for c in counts]
+    from . import dist as bdist
+    counts = [int(c.item()) for c in bdist.all_gather_list(torch.tensor([n_s], dtype=torch.int64, device=sample.device), group)]
     mx = max(max(counts), 1)
     mine = torch.zeros((F, mx), dtype=torch.float64, device=sample.device)
     if n_s > 0:
         mine[:, :n_s] = sample.view(F, cap)[:, :n_s]
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine, group=group)
+    parts = bdist.all_gather_list(mine, group)
     tot = sum(counts)
     new_cap = 1
     while new_cap < max(tot, 2):
@@ -368,6 +367,7 @@ def fit_forest_records(rec, plan, num_classes, arity, params, row_offset=0, grou
 
 def _fit(src, num_classes, arity, params, row_offset=0, group=None):
     import torch.distributed as dist
+    from . import dist as bdist
     _lib.require_cuda()
     p = params
     if p.impurity != "gini":
@@ -384,7 +384,7 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
     n_global = n
     if group is not None:
         t = torch.tensor([n], dtype=torch.int64, device=dev)
-        dist.all_reduce(t, group=group)
+        bdist.all_reduce_(t, group)
         n_global = int(t.item())
     mpb, kind, m = build_metadata(n_global, F, C, arity, p.max_bins, T, p.feature_subset_strategy)
     arity = np.asarray(arity, np.int32)
@@ -472,6 +472,8 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
     n_bins, U = int(head[2]), int(head[4])
     if dedup:
         tp = tp[:U]
+    if tp.shape[0] == 0:                                  # a rank without rows still walks the level loop (its collectives): give the
+        tp = torch.zeros((1, stride), dtype=torch.uint8, device=dev)   # kernels a real pointer (data_ptr() of an empty tensor is NULL)
     # ---- R6 bagging: W[tree][unique] = summed Poisson weights; entries = non-zero (unique, weight) pairs per tree
     nb = (U + 1023) // 1024
     W = torch.zeros(max(T * U, 1), dtype=torch.int32, device=dev)
@@ -544,6 +546,7 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
     world = dist.get_world_size(group) if group is not None else 1
     rank = dist.get_rank(group) if group is not None else 0
     REC = 64 + 12 * C                                    # bytes per slot of the scored result: split record + 3 count vectors
+    use_rs = world > 1 and bdist.is_nccl(group)          # reduce-scatter + sharded scoring needs NCCL (gloo test groups all-reduce)
 
     def score_sharded(h_full, gs, sub, lvl, split_, nc_, lc_, rc_):
         """R7r + R8 over `world` ranks: reduce-scatter the level histograms by node block, score this rank's block, all-gather
@@ -647,14 +650,14 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
                 stats["hist_launches"] += 1
                 if PROFILE is not None:
                     PROFILE.setdefault("_hist_entries", []).append(lens[g0:g1].sum())
-            if group is not None and hist_ready is not None and gs * hsz * 4 >= RS_MIN_BYTES and world > 1:
+            if use_rs and hist_ready is not None and gs * hsz * 4 >= RS_MIN_BYTES:
                 score_sharded(hist_full, gs, subset, level, split, node_counts, left_counts, right_counts)
                 del h
                 continue
             if group is not None:                       # R7r: the one data-path collective
                 if PROFILE is not None:
                     ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
-                dist.all_reduce(h, group=group)
+                bdist.all_reduce_(h, group)
                 if PROFILE is not None:
                     ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
                     PROFILE.setdefault("level_exchange", []).append((ev0, ev1))

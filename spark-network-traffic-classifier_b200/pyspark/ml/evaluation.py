@@ -22,7 +22,7 @@ class MulticlassClassificationEvaluator(Params):
         mx = (torch.maximum(pred.max(), lab.max()) if pred.numel() else torch.zeros((), dtype=torch.float64, device=pred.device)).reshape(1)
         if bdist.group() is not None:
             import torch.distributed as dist
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=bdist.group())
+            bdist.all_reduce_(mx, bdist.group(), op=dist.ReduceOp.MAX)
         C = int(mx.item()) + 1
         return bdist.all_reduce_sum_(fr.confusion_matrix(pred, lab, C)).cpu()
 
