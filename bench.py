@@ -14,6 +14,8 @@ One "step" = one pass of the hot path over the whole record batch:
 `--impl reference`: the CPU arm — the oracle ("port": Spark itself cannot run here, no JVM) on every host thread.
 `--workload`: kdd_full (configs[1], default) | kdd10 (configs[0]) | kdd_script (kdd99.py:64 as written: 23 classes) |
             cicids_wed (configs[2]) | cicids_full (configs[3]) | cicids_script (cicids17.py:68 as written) | stream (configs[4]).
+            The CICIDS workloads take the reference script's forest (20 trees, maxDepth 5, maxBins 78); `--trees 100 --depth 16`
+            gives the configs[1]-sized forest on CICIDS-shaped rows (a stress case: 1.5 M nodes).
 `--scaling`: weak (rows per GPU fixed, default) | strong (the workload's global rows sharded over the ranks; every N prints
             `forest_hash`, equal for every N: integer histograms + global-row-keyed RNG).
 Launch: python bench.py --gpus N --steps K --warmup W   (N>1 under torchrun, one rank per GPU).
@@ -40,8 +42,8 @@ WORKLOADS = {
     "kdd_full": ("kdd", 4898431, 5, 100, 16, 70, "f32", "BASELINE configs[1]"),
     "kdd10": ("kdd", 494021, 2, 20, 5, 70, "f32", "BASELINE configs[0]; RandomForestClassifier(numTrees=20, maxBins=70) kdd99.py:64"),
     "kdd_script": ("kdd", 4898431, 23, 20, 5, 70, "f32", "kdd99.py:64 as written (23 attack labels)"),
-    "cicids_wed": ("cicids", 692703, 6, 100, 16, 78, "f64", "BASELINE configs[2]"),
-    "cicids_full": ("cicids", 2830743, 15, 100, 16, 78, "f64", "BASELINE configs[3]"),
+    "cicids_wed": ("cicids", 692703, 6, 20, 5, 78, "f64", "BASELINE configs[2]; RandomForestClassifier(numTrees=20, maxBins=78) cicids17.py:68"),
+    "cicids_full": ("cicids", 2830743, 15, 20, 5, 78, "f64", "BASELINE configs[3]; RandomForestClassifier(numTrees=20, maxBins=78) cicids17.py:68"),
     "cicids_script": ("cicids", 755774, 14, 20, 5, 78, "f64", "cicids17.py:68 as written (rows/classes left by the six filters)"),
     "stream": ("kdd", 1 << 26, 5, 100, 16, 70, "f32", "BASELINE configs[4]: rows per step (2^26-row chunk), 15 steps = 1.0e9 rows"),
 }

@@ -81,7 +81,7 @@ constexpr int kEncThreads = 256;
 constexpr int kEncMaxCat = 8;     // distinct categorical sources whose rank is shared through shared memory
 
 template <typename OUT>
-__global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a) {
+__global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const EncodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: [in ring][out x3][mbar][badtag 2*R][plan][lut]
     uint8_t* in_base = smem;
@@ -177,9 +177,45 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
     const int dstep = fixed ? n_out : bd;
     const bool active = fixed ? (tid < rp * n_out) : true;
 
-    // one tight loop per source kind: the slot (and so the kind) is fixed per thread, rows are strided by rp
-    auto do_slot = [&](const b200flow_slot& sl, const int cat, const int d, const uint8_t* in_t, OUT* out_t, int32_t* bad, const int tag,
-                       const int rows) {
+    b200flow_slot my_sl = plan_sh[0]; int my_cat = -2;
+    if (fixed && active) { my_sl = plan_sh[d0]; my_cat = slot_cat[d0]; }
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kEncStages, o = it % kEncOutBufs, ob = it & 1;
+        const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
+        const int64_t row_base = tile * R;
+        const int rows = (int)min((int64_t)R, a.n_rows - row_base);
+        const bool full = rows == R;
+        uint8_t* in_t = in_base + (size_t)s * a.in_stride;
+        OUT* out_t = (OUT*)(out_base + (size_t)o * a.out_stride);
+        int32_t* bad = badtag + ob * R;
+        const int tag = it + 1;
+
+        mbar_wait(&mbar[s], ph);
+        if (!full) {
+            const uint32_t* src = (const uint32_t*)(a.records + row_base * row_bytes);
+            for (int i = tid; i < rows * row_bytes / 4; i += bd) ((uint32_t*)in_t)[i] = __ldg(src + i);
+            __syncthreads();
+        }
+
+        if (nsrc > 0) {
+            for (int idx = tid; idx < rows * nsrc; idx += bd) {
+                const int r = idx / nsrc, c = idx - r * nsrc;
+                const int code = *(const int32_t*)(in_t + r * row_bytes + cat_tab[c]);
+                const int rank = (code >= 0 && code < cat_tab[2 * (kEncMaxCat + 1) + c]) ? lut[cat_tab[(kEncMaxCat + 1) + c] + code] : -1;
+                if (rank < 0) bad[r] = tag;
+                if (c < ncat) rank_sh[r * kEncMaxCat + c] = rank;
+                else if (a.label_out) a.label_out[row_base + r] = rank;
+            }
+            if (ncat > 0) __syncthreads();          // ranks visible to the slot loops (label-only: nothing to wait for)
+        }
+        if (active) {
+            // one tight loop per source kind: the slot (and so the kind) is fixed per thread, rows are strided by rp; with one slot
+            // per thread (n_out <= blockDim) its descriptor lives in registers, loaded once before the tile loop
+            for (int d = d0; d < n_out; d += dstep) {
+                b200flow_slot sl = my_sl; int cat = my_cat;
+                if (!fixed) { sl = plan_sh[d]; cat = slot_cat[d]; }
                 const uint8_t* p = in_t + r0 * row_bytes + sl.src_off;
                 OUT* op = out_t + r0 * n_out + d;
                 const int pstep = rp * row_bytes, ostep = rp * n_out;
@@ -235,43 +271,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncodeArgs a)
                         }
                     }
                 }
-    };
-    b200flow_slot my_sl = plan_sh[0]; int my_cat = -2;
-    if (fixed && active) { my_sl = plan_sh[d0]; my_cat = slot_cat[d0]; }
-
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % kEncStages, o = it % kEncOutBufs, ob = it & 1;
-        const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
-        const int64_t row_base = tile * R;
-        const int rows = (int)min((int64_t)R, a.n_rows - row_base);
-        const bool full = rows == R;
-        uint8_t* in_t = in_base + (size_t)s * a.in_stride;
-        OUT* out_t = (OUT*)(out_base + (size_t)o * a.out_stride);
-        int32_t* bad = badtag + ob * R;
-        const int tag = it + 1;
-
-        mbar_wait(&mbar[s], ph);
-        if (!full) {
-            const uint32_t* src = (const uint32_t*)(a.records + row_base * row_bytes);
-            for (int i = tid; i < rows * row_bytes / 4; i += bd) ((uint32_t*)in_t)[i] = __ldg(src + i);
-            __syncthreads();
-        }
-
-        if (nsrc > 0) {
-            for (int idx = tid; idx < rows * nsrc; idx += bd) {
-                const int r = idx / nsrc, c = idx - r * nsrc;
-                const int code = *(const int32_t*)(in_t + r * row_bytes + cat_tab[c]);
-                const int rank = (code >= 0 && code < cat_tab[2 * (kEncMaxCat + 1) + c]) ? lut[cat_tab[(kEncMaxCat + 1) + c] + code] : -1;
-                if (rank < 0) bad[r] = tag;
-                if (c < ncat) rank_sh[r * kEncMaxCat + c] = rank;
-                else if (a.label_out) a.label_out[row_base + r] = rank;
             }
-            if (ncat > 0) __syncthreads();          // ranks visible to the slot loops (label-only: nothing to wait for)
-        }
-        if (active) {
-            if (fixed) do_slot(my_sl, my_cat, d0, in_t, out_t, bad, tag, rows);     // one slot per thread, hoisted out of the tile loop
-            else for (int d = d0; d < n_out; d += dstep) do_slot(plan_sh[d], slot_cat[d], d, in_t, out_t, bad, tag, rows);
         }
         if (tid == 0) bulk_wait_read<1>();           // all but the latest store have drained: the next tile's out buffer is free
         fence_proxy_async();

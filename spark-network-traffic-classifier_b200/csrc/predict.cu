@@ -3,6 +3,8 @@
 // randomSplit and stable row compaction.
 // Reference call sites: model.transform(test_set) kdd99.py:82 / cicids17.py:86; evaluator.evaluate
 // kdd99.py:86-91; randomSplit kdd99.py:52; where / handleInvalid="skip" cicids17.py:30-35,41.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200flow {
@@ -18,7 +20,6 @@ namespace b200flow {
 // them).  The top `top_levels` levels of the CURRENT tree (2^K - 1 nodes, heap-indexed by MLlib's node id) are therefore
 // staged in shared memory, double-buffered with cp.async one tree ahead: a scattered LDS.128 costs a handful of bank
 // wavefronts instead of 32 tag lookups, and only the levels below K go to the L1/L2.
-constexpr int kPredRows = 2;
 
 // top[tree][nid] = the tree's node with MLlib id nid, for nid < 2^K (entry 0 unused)
 __global__ void __launch_bounds__(256) build_top_kernel(const int4* __restrict__ nodes, const int32_t* __restrict__ node_tree,
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(256) build_top_kernel(const int4* __restrict__
     if ((uint32_t)nd.w < (1u << K)) top[((int64_t)node_tree[i] << K) + nd.w] = nd;
 }
 
+template <int kPredRows>
 __global__ void __launch_bounds__(128) predict_kernel(const uint8_t* __restrict__ tp, int stride, int64_t n,
                                                       const b200flow_node* __restrict__ nodes,
                                                       const unsigned long long* __restrict__ node_mask,
@@ -224,16 +226,26 @@ extern "C" int b200flow_predict(const uint8_t* tp, int32_t tp_stride, int64_t n_
     B2F_REQUIRE(dt_mode ? pool_counts != nullptr : leaf_prob != nullptr, "predict: missing leaf payload");
     B2F_REQUIRE(((uintptr_t)tp & 15) == 0, "predict: tp must be 16-byte aligned");
     B2F_REQUIRE(!top_nodes || (top_levels >= 1 && top_levels <= 10 && ((uintptr_t)top_nodes & 15) == 0), "predict: bad top table");
+    static int rows_per_thread = -1;                      // tuning knob: independent tree walks per thread (memory-level parallelism)
+    if (rows_per_thread < 0) { const char* e = getenv("B200FLOW_PRED_ROWS"); rows_per_thread = (e && atoi(e) == 4) ? 4 : 2; }
+    const int kPredRows = rows_per_thread;
     int bd = 128;
     size_t per_thread = ((size_t)tp_stride + (size_t)C * 8) * kPredRows;
     while (bd > 32 && per_thread * bd > 96 * 1024) bd >>= 1;
     size_t smem = per_thread * bd + (top_nodes ? (size_t)2 * 16 * ((size_t)1 << top_levels) : 0);
     B2F_REQUIRE(smem <= 200 * 1024, "predict: too many classes/features for shared memory");
-    cudaError_t e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("predict: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
     int grid = grid_for(n_rows, bd * kPredRows, kNumSMs * 16);
-    predict_kernel<<<grid, bd, smem, (cudaStream_t)stream>>>(tp, tp_stride, n_rows, nodes, (const unsigned long long*)node_mask, leaf_prob,
-                                                             pool_counts, T, C, dt_mode, (const int4*)top_nodes, top_levels, raw, prob, pred);
+    cudaError_t e;
+    if (kPredRows == 4) {
+        e = cudaFuncSetAttribute(predict_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) predict_kernel<4><<<grid, bd, smem, (cudaStream_t)stream>>>(tp, tp_stride, n_rows, nodes, (const unsigned long long*)node_mask, leaf_prob,
+                                                                                          pool_counts, T, C, dt_mode, (const int4*)top_nodes, top_levels, raw, prob, pred);
+    } else {
+        e = cudaFuncSetAttribute(predict_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) predict_kernel<2><<<grid, bd, smem, (cudaStream_t)stream>>>(tp, tp_stride, n_rows, nodes, (const unsigned long long*)node_mask, leaf_prob,
+                                                                                          pool_counts, T, C, dt_mode, (const int4*)top_nodes, top_levels, raw, prob, pred);
+    }
+    if (e != cudaSuccess) { set_error("predict: %s", cudaGetErrorString(e)); return B200FLOW_ERR_CUDA; }
     return check_launch("predict");
 }
 

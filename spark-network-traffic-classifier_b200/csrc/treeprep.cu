@@ -324,7 +324,9 @@ __global__ void __launch_bounds__(256) dedup_min_kernel(int64_t n, const int32_t
     const int lane = lane_id();
     const int sl = i < n ? slot_of[i] : -1 - lane;
     const uint32_t g = __match_any_sync(0xffffffffu, sl);
-    if (i < n && (int)(__ffs(g) - 1) == lane) atomicMin(&minrow[sl], (int)i);
+    // a plain read first: once a small row index sits in the slot, later (larger) candidates skip the atomic altogether, so the
+    // hot slots (smurf, neptune) take a few hundred atomics instead of one per warp (ncu: 0.24 ms at 1 % issue before)
+    if (i < n && (int)(__ffs(g) - 1) == lane && (int)i < *(volatile const int32_t*)&minrow[sl]) atomicMin(&minrow[sl], (int)i);
 }
 __global__ void __launch_bounds__(256) dedup_flag_kernel(int64_t n, const int32_t* __restrict__ slot_of, const int32_t* __restrict__ minrow,
                                                          int32_t* rep, int32_t* flag) {
@@ -347,11 +349,31 @@ __global__ void __launch_bounds__(256) dedup_emit_kernel(const uint8_t* __restri
 // rows grouped by unique id (counting sort): perm[p] = row, uperm[p] = its unique id, non-decreasing in p.  With the rows of
 // a duplicate group adjacent, bag_weights merges a whole group inside a warp and issues ONE global RED per (warp-run, tree)
 // instead of one per row.  Atomics on the group counters are warp-aggregated (match.any on the id).
+constexpr int kGroupTab = 256;          // per-CTA direct-mapped (unique id -> pending count) cache of group_count
+
 __global__ void __launch_bounds__(256) group_count_kernel(const int32_t* __restrict__ uid, int64_t n, int32_t* gsize) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int u = i < n ? uid[i] : -1 - (int)lane_id();
-    const uint32_t g = __match_any_sync(0xffffffffu, u);
-    if (i < n && (int)(__ffs(g) - 1) == lane_id()) atomicAdd(&gsize[u], __popc(g));
+    // persistent CTAs; the warp leaders of a duplicate group add into a small shared-memory cache keyed by the unique id, and
+    // only evictions and the final flush touch global memory: a hot group (a third of KDD99 is one smurf record) costs one global
+    // atomic per CTA instead of one per warp (ncu: 0.28 ms of pure same-address atomics before)
+    __shared__ int tab_key[kGroupTab];
+    __shared__ int tab_cnt[kGroupTab];
+    for (int k = threadIdx.x; k < kGroupTab; k += blockDim.x) { tab_key[k] = -1; tab_cnt[k] = 0; }
+    __syncthreads();
+    const int lane = lane_id();
+    const int64_t n_pad = (n + 255) & ~(int64_t)255;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        const int u = i < n ? uid[i] : -1 - lane;
+        const uint32_t g = __match_any_sync(0xffffffffu, u);
+        if (i < n && (int)(__ffs(g) - 1) == lane) {
+            const int c = __popc(g), h = u & (kGroupTab - 1);
+            const int old = atomicCAS(&tab_key[h], -1, u);                 // claim an empty line, or find who owns it
+            if (old == -1 || old == u) atomicAdd(&tab_cnt[h], c);
+            else atomicAdd(&gsize[u], c);                                   // line taken by another id: straight to global
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kGroupTab; k += blockDim.x)
+        if (tab_key[k] >= 0 && tab_cnt[k]) atomicAdd(&gsize[tab_key[k]], tab_cnt[k]);
 }
 __global__ void __launch_bounds__(256) group_fill_kernel(const int32_t* __restrict__ uid, int64_t n, const int64_t* __restrict__ goff,
                                                          int32_t* cursor, int32_t* perm, int32_t* uperm) {
@@ -390,6 +412,40 @@ __global__ void __launch_bounds__(256) bag_weights_kernel(uint64_t seed, int T, 
     if (threadIdx.x < 32) cdf_sh[threadIdx.x] = cdf ? cdf[threadIdx.x] : 0;
     __syncthreads();
     const int n_quads = (T + 3) >> 2;
+    // Fast path for the hot duplicate groups: with the rows grouped (perm given, uid sorted along the positions) a CTA whose first
+    // and last position carry the same unique id lies entirely inside ONE group — the smurf and neptune floods span thousands of
+    // CTAs.  Its 1024 weights per tree are summed in registers, by shuffles and through shared memory, and ONE global RED per tree
+    // leaves the CTA (31 x fewer same-address REDs than one per 32-position run; ncu: bag_weights was bound by exactly those).
+    {
+        const int64_t p_first = (int64_t)blockIdx.x * kBagBlockRows, p_last = min(n, p_first + kBagBlockRows) - 1;
+        if (perm && uid && cdf && p_last - p_first + 1 == kBagBlockRows && uid[p_first] == uid[p_last]) {
+            __shared__ uint32_t part[8][4];
+            const int64_t u = uid[p_first];
+            uint64_t grow[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) grow[k] = (uint64_t)(row_offset + (int64_t)perm[p_first + k * 256 + threadIdx.x]);
+            for (int tq = 0; tq < n_quads; ++tq) {
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 r = bag_draw4(seed, tq, grow[k]);
+                    w[0] += poisson_weight_fast(r.x, head, cdf_sh); w[1] += poisson_weight_fast(r.y, head, cdf_sh);
+                    w[2] += poisson_weight_fast(r.z, head, cdf_sh); w[3] += poisson_weight_fast(r.w, head, cdf_sh);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) w[q] = warp_sum(w[q]);
+                if (lane == 0) { part[threadIdx.x >> 5][0] = w[0]; part[threadIdx.x >> 5][1] = w[1]; part[threadIdx.x >> 5][2] = w[2]; part[threadIdx.x >> 5][3] = w[3]; }
+                __syncthreads();
+                if (threadIdx.x < 4 && tq * 4 + (int)threadIdx.x < T) {
+                    uint32_t tot = 0;
+                    for (int q = 0; q < 8; ++q) tot += part[q][threadIdx.x];
+                    if (tot) atomicAdd(&W[(int64_t)(tq * 4 + threadIdx.x) * U + u], tot);
+                }
+                __syncthreads();
+            }
+            return;
+        }
+    }
     // position p of the (optionally grouped) order: lane-consecutive positions so that a duplicate group is a run of lanes
     const int64_t pb = (int64_t)blockIdx.x * kBagBlockRows + (threadIdx.x >> 5) * 128 + lane;
     for (int k = 0; k < 4; ++k) {
@@ -568,7 +624,7 @@ extern "C" int b200flow_group_rows(const int32_t* uid, int64_t n_rows, int64_t n
     cudaMemsetAsync(gsize, 0, (size_t)n_unique * 4, st);
     cudaMemsetAsync(cursor, 0, (size_t)n_unique * 4, st);
     const unsigned grid = (unsigned)((n_rows + 255) / 256);
-    group_count_kernel<<<grid, 256, 0, st>>>(uid, n_rows, gsize);
+    group_count_kernel<<<grid_for(n_rows, 256 * 16, kNumSMs * 8), 256, 0, st>>>(uid, n_rows, gsize);
     int rc = b200flow_exclusive_scan_i32_to_i64(gsize, n_unique, goff, nullptr, stream);
     if (rc) return rc;
     group_fill_kernel<<<grid, 256, 0, st>>>(uid, n_rows, goff, cursor, perm, uperm);
