@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(kBinMaxThreads) encode_bins_kernel(const Encod
     int32_t* nthr_sh = (int32_t*)(plan_sh + F);
     int32_t* arity_sh = nthr_sh + F;
     int32_t* lut_sh = arity_sh + F;
-    TT* thr_sh = (TT*)(((uintptr_t)(lut_sh + (a.lut_in_smem ? a.lut_total : 0)) + 7) & ~(uintptr_t)7);
+    // (offset arithmetic on the shared window keeps the address space: a pointer rebuilt from a uintptr_t makes every search load generic)
+    TT* thr_sh = (TT*)(smem + (((size_t)((const uint8_t*)(lut_sh + (a.lut_in_smem ? a.lut_total : 0)) - smem) + 7) & ~(size_t)7));
     const int64_t n_tiles = (a.n_rows + R - 1) / R;
     const uint32_t tile_in_bytes = (uint32_t)R * row_bytes;
 
@@ -454,21 +455,29 @@ __global__ void __launch_bounds__(kBinMaxThreads) encode_bins_kernel(const Encod
 #pragma unroll
                     for (int q = 0; q < RPL; ++q) b[q] = 0;
                     if (sizeof(TT) == 8) {
-                        const double* thr = (a.thr_in_smem ? (const double*)thr_sh : a.thresholds) + (int64_t)f * ns;
-                        for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {
+                        if (a.thr_in_smem) {                // table (+ padding) in shared memory: unconditional load, predicated add
+                            const double* thr = (const double*)thr_sh + f * ns;
+                            for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {
 #pragma unroll
-                            for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; if (i < nt && !(v[q] <= thr[i])) b[q] += st; }
+                                for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; const double t = thr[i]; b[q] += (i < nt && !(v[q] <= t)) ? st : 0; }
+                            }
+                        } else {
+                            const double* thr = a.thresholds + (int64_t)f * ns;
+                            for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {
+#pragma unroll
+                                for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; if (i < nt && !(v[q] <= thr[i])) b[q] += st; }
+                            }
                         }
                     } else {                                // float table, non-f32 source whose value an f32 matrix would have held
-                        const float* thr = (const float*)thr_sh + (int64_t)f * ns;
+                        const float* thr = (const float*)thr_sh + f * ns;
                         for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {
 #pragma unroll
-                            for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; if (i < nt && !((float)v[q] <= thr[i])) b[q] += st; }
+                            for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; const float t = thr[i]; b[q] += (i < nt && !((float)v[q] <= t)) ? st : 0; }
                         }
                     }
                 }
             } else {                                        // f32 field, float thresholds: no fp64 at all
-                const float* thr = (const float*)thr_sh + (int64_t)f * ns;
+                const float* thr = (const float*)thr_sh + f * ns;
                 const bool ident = sl.mean == 0.0 && sl.scale == 1.0;
                 float v[RPL];
 #pragma unroll
@@ -479,9 +488,9 @@ __global__ void __launch_bounds__(kBinMaxThreads) encode_bins_kernel(const Encod
                     if (!ident) v[q] = (float)(((double)v[q] - sl.mean) * sl.scale);      // round_f32 mode: the f32 matrix value
                     b[q] = 0;
                 }
-                for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {
+                for (int st = nt > 0 ? 1 << (31 - __clz(nt)) : 0; st > 0; st >>= 1) {     // the padded table makes the load unconditional
 #pragma unroll
-                    for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; if (i < nt && !(v[q] <= thr[i])) b[q] += st; }
+                    for (int q = 0; q < RPL; ++q) { const int i = b[q] + st - 1; const float t = thr[i]; b[q] += (i < nt && !(v[q] <= t)) ? st : 0; }
                 }
             }
 #pragma unroll
@@ -667,7 +676,7 @@ extern "C" int b200flow_encode_bins(const void* records, int64_t n_rows, int32_t
     // float thresholds when every continuous value is exactly a float: f32 fields with identity scaling, or the f32 feature
     // matrix being emulated (round_f32); the plan is a HOST-side fact of the caller, passed as thr_f32
     const bool f32_table = thr_f32 != 0;
-    const size_t thr_smem = (size_t)F * (max_bins - 1) * (f32_table ? 4 : 8);
+    const size_t thr_smem = ((size_t)F * (max_bins - 1) + 256) * (f32_table ? 4 : 8);   // + 256 entries: the branch-free descent may read (never use) past a row
     a.thr_in_smem = (f32_table || thr_smem <= 56 * 1024) ? 1 : 0;   // a double table beyond that stays in global memory (L1 keeps the top levels)
     B2F_REQUIRE(!f32_table || thr_smem <= 100 * 1024, "encode_bins: float threshold table exceeds shared memory");
     const size_t fixed_bytes = kEncStages * 8 + (size_t)F * sizeof(b200flow_slot) + 8 * (size_t)F + (a.lut_in_smem ? (size_t)a.lut_total * 4 : 0) + 16 +

@@ -49,6 +49,31 @@ def _arity_from_attrs(attrs, F):
     return [int(a.get("arity", 0)) if a.get("type") in ("nominal", "binary") else 0 for a in attrs]
 
 
+def _lazy_plan(df, fcol):
+    """(encode plan, emulate-f32 flag) when the features column is still lazy — VectorAssembler over raw record fields whose
+    kernel has not run — so that trees can be trained / applied straight from the records (fused encode -> bins); else None."""
+    fc = df._cols.get(fcol)
+    if fc is None or fc.kind != "vector" or not fc.lazy or fc.prov is None or fc.prov[0] != "plan" or df._rec is None:
+        return None
+    return fc.prov[1]
+
+
+def _records_fit_inputs(df, est):
+    """-> (records, plan with the label column set, num_classes, per-slot attrs) for the fused record path, or None."""
+    import copy
+    fcol, lcol = est.getOrDefault("featuresCol"), est.getOrDefault("labelCol")
+    plan = _lazy_plan(df, fcol)
+    lc = df._cols.get(lcol)
+    if plan is None or lc is None or lc.prov is None or lc.prov[0] != "index" or not lc.lazy:
+        return None
+    lab_meta = lc.meta.get("ml_attr", {})
+    if lab_meta.get("type") != "nominal":
+        return None
+    p2 = copy.copy(plan); p2.slots = list(plan.slots); p2.luts = list(plan.luts); p2._dev = None
+    p2.set_label(lc.prov[1], lc.prov[2])
+    return df._rec, p2, len(lab_meta["vals"]), df._cols[fcol].meta.get("attrs")
+
+
 class _TreeParams:
     _defaults = {"featuresCol": "features", "labelCol": "label", "predictionCol": "prediction",
                  "probabilityCol": "probability", "rawPredictionCol": "rawPrediction", "maxDepth": 5, "maxBins": 32,
@@ -73,14 +98,24 @@ class _TreeClassifierBase(Estimator, _TreeParams):
                                seed=_default_seed(self) if seed is None else int(seed), bootstrap=bootstrap)
 
     def _train(self, df, params):
-        x, y, C, attrs = _features_and_labels(df, self)
-        if C > 100:
-            raise IllegalArgumentException("Classifier inferred %d classes; maximum is 100" % C)
+        from .feature import SparkException
+        fused = _records_fit_inputs(df, self)
         try:
             grp = bdist.group()
+            if fused is not None:                           # lazy VectorAssembler output: bin straight from the raw records
+                rec, plan, C, attrs = fused
+                if C > 100:
+                    raise IllegalArgumentException("Classifier inferred %d classes; maximum is 100" % C)
+                off, _ = bdist.global_offset(rec.shape[0], rec.device, grp)
+                return fr.fit_forest_records(rec, plan, C, _arity_from_attrs(attrs, plan.n_out), params, row_offset=off, group=grp)
+            x, y, C, attrs = _features_and_labels(df, self)
+            if C > 100:
+                raise IllegalArgumentException("Classifier inferred %d classes; maximum is 100" % C)
             off, _ = bdist.global_offset(x.shape[0], x.device, grp)
             forest = fr.fit_forest(x, y.to(torch.int32), C, _arity_from_attrs(attrs, x.shape[1]), params,
                                    row_offset=off, group=grp)
+        except fr.InvalidRowsError as e:                    # NaN / null under handleInvalid="error": surfaces at the action, as in Spark
+            raise SparkException("Encountered NaN/null while assembling a row with handleInvalid = \"error\" (%s)" % e)
         except ValueError as e:        # includes b200flow's UnsupportedParamError; CUDA failures propagate as they are
             raise IllegalArgumentException(str(e))
         return forest
@@ -146,8 +181,16 @@ class _ForestModelBase(Model, _TreeParams):
         fcol = self.getOrDefault("featuresCol")
         if fcol not in df._cols or df._cols[fcol].kind != "vector":
             raise IllegalArgumentException("Column %s must be of type vector" % fcol)
-        x = df._cols[fcol].data
-        raw, prob, pred = self._forest.predict(x)          # R9: bin + walk all trees on the GPU
+        plan = _lazy_plan(df, fcol)
+        if plan is not None and plan.n_out == self._forest.F:   # lazy features: fused encode -> bins -> tree walk, no dense matrix
+            from .feature import SparkException
+            try:
+                raw, prob, pred, _ = self._forest.predict_records(df._rec, plan, on_invalid="error" if plan.check_nan else "ignore")
+            except fr.InvalidRowsError as e:
+                raise SparkException("Encountered NaN/null while assembling a row with handleInvalid = \"error\" (%s)" % e)
+        else:
+            x = df._cols[fcol].data
+            raw, prob, pred = self._forest.predict(x)          # R9: bin + walk all trees on the GPU
         cols = dict(df._cols)
         for name, key, kind in ((self.getOrDefault("rawPredictionCol"), raw, "vector"),
                                 (self.getOrDefault("probabilityCol"), prob, "vector"),

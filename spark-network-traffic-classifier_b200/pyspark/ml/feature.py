@@ -143,8 +143,9 @@ class StringIndexerModel(Model):
             # every row's label is known (the counts of this very record buffer say so): nothing to check, nothing to drop.
             # The index column is fully described by its provenance, so its kernel is deferred until the values are read —
             # VectorAssembler fuses the lookup into the one encode pass instead (SURVEY 8a R2+R3).
+            mk = lambda r: plan.run(r, torch.float64, want_valid=False)[0].view(-1)     # noqa: E731
             newc = ColumnData("numeric", None, "f64", {"ml_attr": {"type": "nominal", "vals": labels}},
-                              ("index", field, lut, labels), thunk=lambda: plan.run(rec, torch.float64, want_valid=False)[0].view(-1))
+                              ("index", field, lut, labels), thunk=lambda: mk(rec), maker=mk)
             cols = dict(df._cols); cols[out] = newc
             return df._with(cols=cols)
         vals, _, valid = plan.run(rec, torch.float64)
@@ -208,8 +209,26 @@ class VectorAssembler(Transformer):
             # f32 record fields, index ranks and one-hot flags are exact in f32: keep the vector in f32 (half the bytes through
             # assemble, randomSplit and binning); values widen to the same doubles whenever they are read as f64
             exact32 = all(s[0] in (SRC_F32, SRC_INDEX, SRC_ONEHOT) and s[5] == 0.0 and s[6] == 1.0 for s in plan.slots)
-            feats, _, valid = plan.run(df._rec, torch.float32 if exact32 else torch.float64)
+            vdtype = torch.float32 if exact32 else torch.float64
             prov = ("plan", plan)
+            if hi != "skip":
+                # No row can disappear ("error" raises, "keep" keeps): the vector is fully described by the plan, so nothing is
+                # computed here.  A tree trainer / model downstream bins straight from the records (fused encode -> bins, the
+                # dense matrix never exists); anything else that reads the values runs the fused encode kernel then.  Like
+                # Spark's lazy transform, a NaN under handleInvalid="error" surfaces at the action that consumes the column.
+                plan.check_nan = 1 if hi == "error" else 0
+
+                def mk(r, plan=plan, vdtype=vdtype, hi=hi):
+                    feats, _, valid = plan.run(r, vdtype, want_valid=(hi == "error"))
+                    if hi == "error" and r.shape[0] and int((valid == 0).sum().item()):
+                        raise SparkException("Encountered NaN/null while assembling a row with handleInvalid = \"error\". Consider "
+                                             "removing NaNs from dataset or using handleInvalid = \"keep\" or \"skip\".")
+                    return feats
+                rec0 = df._rec
+                newc = ColumnData("vector", None, "f32" if exact32 else "f64", {"attrs": attrs}, prov, thunk=lambda: mk(rec0), maker=mk)
+                cols = dict(df._cols); cols[out] = newc
+                return df._with(cols=cols)
+            feats, _, valid = plan.run(df._rec, vdtype)
         else:                                               # columns without raw provenance: concatenate, then one pass
             parts = [_materialize(df, c) for c in cols_in]
             for name, part in zip(cols_in, parts):

@@ -25,21 +25,34 @@ class ColumnData:
     'vector' ([n, D] tensor).  meta carries ML attributes (nominal values / per-slot attrs);
     prov records how the column derives from raw record fields so later stages can fuse."""
 
-    def __init__(self, kind, data=None, dtype=None, meta=None, prov=None, thunk=None):
+    def __init__(self, kind, data=None, dtype=None, meta=None, prov=None, thunk=None, maker=None):
         self.kind, self._data, self.dtype, self.meta, self.prov = kind, data, dtype, dict(meta or {}), prov
         self._thunk = thunk                    # lazy column: () -> tensor, run on first access of .data
+        self._maker = maker                    # lazy column derived from the record buffer: (records) -> tensor; lets row
+        #                                        filters (where / randomSplit) move the RECORDS only and re-bind the column
+
+    @property
+    def lazy(self):
+        """True while the column exists only as its provenance (no kernel has produced its values yet)."""
+        return self._data is None and (self._thunk is not None or self._maker is not None)
+
+    def rebound(self, rec):
+        """the same lazy column over another (filtered) record buffer."""
+        mk = self._maker
+        return ColumnData(self.kind, None, self.dtype, self.meta, self.prov, thunk=lambda: mk(rec), maker=mk)
 
     @property
     def data(self):
-        """the column's tensor.  A transformer whose output is fully described by `prov` (e.g. StringIndexerModel on a raw
-        code field) defers its kernel until somebody reads the values — a later VectorAssembler fuses it instead."""
+        """the column's tensor.  A transformer whose output is fully described by `prov` (StringIndexerModel on a raw code field,
+        VectorAssembler over raw fields) defers its kernel until somebody reads the values — a later VectorAssembler fuses the
+        lookup, and the tree trainer bins straight from the records (fused encode -> bins) without the vector ever existing."""
         if self._data is None and self._thunk is not None:
             self._data, self._thunk = self._thunk(), None
         return self._data
 
     @data.setter
     def data(self, v):
-        self._data, self._thunk = v, None
+        self._data, self._thunk, self._maker = v, None, None
 
 
 class Column:
@@ -211,8 +224,11 @@ class DataFrame:
 
     def _with(self, cols=None, n=None, rec="same", dicts=None):
         same = isinstance(rec, str) and n is None and dicts is None
+        cols = dict(self._cols) if cols is None else cols
+        if not isinstance(rec, str) and rec is not None:    # another record buffer: still-lazy derived columns follow it
+            cols = {k: (c.rebound(rec) if (c.kind != "field" and c.lazy and c._maker is not None) else c) for k, c in cols.items()}
         return DataFrame(self._n if n is None else n, self._rec if isinstance(rec, str) else rec, self._schema,
-                         self._dicts if dicts is None else dicts, dict(self._cols) if cols is None else cols, self._session,
+                         self._dicts if dicts is None else dicts, cols, self._session,
                          self._cat_counts if same else None)
 
     def _device(self):
@@ -324,8 +340,11 @@ class DataFrame:
         return c.data
 
     def _compact_bufs(self):
-        needs_rec = self._rec is not None and any(c.kind == "field" for c in self._cols.values())
-        names = [k for k, c in self._cols.items() if c.kind != "field"]
+        """buffers a row filter has to move: the record buffer (when a base field or a still-lazy derived column needs it) and
+        every MATERIALISED derived column.  Lazy columns with a maker are not computed: they are re-bound to the filtered records."""
+        lazy = [k for k, c in self._cols.items() if c.kind != "field" and c.lazy and c._maker is not None and self._rec is not None]
+        needs_rec = self._rec is not None and (any(c.kind == "field" for c in self._cols.values()) or bool(lazy))
+        names = [k for k, c in self._cols.items() if c.kind != "field" and k not in lazy]
         return needs_rec, names, ([self._rec] if needs_rec else []) + [self._cols[k].data for k in names]
 
     def _compact(self, flag):
@@ -342,8 +361,10 @@ class DataFrame:
         for name, c in self._cols.items():
             if c.kind == "field":
                 cols[name] = c
-            else:
+            elif name in names:
                 cols[name] = ColumnData(c.kind, outs[names.index(name)], c.dtype, c.meta, c.prov if rec is not None else None)
+            else:                                            # still lazy: the same provenance over the filtered records
+                cols[name] = c.rebound(rec)
         return DataFrame(k, rec, self._schema if rec is not None else None, self._dicts if rec is not None else {}, cols,
                          self._session)
 

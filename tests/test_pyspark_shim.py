@@ -243,3 +243,45 @@ def test_indexer_columns_are_lazy_and_fused_but_identical():
     m_few = StringIndexer(inputCol="service", outputCol="s_num").fit(DataFrame.fromRecords(few.contiguous(), schema, dicts))
     with pytest.raises(SparkException):
         m_few.transform(df)
+
+
+def test_lazy_assembled_vector_feeds_the_trees_from_raw_records():
+    """VectorAssembler over raw record fields defers its kernel (like Spark's lazy transform); select / randomSplit move the
+    RECORDS only, RandomForestClassifier.fit and model.transform bin straight from them (fused encode -> bins), and the result
+    equals the eager path (vector materialised before the split) exactly.  A NaN under handleInvalid="error" raises at the action."""
+    from b200flow import synth
+    from pyspark.ml import Pipeline
+    from pyspark.ml.classification import RandomForestClassifier
+    from pyspark.ml.evaluation import MulticlassClassificationEvaluator
+    from pyspark.ml.feature import SparkException, StringIndexer, VectorAssembler
+    from pyspark.sql import DataFrame
+    rec, dicts = synth.make_kdd(40000, 5, seed=21, device="cuda")
+    schema = synth.kdd_schema()
+    cats = synth.KDD_CATEGORICAL
+
+    def flow(materialise, records=rec):
+        df = DataFrame.fromRecords(records, schema, dicts)
+        stages = [StringIndexer(inputCol=c, outputCol=c + "_num") for c in cats] + [StringIndexer(inputCol="label", outputCol="label_num")]
+        df = Pipeline(stages=stages).fit(df).transform(df)
+        numerical = [c for c in df.columns if c not in cats + ["label", "label_num"]]
+        df = VectorAssembler(inputCols=numerical, outputCol="features").transform(df).select(["features", "label_num"])
+        assert df._cols["features"].lazy
+        if materialise:
+            df._cols["features"].data                                               # the fused encode kernel runs now
+            assert not df._cols["features"].lazy
+        train, test = df.randomSplit([0.75, 0.25], seed=2019)
+        assert train._cols["features"].lazy == (not materialise)
+        model = RandomForestClassifier(labelCol="label_num", featuresCol="features", numTrees=6, maxBins=70, maxDepth=7, seed=5).fit(train)
+        pred = model.transform(test)
+        assert pred._cols["features"].lazy == (not materialise)                    # the dense matrix never existed on the lazy path
+        f1 = MulticlassClassificationEvaluator(labelCol="label_num", predictionCol="prediction", metricName="f1").evaluate(pred)
+        return model._forest.export(), pred._cols["prediction"].data, pred._cols["probability"].data, f1, test
+
+    ex_l, pred_l, prob_l, f1_l, test_l = flow(False)
+    ex_e, pred_e, prob_e, f1_e, _ = flow(True)
+    assert all(np.array_equal(ex_l[k], ex_e[k]) for k in ex_e) and torch.equal(pred_l, pred_e) and torch.equal(prob_l, prob_e) and f1_l == f1_e
+    # reading the lazy column after the fact gives the values the eager path assembled
+    assert test_l._cols["features"].data.shape == (test_l.count(), 41)
+    bad = rec.clone(); bad.view(torch.float32)[123, 0] = float("nan")
+    with pytest.raises(SparkException):
+        flow(False, bad)
