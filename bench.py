@@ -204,15 +204,72 @@ def sklearn_pass(wl, rec_np, dicts, a, max_rows=400000):
                     "(exact CART, not MLlib's binned algorithm: context, not parity)" % (a.trees, a.depth)}
 
 
+def cpu_stream_setup(wl, a, train_rows, train=None):
+    """the oracle's resident forest for the stream workload: fitted like the GPU arm's.  `train` = (records, dicts) of the very
+    batch the GPU arm trained on (the CUDA and CPU generators draw different streams for one seed)."""
+    import oracle
+    rec, dicts = train if train is not None else wl.make(train_rows, "cpu", row_offset=0)
+    rec_np = rec.numpy()
+    schema = wl.schema
+    luts, ordered = {}, {}
+    for c in wl.count_cols():
+        cnt = oracle.category_counts(rec_np, schema.row_bytes, schema.offsets[c], len(dicts[c]))
+        ordered[c], luts[c] = oracle.string_index_order(cnt, dicts[c])
+    plan = wl.plan(luts)
+    x, y, _ = oracle.encode(rec_np, schema.row_bytes, plan.slot_array(), plan.lut_array(), *plan.label)
+    fo, meta = oracle.fit_forest(x, y, len(ordered[wl.label_col]), wl.arity(ordered), num_trees=a.trees, max_bins=a.max_bins,
+                                 max_depth=a.depth, seed=2019)
+    return plan, fo, meta
+
+
+def cpu_stream_pass(wl, plan, fo, meta, rec_np):
+    """one stream step on the CPU: encode -> bins -> predict with the resident forest.  -> predictions."""
+    import oracle
+    x, _, _ = oracle.encode(rec_np, wl.schema.row_bytes, plan.slot_array(), plan.lut_array(), *plan.label)
+    tp, _ = oracle.bin_rows(x, meta["thresholds"], meta["n_thr"], meta["arity"], meta["max_bins"])
+    return fo.predict(tp)[2]
+
+
+def run_reference_stream(a, wl, threads):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    train_rows = min(a.rows, 4898431)
+    plan, fo, meta = cpu_stream_setup(wl, a, train_rows)
+    if a.cpu_rows <= 0:
+        probe, _ = wl.make(200000, "cpu", row_offset=a.rows)
+        t0 = time.perf_counter(); cpu_stream_pass(wl, plan, fo, meta, probe.numpy()); probe_s = time.perf_counter() - t0
+        a.cpu_rows = int(max(50000, min(a.rows, 200000 / max(probe_s, 1e-3) * 240.0 / max(a.steps + a.warmup, 1))))
+    rec, _ = wl.make(a.cpu_rows, "cpu", row_offset=a.rows)
+    rec_np = rec.numpy()
+    for _ in range(a.warmup):
+        cpu_stream_pass(wl, plan, fo, meta, rec_np)
+    t = []
+    for _ in range(a.steps):
+        t0 = time.perf_counter(); cpu_stream_pass(wl, plan, fo, meta, rec_np); t.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(t) / len(t)
+    v = a.cpu_rows / (ms / 1e3)
+    line = {"impl": "reference", "metric": "flow-records/sec encode+predict (stream)", "value": v, "unit": "records/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "stream: KDD99-schema synthetic record stream, encode + predict with a resident RandomForest (%d trees, "
+                                   "depth %d) [%s]" % (a.trees, a.depth, a.site), "name": "stream", "rows_per_gpu": a.rows,
+                       "global_rows": a.rows * world, "sample_rows": a.cpu_rows, "features": 41, "classes": a.classes, "num_trees": a.trees,
+                       "max_depth": a.depth, "max_bins": a.max_bins},
+            "cpu_baseline": {"value": v, "unit": "records/s", "cores": threads, "kind": "port",
+                             "sample": "%d-row chunk per step (same generator); oracle encode + bin + predict, forest fitted on %d rows"
+                                       % (a.cpu_rows, train_rows)},
+            "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
 def run_reference(a):
-    """--impl reference: rank 0 only; times the CPU arm (oracle port) with every host thread.  Every step processes the same
-    bounded sample — the whole batch when (steps + warmup) full passes fit in about four minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     threads = oracle.set_num_threads()                           # torchrun exports OMP_NUM_THREADS=1: set the count explicitly
     wl = Workload(a)
+    if a.workload == "stream":
+        return run_reference_stream(a, wl, threads)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     full = a.rows
     if a.cpu_rows <= 0:                                          # calibrate on a small batch, then size the per-step sample
@@ -493,17 +550,15 @@ def main():
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
     d = kern[dom]
     avg_ms = d["ms_per_step"] / max(d["launches_per_step"], 1)
-    ctr = load_counters().get(a.workload, {}).get(dom) or load_counters().get(dom) or {}
-    traffic = ctr.get("dram_bytes_per_launch") if isinstance(ctr, dict) else ctr
+    ctr = (load_counters().get(a.workload) or {}).get(dom) or {}       # counters exist for the workloads that were captured with ncu
+    traffic = ctr.get("dram_bytes_per_launch")
     bound = {"route_hist_level": "lsu (shared-memory pipe: tile fills + tile reads + atomics), not hbm",
              "hist_level": "lsu / record gather", "encode_bins": "issue + shared-memory (binary search), not hbm",
              "predict": "l1 latency (divergent tree walk)", "encode": "hbm"}.get(dom, "hbm")
     roofline = {"kernel": dom, "bound": bound, "achieved": d.get("achieved_gbs"), "peak": peak, "unit": "GB/s",
                 "frac": d.get("frac_of_hbm_peak"), "traffic": traffic, "peak_source": peak_src,
                 "dram_frac": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                "lsu_pct": ctr.get("lsu_pct") if isinstance(ctr, dict) else None,
-                "issue_pct": ctr.get("issue_pct") if isinstance(ctr, dict) else None,
-                "counters_source": ctr.get("source") if isinstance(ctr, dict) else None,
+                "lsu_pct": ctr.get("lsu_pct"), "issue_pct": ctr.get("issue_pct"), "counters_source": ctr.get("source"),
                 "launches_per_step": d["launches_per_step"], "avg_launch_ms": avg_ms, "share_of_step": d["share_of_step"],
                 "note": "achieved = SURVEY 8(d) algorithmic bytes (per level and TRAINING row: F + 1 + 5*T) / CUDA-event kernel time "
                         "inside the timed steps; after row de-duplication the kernel works on (unique record, tree) entries and is "
@@ -567,6 +622,7 @@ def run_stream(a, wl, dev, grp, world, rank, local):
     plan = wl.plan(luts)
     p = fr.ForestParams(num_trees=a.trees, max_depth=a.depth, max_bins=a.max_bins, seed=2019)
     model = fr.fit_forest_records(train_rec, plan, len(ordered[wl.label_col]), wl.arity(ordered), p)
+    train_host = (train_rec.cpu(), dicts) if (world == 1 and not a.no_cpu_baseline) else None
     del train_rec
     chunk, _ = wl.make(rows, dev, row_offset=(rank + 1) * rows)
     torch.cuda.synchronize()
@@ -657,6 +713,17 @@ def run_stream(a, wl, dev, grp, world, rank, local):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "dominant_kernel": dom, "note": "achieved = (record bytes in + 8 B prediction out) x rows / step time, per GPU"},
             "kernels": kern, "cpu_baseline": None}
+    if not a.no_cpu_baseline and world == 1:                    # the oracle on a bounded chunk, with bit parity of the predicted labels
+        import oracle
+        threads = oracle.set_num_threads()
+        n_cpu = min(rows, a.cpu_rows if a.cpu_rows > 0 else 2000000)
+        plan_c, fo, meta = cpu_stream_setup(wl, a, min(rows, 4898431), train_host)
+        chunk_np = chunk[:n_cpu].cpu().numpy()
+        t0 = time.perf_counter(); pred_cpu = cpu_stream_pass(wl, plan_c, fo, meta, chunk_np); dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "records/s", "cores": threads, "kind": "port",
+                                "sample": "the first %d rows of the chunk the GPU arm processed, %.1f s; oracle encode + bin + predict with "
+                                          "its own forest fitted on the same %d training rows" % (n_cpu, dt, min(rows, 4898431)),
+                                "labels_equal": bool(np.array_equal(pred[:n_cpu].cpu().numpy(), pred_cpu)), "rows_compared": int(n_cpu)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -45,6 +45,7 @@ def profile_totals():
             if not k.startswith("_")}
 
 
+ENTRY_BOUND_BYTES = 8 << 30        # the two entry buffers are sized by the bound T * U (no host read of the exact count) up to this many bytes
 HIST_BUDGET_BYTES = int(_os.environ.get("B200FLOW_HIST_BUDGET_GB", "24")) << 30   # cap of one level's histogram buffer (MLlib: maxMemoryInMB); beyond it the level is processed in node groups by the unfused kernels
 # Multi-GPU: level histograms of at least this many bytes are REDUCE-SCATTERED by node (each rank then scores only its own
 # nodes and the 64-byte split records are all-gathered) instead of all-reduced: half the NVLink bytes, 1/world of the scoring.
@@ -491,7 +492,10 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
     if U > 0:
         call("b200flow_bag_count", ptr(W), T, U, ptr(blk_cnt))
     call("b200flow_exclusive_scan_i32_to_i64", ptr(blk_cnt), T * nb, ptr(blk_off), ptr(total))
-    E = int(total.item())
+    # the entry count E stays on the device when its upper bound T * U (every record drawn by every tree) is affordable:
+    # one host round trip less; the exact count is read with the last level's counters
+    e_dev = total.clone()
+    E = T * U if T * U * 16 <= ENTRY_BOUND_BYTES else int(total.item())
     ent = torch.empty((max(E, 1), 2), dtype=torch.int32, device=dev)     # {unique record index, weight}
     ent2 = torch.empty_like(ent)
     if U > 0:
@@ -509,7 +513,7 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
     level = 0
     per_slot_hist = m * n_bins * C * 4
     group_slots = max(1, HIST_BUDGET_BYTES // per_slot_hist)
-    stats = dict(levels=0, slots=0, entries=E, hist_launches=0, rows=n, unique_rows=U)
+    stats = dict(levels=0, slots=0, entries=0, hist_launches=0, rows=n, unique_rows=U)
 
     # launch shape of the fused kernel: entries per routing chunk and subset features per pass (wide nodes — many classes,
     # or a DecisionTree's all-feature histograms — are accumulated in several feature passes, the first of which routes)
@@ -738,6 +742,7 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
 
     leaf_prob = torch.empty((pool_size, C), dtype=torch.float64, device=dev)
     call("b200flow_finalize_forest", pool_size, ptr(pool_counts), C, ptr(leaf_prob))
+    stats["entries"] = int(e_dev.item())
     model = ForestModel(T, C, F, arity, mpb, thresholds, n_thr, nodes, node_mask, pool_counts, node_tree, leaf_prob,
                         node_gain, pool_size, dt_mode=(T == 1 and not p.bootstrap))
     model.train_stats = stats
