@@ -144,6 +144,17 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// read-once / write-once 64-bit accesses marked evict-first in the L2: the bagged-entry stream (1 GB per level) passes through
+// once per level and must not push the re-used TreePoint records (61 MB, gathered at random) out of the 126 MB L2
+__device__ __forceinline__ uint2 ld_evict_first_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));      // .cs = cache-streaming: evict-first
+    return r;
+}
+__device__ __forceinline__ void st_evict_first_u2(void* p, uint2 v) {      // .cs = cache-streaming: evict-first
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
 // streaming (read-once) 128-bit load / store that do not pollute L1
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
     uint4 r;

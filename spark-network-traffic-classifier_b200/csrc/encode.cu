@@ -71,6 +71,7 @@ struct EncodeArgs {
     int label_off, label_lut_off, label_lut_len, check_nan;
     void* out; int32_t* label_out; uint8_t* valid_out;
     int R;            // rows per tile (multiple of 4)
+    int stages;       // depth of the TMA load ring (2 or 3)
     int in_stride;    // bytes per input stage (128-aligned)
     int out_stride;   // bytes per output stage (128-aligned)
 };
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const EncodeArgs
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: [in ring][out x3][mbar][badtag 2*R][plan][lut]
     uint8_t* in_base = smem;
-    uint8_t* out_base = in_base + (size_t)kEncStages * a.in_stride;
+    uint8_t* out_base = in_base + (size_t)a.stages * a.in_stride;
     uint64_t* mbar = (uint64_t*)(out_base + kEncOutBufs * (size_t)a.out_stride);
     int32_t* badtag = (int32_t*)(mbar + kEncStages);
     b200flow_slot* plan_sh = (b200flow_slot*)(badtag + 2 * a.R + ((2 * a.R) & 1));   // keep 8-byte alignment
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const EncodeArgs
     const uint32_t tile_out_bytes = (uint32_t)R * n_out * sizeof(OUT);
 
     if (tid == 0) {
-        for (int s = 0; s < kEncStages; ++s) mbar_init(&mbar[s], 1);
+        for (int s = 0; s < a.stages; ++s) mbar_init(&mbar[s], 1);
         fence_mbar_init();
     }
     for (int i = tid; i < n_out * (int)(sizeof(b200flow_slot) / 4); i += bd) ((uint32_t*)plan_sh)[i] = ((const uint32_t*)a.plan)[i];
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const EncodeArgs
         }
     };
     if (tid == 0)
-        for (int s = 0; s < kEncStages; ++s) {
+        for (int s = 0; s < a.stages; ++s) {
             int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
             if (t < n_tiles) issue_load(t, s);
         }
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const EncodeArgs
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % kEncStages, o = it % kEncOutBufs, ob = it & 1;
-        const uint32_t ph = (uint32_t)(it / kEncStages) & 1u;
+        const int s = it % a.stages, o = it % kEncOutBufs, ob = it & 1;
+        const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
         const int64_t row_base = tile * R;
         const int rows = (int)min((int64_t)R, a.n_rows - row_base);
         const bool full = rows == R;
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const EncodeArgs
         __syncthreads();                            // the only barrier per tile: tile computed, input stage s consumed
         if (tid == 0) {
             if (full) { bulk_s2g((OUT*)a.out + row_base * n_out, out_t, tile_out_bytes); bulk_commit(); }
-            int64_t next = tile + (int64_t)kEncStages * gridDim.x;
+            int64_t next = tile + (int64_t)a.stages * gridDim.x;
             if (next < n_tiles) issue_load(next, s);
         }
         if (!full) {
@@ -597,7 +598,10 @@ extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_
     // tile rows: keep one CTA near 52 KB of smem so four CTAs share an SM (>= 64 KB of loads in flight per SM)
     const int fixed_bytes = kEncStages * 8 + n_out * (int)sizeof(b200flow_slot) + (a.lut_in_smem ? a.lut_total * 4 : 0) + 1024 +
                             3 * (kEncMaxCat + 1) * 4 + 4 * (n_out + 1);
-    const int per_row = row_bytes * kEncStages + n_out * osz * kEncOutBufs + 8 + kEncMaxCat * 4;
+    static int stages = -1;                                // tuning knob: depth of the TMA load ring
+    if (stages < 0) { const char* e = getenv("B200FLOW_ENC_STAGES"); stages = (e && atoi(e) == 2) ? 2 : 3; }
+    a.stages = stages;
+    const int per_row = row_bytes * stages + n_out * osz * kEncOutBufs + 8 + kEncMaxCat * 4;
     static int budget_kb = -1;                             // tuning knob: per-CTA shared memory target
     if (budget_kb < 0) { const char* e = getenv("B200FLOW_ENC_SMEM_KB"); budget_kb = e ? atoi(e) : 52; }
     int budget = budget_kb * 1024 - fixed_bytes;
@@ -609,7 +613,7 @@ extern "C" int b200flow_encode(const void* records, int64_t n_rows, int32_t row_
     a.R = R;
     a.in_stride = (R * row_bytes + 127) & ~127;
     a.out_stride = (R * n_out * osz + 127) & ~127;
-    size_t smem = (size_t)kEncStages * a.in_stride + kEncOutBufs * (size_t)a.out_stride + kEncStages * 8 + (2 * R + 2) * 4 +
+    size_t smem = (size_t)stages * a.in_stride + kEncOutBufs * (size_t)a.out_stride + kEncStages * 8 + (2 * R + 2) * 4 +
                   (size_t)n_out * sizeof(b200flow_slot) + (a.lut_in_smem ? (size_t)a.lut_total * 4 : 0) + 16 +
                   3 * (kEncMaxCat + 1) * 4 + (size_t)R * kEncMaxCat * 4 + 4 * ((size_t)n_out + 1);
     B2F_REQUIRE(smem <= 227 * 1024, "encode: record too wide for shared memory (row_bytes=%d n_out=%d)", row_bytes, n_out);

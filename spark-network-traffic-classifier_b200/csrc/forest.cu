@@ -521,6 +521,11 @@ __global__ void __launch_bounds__(256) partition_level_kernel(
 // entries, or 1 CTA x 32 warps — so that the SM still holds 32 warps.  Nodes whose two child histograms exceed shared
 // memory altogether (DecisionTree: every feature of every node) are processed in FEATURE PASSES: pass p accumulates
 // subset positions [j0, j0 + m_pass) and only pass 0 routes.
+#ifndef B2F_EVICT_FIRST
+#define B2F_EVICT_FIRST 1
+#endif
+constexpr bool kEvictFirst = B2F_EVICT_FIRST != 0;   // entry stream with L2::evict_first (records stay L2-resident)
+
 struct RouteChunk { int32_t slot; int32_t n; long long begin; };   // 16 bytes, one per chunk
 
 __global__ void route_chunks_kernel(const int64_t* __restrict__ chunk_off, int n_slots, const int64_t* __restrict__ n_chunks_dev,
@@ -587,7 +592,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) rou
         const int cn = count_of(d);
         const b2f_entry* ep = a.ent + (((long long)(uint32_t)d.z) | ((long long)d.w << 32)) + wid * kSub;
 #pragma unroll
-        for (int k = 0; k < KS; ++k) x[k] = lane + 32 * k < cn ? __ldg(ep + 32 * k + lane) : make_uint2(0u, 0u);
+        for (int k = 0; k < KS; ++k) x[k] = lane + 32 * k < cn ? (kEvictFirst ? ld_evict_first_u2(ep + 32 * k + lane) : __ldg(ep + 32 * k + lane)) : make_uint2(0u, 0u);
     };
     // The tile is entry-major ([kSub entries][nq quads]) and its kSub * nq 16-byte chunks are copied in linear order, lane
     // after lane: neighbouring lanes fetch neighbouring quads of the SAME record (same 32-byte sector) into neighbouring
@@ -616,8 +621,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) rou
         for (int k = 0; k < KS; ++k) {
             const int d = (p_dec >> (2 * k)) & 3;
             const uint32_t mL = __ballot_sync(0xffffffffu, d == 1), mR = __ballot_sync(0xffffffffu, d == 2);
-            if (d == 1) a.ent_out[p_sb + baseL + __popc(mL & lt)] = p_e[k];
-            else if (d == 2) a.ent_out[p_se - 1 - (baseR + __popc(mR & lt))] = p_e[k];
+            if (d == 1) { if (kEvictFirst) st_evict_first_u2(a.ent_out + p_sb + baseL + __popc(mL & lt), p_e[k]); else a.ent_out[p_sb + baseL + __popc(mL & lt)] = p_e[k]; }
+            else if (d == 2) { if (kEvictFirst) st_evict_first_u2(a.ent_out + p_se - 1 - (baseR + __popc(mR & lt)), p_e[k]); else a.ent_out[p_se - 1 - (baseR + __popc(mR & lt))] = p_e[k]; }
             baseL += __popc(mL); baseR += __popc(mR);
         }
         pending = false;
