@@ -305,7 +305,8 @@ int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, int32_t F,
  * child, else 0 (its exclusive scan is route_hist_level's chunk_off); also scatters split[s].gain into node_gain[slot_node[s]]
  * when node_gain != NULL (TreeEnsembleModel.featureImportances needs the gains; MLlib keeps them in the Node objects). */
 int b200flow_plan_route(int32_t n_slots, const b200flow_split* split, const int64_t* seg_begin, const int64_t* seg_end,
-                        int32_t chunk_rows, const int32_t* slot_node, double* node_gain, int32_t* n_chunks, void* stream);
+                        int32_t chunk_rows, const int32_t* slot_node, double* node_gain, int32_t* n_chunks,
+                        int32_t* cursors /* NULL, or int32[2 * n_slots] zeroed here for the routing pass */, void* stream);
 
 /* R7/R8 bookkeeping (inside fit: kdd99.py:79, cicids17.py:83): segment table of the next level from the parents' ranges and the partition cursors */
 int b200flow_next_segments(int32_t n_next /* or an upper bound */, const int64_t* n_next_dev /* NULL or the device-side count */,

@@ -58,7 +58,7 @@ _SIGNATURES = {
     "b200flow_route_hist_level": [_P, _I32, _I32, _P, _P, _I32, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _I32, _I32,
                                   _I32, _P, _I32, _P],
     "b200flow_partition_level": [_P, _I32, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P],
-    "b200flow_plan_route": [_I32, _P, _P, _P, _I32, _P, _P, _P, _P],
+    "b200flow_plan_route": [_I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P],
     "b200flow_next_segments": [_I32, _P, _P, _P, _P, _P, _P, _P, _P],
     "b200flow_finalize_forest": [_I64, _P, _I32, _P, _P],
     "b200flow_predict": [_P, _I32, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P],

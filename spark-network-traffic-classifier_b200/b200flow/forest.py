@@ -534,11 +534,11 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
         call("b200flow_feature_subsets", seed, ns, ptr(s_tree), ptr(s_nid), F, m, ptr(sub))
         return sub
 
-    def plan_route(ns, split_, begin_, end_, total_out, s_node=None, gain_out=None):
-        """enqueue the chunk table of a fused routing pass (+ the gains of the scored nodes); the chunk count lands in the
-        device scalar `total_out`."""
+    def plan_route(ns, split_, begin_, end_, total_out, s_node=None, gain_out=None, cursors_=None):
+        """enqueue the chunk table of a fused routing pass (+ the gains of the scored nodes, + zeroed partition cursors); the
+        chunk count lands in the device scalar `total_out`."""
         nch = torch.empty(ns, dtype=torch.int32, device=dev)
-        call("b200flow_plan_route", ns, ptr(split_), ptr(begin_), ptr(end_), route_ch, ptr(s_node), ptr(gain_out), ptr(nch))
+        call("b200flow_plan_route", ns, ptr(split_), ptr(begin_), ptr(end_), route_ch, ptr(s_node), ptr(gain_out), ptr(nch), ptr(cursors_))
         roff = torch.empty(ns + 1, dtype=torch.int64, device=dev)
         call("b200flow_exclusive_scan_i32_to_i64", ptr(nch), ns, ptr(roff), ptr(total_out))
         if PROFILE is not None:
@@ -613,6 +613,7 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
     host_cnt = torch.empty(5, dtype=torch.int64).pin_memory() if _PIN else None
     subset = level_subsets(n_slots, slot_tree, slot_nid)
     hist_ready = None                  # histogram of the CURRENT level when the fused kernel already built it
+    counters = None
     if fused and n_slots * hsz * 4 <= HIST_BUDGET_BYTES:        # (not on E: every rank must take the same collective path)
         # level 0 through the same kernel: T pseudo-parents whose split sends every entry "left" into the tree's root
         pseudo = np.zeros(T, SPLIT_DTYPE); pseudo["bin_thr"] = 255; pseudo["flags"] = 4
@@ -674,8 +675,15 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
         hist_ready = None
         # grow the pool by this level's children and emit the next level's slots
         nblk = (n_slots + 255) // 256
-        counters = torch.zeros(8 + nblk + 1, dtype=torch.int64, device=dev)   # [pool, n_next, overflow, pool_before, route chunks, ...]
-        counters[0:1].fill_(pool_size)                   # a kernel argument, not a pageable H2D copy (which would block the host)
+        if counters is None or counters.numel() < 8 + nblk + 1:
+            # [pool, n_next, overflow, pool_before, route chunks, ...] + per-block scratch; lives across levels: the pool size carries
+            # over on the device, everything else is rewritten by grow_level / the scans (no per-level fill launches)
+            fresh = torch.zeros(8 + 2 * nblk + 1024, dtype=torch.int64, device=dev)
+            if counters is None:
+                fresh[0:1].fill_(pool_size)
+            else:
+                fresh[:8] = counters[:8]
+            counters = fresh
         next_tree = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_nid = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
         next_node = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)
@@ -692,14 +700,14 @@ def _fit(src, num_classes, arity, params, row_offset=0, group=None):
         if speculative:
             # Everything the next level needs is enqueued NOW with device-side counts (children created, routing chunks);
             # the host reads the counts on a side stream while the routing pass runs, so the GPU never waits for Python.
-            roff = plan_route(n_slots, split, seg_begin, seg_end, counters[4:5], slot_node, node_gain)
+            cursors = torch.empty(2 * n_slots, dtype=torch.int32, device=dev)       # zeroed by plan_route
+            roff = plan_route(n_slots, split, seg_begin, seg_end, counters[4:5], slot_node, node_gain, cursors)
             ev_planned = torch.cuda.Event(); ev_planned.record()
             with torch.cuda.stream(side_stream):
                 side_stream.wait_event(ev_planned)
                 cnt = counters[:5].to("cpu", non_blocking=True) if host_cnt is None else host_cnt.copy_(counters[:5], non_blocking=True)
                 ev_read = torch.cuda.Event(); ev_read.record(side_stream)
             next_subset = level_subsets(n_cap, next_tree, next_nid)
-            cursors = torch.zeros(2 * n_slots, dtype=torch.int32, device=dev)
             # children at level + 1 == maxDepth - 1 are scored but never split further into routed nodes: their entries are not written
             hist_next = run_route(roff, counters[4:5], n_slots, split, child_slot, cursors, next_subset, n_cap,
                                   route=level + 2 < p.max_depth)

@@ -447,9 +447,10 @@ __global__ void __launch_bounds__(kGrowBlock) grow_write_kernel(
 __global__ void __launch_bounds__(256) plan_route_kernel(int n_slots, const b200flow_split* __restrict__ split,
                                                          const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end,
                                                          int chunk_rows, const int32_t* __restrict__ slot_node, double* node_gain,
-                                                         int32_t* n_chunks) {
+                                                         int32_t* n_chunks, int32_t* cursors) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
+    if (cursors) { cursors[2 * s] = 0; cursors[2 * s + 1] = 0; }          // the routing pass counts into them
     const int flags = split[s].flags;
     const bool routed = !(flags & 1) && (flags & 6) != 6;
     const int64_t len = seg_end[s] - seg_begin[s];
@@ -909,10 +910,11 @@ extern "C" int b200flow_grow_level(int32_t n_slots, const int32_t* slot_tree, co
 }
 
 extern "C" int b200flow_plan_route(int32_t n_slots, const b200flow_split* split, const int64_t* seg_begin, const int64_t* seg_end,
-                                   int32_t chunk_rows, const int32_t* slot_node, double* node_gain, int32_t* n_chunks, void* stream) {
+                                   int32_t chunk_rows, const int32_t* slot_node, double* node_gain, int32_t* n_chunks, int32_t* cursors,
+                                   void* stream) {
     if (n_slots <= 0) return B200FLOW_OK;
     B2F_REQUIRE(split && seg_begin && seg_end && n_chunks && chunk_rows > 0 && (!node_gain || slot_node), "plan_route: bad arguments");
-    plan_route_kernel<<<(n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_slots, split, seg_begin, seg_end, chunk_rows, slot_node, node_gain, n_chunks);
+    plan_route_kernel<<<(n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_slots, split, seg_begin, seg_end, chunk_rows, slot_node, node_gain, n_chunks, cursors);
     return check_launch("plan_route");
 }
 
