@@ -525,6 +525,13 @@ __global__ void __launch_bounds__(256) partition_level_kernel(
 #ifndef B2F_EVICT_FIRST
 #define B2F_EVICT_FIRST 1
 #endif
+#ifndef B2F_GRAN
+#define B2F_GRAN 16
+#endif
+constexpr int kGran = B2F_GRAN;                       // bytes per LDGSTS granule of the record gather (16, 8 or 4)
+// granules per staged record, and the tile's record pitch in granules (odd for 8 / 4-byte granules: fewer LDS.U8 bank conflicts)
+__host__ __device__ inline int route_granules(int F) { return (F + 1 + kGran - 1) / kGran; }
+__host__ __device__ inline int route_pitch(int F) { return kGran == 16 ? route_granules(F) : (route_granules(F) | 1); }
 constexpr bool kEvictFirst = B2F_EVICT_FIRST != 0;   // entry stream with L2::evict_first (records stay L2-resident)
 
 struct RouteChunk { int32_t slot; int32_t n; long long begin; };   // 16 bytes, one per chunk
@@ -565,9 +572,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) rou
     const int m = M > 0 ? M : a.m;
     const int F = a.F;
     const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
-    const int nq = (F + 1 + 15) / 16;                        // staged 16-byte quads per record
+    const int nq = route_granules(F);                        // staged granules (16-byte quads by default) per record
+    const int rs = route_pitch(F) * kGran;                   // bytes per staged record
     const int nbC = a.n_bins * a.C, hsz = m * nbC;
-    const int tile_words = nq * kSub * 4;
+    const int tile_words = rs * kSub / 4;
     uint32_t* tile = sm_u32 + (size_t)wid * tile_words;      // this warp's [kSub][nq] quad tile (entry-major)
     uint32_t* sh_hist = sm_u32 + (size_t)NW * tile_words;    // [2][hsz]
     int* sh_fpos = (int*)(sh_hist + 2 * hsz);                // [2][m]: byte offset of the feature inside a staged record
@@ -599,14 +607,18 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) rou
     // after lane: neighbouring lanes fetch neighbouring quads of the SAME record (same 32-byte sector) into neighbouring
     // shared addresses, which the L1 fills with fewer wavefronts than one scattered 16-byte fill per lane (ncu source page:
     // 23 instead of 31 wavefronts per LDGSTS).
-    const uint32_t inv_nq = 65536u / (uint32_t)nq + 1u;         // c / nq == (c * inv_nq) >> 16 for c < 1024
+    const uint32_t inv_nq = (1u << 20) / (uint32_t)nq + 1u;     // c / nq == (c * inv_nq) >> 20 for c * nq < 2^20
     auto issue_gather = [&](const int4& d, const b2f_entry* x) {
         const int cn = count_of(d);
         for (int c = lane; c < kSub * nq; c += 32) {           // uniform trip count (KS * nq)
-            const int e = (int)(((uint32_t)c * inv_nq) >> 16), q = c - e * nq;
+            const int e = (int)(((uint32_t)c * inv_nq) >> 20), q = c - e * nq;
             uint32_t r = __shfl_sync(0xffffffffu, x[0].x, e & 31);
             if (KS == 2) { const uint32_t r1 = __shfl_sync(0xffffffffu, x[KS - 1].x, e & 31); r = e < 32 ? r : r1; }
-            if (e < cn) cp_async16(tile + c * 4, a.tp + (int64_t)r * a.stride + q * 16);
+            if (e < cn) {
+                uint8_t* dst = (uint8_t*)tile + e * rs + q * kGran;
+                const uint8_t* src = a.tp + (int64_t)r * a.stride + q * kGran;
+                if (kGran == 16) cp_async16(dst, src); else if (kGran == 8) cp_async8(dst, src); else cp_async4(dst, src);
+            }
         }
         cp_async_commit();
     };
@@ -634,7 +646,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) rou
     entries_of(d0, e);
     entries_of(d1, f);
     int cur_slot = -1;
-    const int rs = nq * 16;                                    // bytes per staged record
     const int lab_pos = F;                                     // byte of the label inside a staged record
     const uint8_t* tile8 = (const uint8_t*)tile;               // [kSub entries][nq * 16 bytes]
     for (int64_t c = c0; c < c1; ++c) {
@@ -737,8 +748,7 @@ constexpr size_t kSmemPerSM = 227 * 1024;                  // 232,448 B usable p
 constexpr size_t kSmemCtaOverhead = 1024 + 128;            // driver reservation per CTA + the kernel's static shared memory
 
 static size_t route_hist_smem(int F, int mp, int n_bins, int C, int nw, int ks) {
-    const size_t nq = (size_t)(F + 1 + 15) / 16;
-    return (size_t)nw * ks * 32 * nq * 16 + 2 * (size_t)mp * n_bins * C * 4 + 2 * (size_t)mp * 4 + 64;
+    return (size_t)nw * ks * 32 * route_pitch(F) * kGran + 2 * (size_t)mp * n_bins * C * 4 + 2 * (size_t)mp * 4 + 64;
 }
 static int route_max_ctas(int nw) { return nw == 8 ? 4 : (nw == 16 ? 2 : 1); }   // __launch_bounds__
 
