@@ -3,7 +3,8 @@
 RandomForestClassifier / DecisionTreeClassifier (kdd99.py:61,64; cicids17.py:65,68) are the hot path and run
 entirely on the b200flow CUDA kernels (histogram build, Gini split scoring, batch predict).
 LogisticRegression and NaiveBayes (kdd99.py:57,67; cicids17.py:61,71) are OUT of the kernel scope (SURVEY.md
-§8f rank 4): they are small torch implementations that exist only so the reference scripts run to completion.
+§8f rank 4): torch fp64 implementations of MLlib's statistics / objective (b200flow/linear.py), checked against a numpy
+restatement and scikit-learn in tests/test_linear_models.py.
 """
 import zlib
 
@@ -12,6 +13,7 @@ import torch
 
 from b200flow import dist as bdist
 from b200flow import forest as fr
+from b200flow import linear as _linear
 
 from . import Estimator, Model
 from ..sql import ColumnData
@@ -278,8 +280,7 @@ class _ProbModel(Model):
     _defaults = {"featuresCol": "features", "labelCol": "label", "predictionCol": "prediction",
                  "probabilityCol": "probability", "rawPredictionCol": "rawPrediction"}
 
-    def _emit(self, df, raw):
-        prob = torch.softmax(raw, 1)
+    def _emit(self, df, raw, prob):
         pred = torch.argmax(raw, 1).to(torch.float64)
         cols = dict(df._cols)
         cols[self.getOrDefault("rawPredictionCol")] = ColumnData("vector", raw, "f64")
@@ -289,8 +290,8 @@ class _ProbModel(Model):
 
 
 class LogisticRegression(Estimator):
-    """Multinomial elastic-net logistic regression on standardized features, proximal gradient (FISTA) — a
-    functional stand-in for MLlib's OWLQN (not a parity target; kdd99.py:57, cicids17.py:61)."""
+    """Multinomial / binomial elastic-net logistic regression with MLlib's objective (standardised features, unpenalised
+    intercepts), minimised by OWL-QN: b200flow/linear.py (kdd99.py:57-58, cicids17.py:61-62)."""
     _defaults = dict(_ProbModel._defaults, maxIter=100, regParam=0.0, elasticNetParam=0.0, tol=1e-6, fitIntercept=True,
                      standardization=True, family="auto", threshold=0.5)
 
@@ -302,53 +303,47 @@ class LogisticRegression(Estimator):
 
     def _fit(self, df):
         x, y, C, _ = _features_and_labels(df, self)
-        x = x.to(torch.float64); n, D = x.shape
-        std = x.std(0, unbiased=True); inv = torch.where(std > 0, 1.0 / std, torch.zeros_like(std))
-        xs = x * inv
-        Y = torch.nn.functional.one_hot(y.long(), C).to(torch.float64)
-        lam, alpha = float(self.getOrDefault("regParam")), float(self.getOrDefault("elasticNetParam"))
-        l1, l2 = lam * alpha, lam * (1.0 - alpha)
-        W = torch.zeros((D, C), dtype=torch.float64, device=x.device)
-        pri = Y.mean(0).clamp_min(1e-12)
-        b = torch.log(pri) - torch.log(pri).mean()
-        L = 0.25 * float((xs * xs).sum(1).mean().item()) + l2 + 1e-12     # Lipschitz bound of the smooth part
-        Z, t = W.clone(), 1.0
-        for _ in range(int(self.getOrDefault("maxIter"))):
-            P = torch.softmax(xs @ Z + b, 1)
-            G = xs.t() @ (P - Y) / n + l2 * Z
-            if self.getOrDefault("fitIntercept"):
-                b = b - (P - Y).mean(0) / 0.25
-            Wn = Z - G / L
-            Wn = torch.sign(Wn) * torch.clamp(Wn.abs() - l1 / L, min=0.0)
-            tn = 0.5 * (1.0 + (1.0 + 4.0 * t * t) ** 0.5)
-            Z = Wn + ((t - 1.0) / tn) * (Wn - W)
-            W, t = Wn, tn
-        m = LogisticRegressionModel((W * inv[:, None]).contiguous(), b, C)
+        g = self.getOrDefault
+        if g("family") not in ("auto", "binomial", "multinomial"):
+            raise IllegalArgumentException("family must be auto, binomial or multinomial")
+        try:
+            fit = _linear.lr_fit(x, y, C, max_iter=int(g("maxIter")), reg_param=float(g("regParam")), elastic_net=float(g("elasticNetParam")),
+                                 tol=float(g("tol")), fit_intercept=bool(g("fitIntercept")), standardization=bool(g("standardization")),
+                                 family=g("family"))
+        except ValueError as e:
+            raise IllegalArgumentException(str(e))
+        m = LogisticRegressionModel(fit, C)
         m._paramMap = {k: v for k, v in self._paramMap.items() if k in m._all_defaults()}
         return m
 
 
+class _TrainingSummary:
+    def __init__(self, hist, iterations):
+        self.objectiveHistory, self.totalIterations = list(hist), int(iterations)
+
+
 class LogisticRegressionModel(_ProbModel):
-    def __init__(self, W, b, C):
+    def __init__(self, fit, C):
         super().__init__()
-        self._W, self._b, self.numClasses = W, b, C
+        self._fit_result, self.numClasses = fit, C
+        self.summary = _TrainingSummary(fit.objective_history, fit.iterations)
 
     @property
     def coefficientMatrix(self):
-        return self._W.t().cpu().numpy()
+        return self._fit_result.coef.cpu().numpy()
 
     @property
     def interceptVector(self):
-        return self._b.cpu().numpy()
+        return self._fit_result.intercept.cpu().numpy()
 
     def _transform(self, df):
-        x = df._cols[self.getOrDefault("featuresCol")].data.to(torch.float64)
-        return self._emit(df, x @ self._W + self._b)
+        raw = _linear.lr_raw(self._fit_result, df._cols[self.getOrDefault("featuresCol")].data)
+        return self._emit(df, raw, _linear.lr_probability(self._fit_result, raw))
 
 
 class NaiveBayes(Estimator):
-    """Multinomial naive Bayes with Laplace smoothing (kdd99.py:67, cicids17.py:71); rejects negative features
-    as MLlib does (the reason for the where-filters at cicids17.py:30-35)."""
+    """Multinomial naive Bayes with MLlib's smoothed prior and likelihood (b200flow/linear.py; kdd99.py:67, cicids17.py:71);
+    rejects negative features as MLlib does (the reason for the where-filters at cicids17.py:30-35)."""
     _defaults = dict(_ProbModel._defaults, smoothing=1.0, modelType="multinomial")
 
     def __init__(self, featuresCol=None, labelCol=None, predictionCol=None, probabilityCol=None, rawPredictionCol=None,
@@ -360,33 +355,28 @@ class NaiveBayes(Estimator):
         if self.getOrDefault("modelType") != "multinomial":
             raise IllegalArgumentException("only modelType='multinomial' is implemented")
         x, y, C, _ = _features_and_labels(df, self)
-        x = x.to(torch.float64)
-        if bool((x < 0).any().item()):
-            raise IllegalArgumentException("requirement failed: Naive Bayes requires nonnegative feature values but found a negative value.")
-        Y = torch.nn.functional.one_hot(y.long(), C).to(torch.float64)
-        lam = float(self.getOrDefault("smoothing"))
-        cls_n = Y.sum(0)
-        feat = Y.t() @ x                                             # [C, D] per-class feature sums
-        pi = torch.log(cls_n + lam) - torch.log(cls_n.sum() + C * lam)
-        theta = torch.log(feat + lam) - torch.log(feat.sum(1, keepdim=True) + x.shape[1] * lam)
-        m = NaiveBayesModel(pi, theta, C)
+        try:
+            fit = _linear.nb_fit(x, y, C, float(self.getOrDefault("smoothing")))
+        except ValueError as e:
+            raise IllegalArgumentException(str(e))
+        m = NaiveBayesModel(fit, C)
         m._paramMap = {k: v for k, v in self._paramMap.items() if k in m._all_defaults()}
         return m
 
 
 class NaiveBayesModel(_ProbModel):
-    def __init__(self, pi, theta, C):
+    def __init__(self, fit, C):
         super().__init__()
-        self._pi, self._theta, self.numClasses = pi, theta, C
+        self._fit_result, self.numClasses = fit, C
 
     @property
     def pi(self):
-        return self._pi.cpu().numpy()
+        return self._fit_result.pi.cpu().numpy()
 
     @property
     def theta(self):
-        return self._theta.cpu().numpy()
+        return self._fit_result.theta.cpu().numpy()
 
     def _transform(self, df):
-        x = df._cols[self.getOrDefault("featuresCol")].data.to(torch.float64)
-        return self._emit(df, x @ self._theta.t() + self._pi)
+        raw = _linear.nb_raw(self._fit_result, df._cols[self.getOrDefault("featuresCol")].data)
+        return self._emit(df, raw, torch.softmax(raw, 1))
