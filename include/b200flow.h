@@ -360,6 +360,48 @@ int b200flow_compact_rows(const void* rows, int64_t n_rows, int32_t row_bytes,
                           const uint8_t* flag, int32_t want, void* out_rows,
                           int64_t* scratch, int64_t* n_kept, void* stream);
 
+/* -------------------------------------------------- CSV text -> flow records ---
+ * replaces `spark.read.csv(path, inferSchema=True, header=...)` at kdd99.py:25 and
+ * cicids17.py:19-20.  The caller copies the file's bytes to the device (16-byte aligned) and owns every buffer.
+ * Unquoted fields, ',' delimiter, LF or CRLF line ends, blank lines skipped (univocity's default).
+ * Column classes follow Spark's inference order; parsing is exact (Java parseInt / parseDouble semantics, see
+ * csrc/csv_number.h) or the field is counted in bad[] — never approximated. */
+#define B200FLOW_CSV_NULL   0
+#define B200FLOW_CSV_INT32  1
+#define B200FLOW_CSV_INT64  2   /* inference only: such a column is read as DOUBLE (the record layout has no int64) */
+#define B200FLOW_CSV_DOUBLE 3
+#define B200FLOW_CSV_STRING 4   /* stored as an int32 dictionary code; -1 = null */
+typedef struct b200flow_csv_col {
+    int32_t type;       /* B200FLOW_CSV_INT32 / DOUBLE / STRING */
+    int32_t rec_off;    /* byte offset of the field inside the output record (4-byte aligned) */
+    int32_t str_index;  /* STRING: which dictionary table (0..n_string_columns-1) */
+    int32_t reserved;
+} b200flow_csv_col;
+/* bad[8] (device, zero-initialised except [1] and [5] = ~0): [0] rows whose field count != n_cols, [1] first such row,
+ * [2] rows longer than 4096 bytes, [3] fields that do not parse as their column's type, [4] numeric literals outside the
+ * exact range (more than 19 digits that straddle a rounding boundary, |exponent| > 27), [5] first (row << 16 | col) of
+ * [3]/[4], [6] dictionary table full, [7] dictionary lookups that failed (hash collision). */
+
+/* line index, step 1: counts[b] = non-empty lines starting in text block b (4096 bytes each); flags[0] bit 0 = a '"' was seen */
+int b200flow_csv_count_lines(const uint8_t* text, int64_t n_bytes, int32_t* counts, unsigned long long* flags, void* stream);
+/* line index, step 2: bases = exclusive prefix sum of counts (int64); row_starts[i] = byte offset of non-empty line i */
+int b200flow_csv_line_starts(const uint8_t* text, int64_t n_bytes, const int64_t* bases, int64_t* row_starts, void* stream);
+/* inferSchema: col_class[c] = max over rows of the field's class (atomicMax into zeroed int32[n_cols]), col_null[c] = 1 if
+ * any field of the column is empty.  flags: bit 0 ignoreLeadingWhiteSpace, bit 1 ignoreTrailingWhiteSpace. */
+int b200flow_csv_infer(const uint8_t* text, int64_t n_bytes, const int64_t* row_starts, int64_t n_rows, int32_t n_cols,
+                       int32_t flags, int32_t* col_class, int32_t* col_null, unsigned long long* bad, void* stream);
+/* string columns: keys [n_str][2^cap_log2] (zeroed) receive the 64-bit FNV-1a hash of every distinct value, pos_len
+ * (filled with INT64_MAX) the smallest (byte offset << 16 | length) at which it occurs — order of first appearance */
+int b200flow_csv_dictionary(const uint8_t* text, int64_t n_bytes, const int64_t* row_starts, int64_t n_rows, int32_t n_cols,
+                            int32_t flags, const b200flow_csv_col* cols, unsigned long long* keys, long long* pos_len,
+                            int32_t cap_log2, unsigned long long* bad, void* stream);
+/* fields -> records[n_rows][row_bytes]; slot_code[n_str][2^cap_log2] = dictionary code of each occupied slot (the host
+ * assigns codes after reading the tables); a STRING field must byte-equal its slot's first occurrence or bad[7] counts it */
+int b200flow_csv_parse(const uint8_t* text, int64_t n_bytes, const int64_t* row_starts, int64_t n_rows, int32_t n_cols,
+                       int32_t flags, const b200flow_csv_col* cols, const unsigned long long* keys, const long long* pos_len,
+                       const int32_t* slot_code, int32_t cap_log2, void* records, int32_t row_bytes, unsigned long long* bad,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

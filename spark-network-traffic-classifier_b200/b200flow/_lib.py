@@ -67,6 +67,11 @@ _SIGNATURES = {
     "b200flow_confusion": [_P, _P, _I64, _I32, _P, _P],
     "b200flow_random_split": [_U64, _I64, _I64, _P, _I32, _P, _P],
     "b200flow_compact_rows": [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P],
+    "b200flow_csv_count_lines": [_P, _I64, _P, _P, _P],
+    "b200flow_csv_line_starts": [_P, _I64, _P, _P, _P],
+    "b200flow_csv_infer": [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _P],
+    "b200flow_csv_dictionary": [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _P],
+    "b200flow_csv_parse": [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _I32, _P, _P],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["b200flow_last_error", "b200flow_version", "b200flow_route_hist_config"])
 

@@ -20,6 +20,10 @@ from b200flow.encode import RecordSchema
 
 
 # ----------------------------------------------------------------------------------- columns
+class AnalysisException(Exception):
+    """pyspark.sql.utils.AnalysisException: what spark.read raises for input it cannot load"""
+
+
 class ColumnData:
     """One DataFrame column.  kind: 'field' (lives in the record buffer), 'numeric' ([n] tensor),
     'vector' ([n, D] tensor).  meta carries ML attributes (nominal values / per-slot attrs);
@@ -455,7 +459,8 @@ def _read_csv(paths, header, inferSchema, strip_lead, strip_trail, device):
     frames = []
     for p in paths:
         pdf = pd.read_csv(p, header=0 if header else None, skipinitialspace=bool(strip_lead), low_memory=False,
-                          dtype=None if inferSchema else str, keep_default_na=True, encoding="utf-8", encoding_errors="replace")
+                          dtype=None if inferSchema else str, keep_default_na=True, encoding="utf-8", encoding_errors="replace",
+                          float_precision="round_trip")
         if header:
             cols = [str(c) for c in pdf.columns]
             cols = [c.strip() if (strip_lead or strip_trail) else c for c in cols]
@@ -516,8 +521,20 @@ class DataFrameReader:
             paths.extend(hits)
         if not paths:
             raise FileNotFoundError("Path does not exist: %s" % path)
-        rec, rschema, dicts = _read_csv(paths, header, infer, _truthy(ignoreLeadingWhiteSpace), _truthy(ignoreTrailingWhiteSpace),
-                                        torch.device("cuda", torch.cuda.current_device()))
+        lead = _truthy(ignoreLeadingWhiteSpace if ignoreLeadingWhiteSpace is not None else o.get("ignoreLeadingWhiteSpace", False))
+        trail = _truthy(ignoreTrailingWhiteSpace if ignoreTrailingWhiteSpace is not None else o.get("ignoreTrailingWhiteSpace", False))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        engine = str(o.get("b200flow.csvEngine", "device")).lower()
+        if engine == "device":                                   # csrc/csv.cu: index, inference, dictionaries and parsing on the GPU
+            from b200flow import csvio
+            try:
+                rec, rschema, dicts = csvio.read_csv(paths, header, infer, lead, trail, dev)
+            except csvio.CsvFormatError as e:
+                raise AnalysisException(str(e))
+        elif engine == "host":                                   # explicit opt-in (quoted fields): pandas on the host, then one H2D copy
+            rec, rschema, dicts = _read_csv(paths, header, infer, lead, trail, dev)
+        else:
+            raise ValueError("b200flow.csvEngine must be 'device' or 'host'")
         return DataFrame._from_records(rec, rschema, dicts, self._session)
 
 
