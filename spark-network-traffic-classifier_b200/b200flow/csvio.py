@@ -27,48 +27,68 @@ class CsvFormatError(B200FlowError, ValueError):
     """input the device CSV reader does not accept (it never guesses): quoted fields, ragged rows, inexact literals"""
 
 
+_STAGE_BYTES = 32 << 20
+_stage = []                              # two pinned staging blocks, allocated once (page-locking costs more than the copy)
+
+
 def _load_text(paths, device):
-    """files -> one device byte buffer (each file ends with a newline), its pinned host twin, and the files' base offsets."""
+    """files -> one device byte buffer (every file ends with a newline) + the files' base offsets + each file's first 64 KB.
+    Double-buffered: the next block is read from the file while the previous one is on its way to the GPU."""
     import os
     sizes = [os.path.getsize(p) for p in paths]
     total = sum(s + 1 for s in sizes)
-    pad = (-total) % 16 + 16
-    host = torch.empty(total + pad, dtype=torch.uint8).pin_memory()
-    view = host.numpy()
-    bases, o = [], 0
+    text = torch.empty(total + (-total) % 16 + 16, dtype=torch.uint8, device=device)
+    if not _stage:
+        _stage.extend(torch.empty(_STAGE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2))
+    copy_stream = torch.cuda.Stream(device)
+    copy_stream.wait_stream(torch.cuda.current_stream(device))
+    free = [None, None]                                                  # event: the block's last copy has left the host
+    bases, heads, o, k = [], [], 0, 0
     for p, s in zip(paths, sizes):
         bases.append(o)
+        last = 0x0A
         with open(p, "rb") as f:
-            got = f.readinto(memoryview(view[o:o + s]))
-        if got != s:
-            raise IOError("short read of %s" % p)
-        o += s
-        if s == 0 or view[o - 1] != 0x0A:
-            view[o] = 0x0A; o += 1
-    view[o:] = 0x0A
-    n_bytes = o
-    text = host.to(device, non_blocking=True)
-    return text, view, n_bytes, bases
+            done = 0
+            while done < s:
+                blk = _stage[k & 1]
+                if free[k & 1] is not None:
+                    free[k & 1].synchronize()
+                got = f.readinto(memoryview(blk.numpy())[:min(_STAGE_BYTES, s - done)])
+                if not got:
+                    raise IOError("short read of %s" % p)
+                if done == 0:
+                    heads.append(bytes(blk.numpy()[:min(got, 1 << 16)]))
+                last = int(blk[got - 1])
+                with torch.cuda.stream(copy_stream):
+                    text[o:o + got].copy_(blk[:got], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(copy_stream); free[k & 1] = ev
+                o += got; done += got; k += 1
+        if s == 0:
+            heads.append(b"")
+        if last != 0x0A:
+            with torch.cuda.stream(copy_stream):
+                text[o:o + 1].fill_(0x0A)
+            o += 1
+    with torch.cuda.stream(copy_stream):
+        text[o:].fill_(0x0A)
+    torch.cuda.current_stream(device).wait_stream(copy_stream)
+    return text, o, bases, heads
 
 
-def _first_line(view, start, end):
-    """(offset, bytes) of the first non-empty line in view[start:end] (host; only used for the header / column count)"""
-    o = start
-    while o < end:
-        chunk = view[o:min(end, o + (1 << 16))].tobytes()
-        nl = chunk.find(b"\n")
+def _first_line(head):
+    """(offset, bytes) of the first non-empty line of a file, from its first 64 KB (host; header / column count only)"""
+    o = 0
+    while o < len(head):
+        nl = head.find(b"\n", o)
         if nl < 0:
-            chunk = view[o:end].tobytes()
-            nl = chunk.find(b"\n")
-            if nl < 0:
-                nl = len(chunk)
-        line = chunk[:nl]
+            nl = len(head)
+        line = head[o:nl]
         if line.endswith(b"\r"):
             line = line[:-1]
         if line:
             return o, line
-        o += nl + 1
-    return end, b""
+        o = nl + 1
+    return len(head), b""
 
 
 def _dedup_names(names):
@@ -112,18 +132,30 @@ def _raise_bad(bad, names, what):
         raise CsvFormatError("%s: %d string field(s) collide in the 64-bit dictionary hash" % (what, int(b[7])))
 
 
-def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_trail=False, device=None):
-    """-> (records uint8[n_rows, row_bytes] on the device, RecordSchema, {string column: [values in order of first appearance]})"""
+def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_trail=False, device=None, stats=None):
+    """-> (records uint8[n_rows, row_bytes] on the device, RecordSchema, {string column: [values in order of first appearance]})
+    stats (optional dict): receives the wall time of each phase in seconds (adds a device synchronize per phase)."""
+    import time
     require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     paths = list(paths)
-    text, view, n_bytes, bases = _load_text(paths, dev)
+    t_last = [time.perf_counter()]
+
+    def lap(name):
+        if stats is not None:
+            torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            stats[name] = stats.get(name, 0.0) + now - t_last[0]
+            t_last[0] = now
+
+    text, n_bytes, bases, heads = _load_text(paths, dev)
+    lap("read_files_h2d_s")
     flags = (1 if strip_lead else 0) | (2 if strip_trail else 0)
     row_starts, saw_quote = index_lines(text, n_bytes)
+    lap("line_index_s")
     if saw_quote:
         raise CsvFormatError("quoted fields are not supported by the device CSV reader (use option('b200flow.csvEngine', 'host'))")
-    ends = bases[1:] + [n_bytes]
-    first = [_first_line(view, b, e) for b, e in zip(bases, ends)]
+    first = [(b + o, ln) for b, (o, ln) in zip(bases, (_first_line(h) for h in heads))]
     lead = next((ln for _, ln in first if ln), b"")
     if header:
         names = [c.decode("utf-8", "replace") for c in lead.split(b",")]
@@ -150,6 +182,7 @@ def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_tr
         col_class, col_null = cls[:n_cols], cls[n_cols:]
     else:
         col_class, col_null = np.full(n_cols, CSV_STRING, np.int32), np.zeros(n_cols, np.int32)
+    lap("infer_schema_s")
     fields, cols = [], np.zeros(n_cols, COL_DTYPE)
     str_cols = []
     for c, name in enumerate(names):
@@ -189,13 +222,20 @@ def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_tr
         _raise_bad(bad, names, "dictionary")
         occ_h, pl_h = occ.cpu().numpy(), pos_len.cpu().numpy()
         code_h = np.full(occ_h.shape, -1, np.int32)
+        # the distinct values' bytes: one gather on the device, one copy back
+        v_all = pl_h[occ_h]
+        lens = (v_all & 0xFFFF).astype(np.int64)
+        ends_ = np.cumsum(lens)
+        idx = np.repeat((v_all >> 16) - (ends_ - lens), lens) + np.arange(int(ends_[-1]) if len(ends_) else 0)
+        blob = text[torch.from_numpy(idx).to(dev)].cpu().numpy().tobytes() if len(idx) else b""
+        at = dict(zip(v_all.tolist(), (ends_ - lens).tolist()))
         for si, c in enumerate(str_cols):
             slots = np.nonzero(occ_h[si])[0]
             slots = slots[np.argsort(pl_h[si, slots], kind="stable")]        # order of first appearance in the file(s)
             values, code_of = [], {}
             for sl in slots:
-                v = int(pl_h[si, sl]); o, ln = v >> 16, v & 0xFFFF
-                s = bytes(view[o:o + ln]).decode("utf-8", "replace")
+                v = int(pl_h[si, sl]); ln = v & 0xFFFF
+                s = blob[at[v]:at[v] + ln].decode("utf-8", "replace")
                 if s not in code_of:
                     code_of[s] = len(values); values.append(s)
                 code_h[si, sl] = code_of[s]
@@ -204,6 +244,7 @@ def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_tr
     for c in str_cols:
         dicts.setdefault(names[c], [])
 
+    lap("dictionaries_s")
     # ---- fields -> records
     rec = torch.zeros((max(n_rows, 1), schema.row_bytes), dtype=torch.uint8, device=dev)
     if n_rows:
@@ -211,4 +252,5 @@ def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_tr
         call("b200flow_csv_parse", ptr(text), n_bytes, ptr(row_starts), n_rows, n_cols, flags, ptr(cols_d), ptr(keys), ptr(pos_len), ptr(slot_code),
              cap_log2, ptr(rec), schema.row_bytes, ptr(bad))
         _raise_bad(bad, names, "parse")
+    lap("parse_s")
     return rec[:n_rows], schema, dicts

@@ -40,14 +40,10 @@ def main():
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
     out["device_s"] = float(np.median(ts)); out["device_GBps"] = size / out["device_s"] / 1e9; out["device_rows_per_s"] = n / out["device_s"]
-    # kernels only (text already resident): events around the four passes
-    text, view, nb, bases = csvio._load_text([p], torch.device("cuda"))
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    rs, _ = csvio.index_lines(text, nb)
-    e1.record(); torch.cuda.synchronize()
-    out["index_ms"] = e0.elapsed_time(e1)
+    phases = {}
+    for _ in range(3):
+        csvio.read_csv([p], False, True, stats=phases)
+    out["phases_ms"] = {k: round(v / 3 * 1e3, 3) for k, v in phases.items()}
     t0 = time.perf_counter()
     pd.read_csv(p, header=None, float_precision="round_trip")
     out["pandas_s"] = time.perf_counter() - t0
