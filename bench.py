@@ -555,6 +555,8 @@ def main():
     bound = {"route_hist_level": "lsu (shared-memory pipe: tile fills + tile reads + atomics), not hbm",
              "hist_level": "lsu / record gather", "encode_bins": "issue + shared-memory (binary search), not hbm",
              "predict": "l1 latency (divergent tree walk)", "encode": "hbm"}.get(dom, "hbm")
+    if dom == "route_hist_level" and ctr.get("lsu_pct") is not None and ctr["lsu_pct"] < 60:
+        bound = "gather latency (wide nodes: long-scoreboard stall, one record gather in flight per warp), not hbm"    # ncu: profiles/r02_route_hist_*_ncu.txt
     roofline = {"kernel": dom, "bound": bound, "achieved": d.get("achieved_gbs"), "peak": peak, "unit": "GB/s",
                 "frac": d.get("frac_of_hbm_peak"), "traffic": traffic, "peak_source": peak_src,
                 "dram_frac": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None,

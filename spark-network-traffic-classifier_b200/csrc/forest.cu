@@ -12,6 +12,7 @@
 // with sparse global REDs, so the multi-GPU all-reduce sees one dense uint32 buffer per level.
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -512,7 +513,9 @@ __global__ void __launch_bounds__(256) partition_level_kernel(
 //   * the gather brings each entry's 64-byte-aligned TreePoint record (one HBM burst) into a shared-memory tile,
 //     ONCE per entry per level — partition_level + hist_level gathered it twice and were bound by exactly that;
 //   * every entry is routed by the parent's split and accumulated into its CHILD's histogram (child feature subset)
-//     in shared memory; the lanes that hit the same counter as the first active lane are merged (top-group merge);
+//     in shared memory with shared atomics; lane i takes the child's subset features in the ROTATED order (i + t) % m, so
+//     that one warp instruction spreads over all m features: the byte reads of the tile fall on random banks instead of
+//     a guaranteed 4-way conflict (48-byte pitch), and at most 32 / m lanes can meet on one hot counter;
 //   * kept entries go to the child's range (left grows up from seg_begin, right grows down from seg_end; one cursor
 //     reservation per warp step and side); the two child histograms stay in shared memory while consecutive chunks
 //     belong to the same parent and are flushed with sparse global REDs when the parent changes.
@@ -565,7 +568,7 @@ struct RouteArgs {
 //     write-out of step t-1 (its cursor reservation, a global atomic issued one step earlier, has landed by now)
 //     route + histogram of step t from the tile
 // CTA-wide barriers happen only when the parent slot changes (flush + re-zero of the two child histograms).
-template <int M, int NW, int KS, int MERGE>   // MERGE: 0 plain shared atomics, 1 top-group merge
+template <int M, int NW, int KS, int MERGE>   // MERGE: 0 plain shared atomics (runtime m), 1 top-group merge, 2 rotated features
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) route_hist_level_kernel(const RouteArgs a) {
     extern __shared__ __align__(16) uint32_t sm_u32[];
     constexpr int kThreads = NW * 32, kSub = KS * 32;
@@ -695,7 +698,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) rou
                     uint32_t* hist = sh_hist + side * hsz;
                     const uint32_t lab = tile8[lab_pos + i * rs];
                     const uint32_t w = e[k].y;
-                    if (M > 0 && MERGE) {
+                    if (M > 0 && MERGE == 1) {
                         // top-group merge: per feature, the lanes that share the first active lane's (bin, label, child) counter are
                         // summed with ONE redux over the whole active mask (the others contribute 0: no divergence) and issue one
                         // shared atomic; the other lanes add alone.  Measured and dropped: whole-key match.any merge (46 ms per fit
@@ -712,6 +715,18 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) rou
                             const bool top = key == __shfl_sync(active, key, l0);          // same counter as the first active lane
                             const uint32_t sum = __reduce_add_sync(active, top ? w : 0u);  // no divergence: the others contribute 0
                             if (!top || lane == l0) atomicAdd(addr, top ? sum : w);
+                        }
+                    } else if (M > 0 && MERGE == 2) {
+                        // rotated features: lane i walks the subset positions in the order (i + t) % M, so that one warp
+                        // instruction spreads over all M features — the lanes 8 apart (same bank for a 48-byte pitch) read
+                        // different record words, and only ~32 / M lanes can meet on one hot counter.  Integer sums: same result.
+                        int j = lane % M;
+#pragma unroll
+                        for (int t = 0; t < M; ++t) {
+                            const int fp = fpos[j];
+                            const uint32_t bin = tile8[fp + i * rs];
+                            atomicAdd(&hist[j * nbC + bin * a.C + lab], w);
+                            j = j + 1 == M ? 0 : j + 1;
                         }
                     } else {
                         for (int j = 0; j < m; ++j) {
@@ -753,7 +768,9 @@ static size_t route_hist_smem(int F, int mp, int n_bins, int C, int nw, int ks) 
 static int route_max_ctas(int nw) { return nw == 8 ? 4 : (nw == 16 ? 2 : 1); }   // __launch_bounds__
 
 // Picks (warps per CTA, entries per lane, features per pass): the fewest passes first (every extra pass gathers the
-// records again), then the most resident warps per SM (<= 32 matter), then the most entries in flight, then the smallest chunk.
+// records again), then the most entries in flight per SM (resident warps x entries per lane; measured with the rotated
+// update, CICIDS 6-class: 8x2 with 24 warps 0.87 ms per level vs 8x1 with 32 warps 1.05), then the most resident warps,
+// then the smallest chunk.
 static bool route_cfg(int F, int m, int n_bins, int C, RouteCfg* out) {
     static const int cand[5][2] = {{8, 2}, {8, 1}, {16, 2}, {16, 1}, {32, 1}};
     int force_nw = 0, force_ks = 0;                         // tuning / test knob, read per call: B200FLOW_ROUTE_SHAPE=<warps>x<entries per lane>
@@ -774,7 +791,7 @@ static bool route_cfg(int F, int m, int n_bins, int C, RouteCfg* out) {
         int per_sm = (int)(kSmemPerSM / (smem + kSmemCtaOverhead));
         if (per_sm > route_max_ctas(nw)) per_sm = route_max_ctas(nw);
         const int warps = per_sm * nw > 32 ? 32 : per_sm * nw;
-        const long key = ((long)warps << 20) + ((long)(warps * ks) << 10) + (1023 - nw * ks);
+        const long key = ((long)(warps * ks) << 20) + ((long)warps << 10) + (1023 - nw * ks);
         if (key > best_key) { best_key = key; best = i; }
     }
     if (best < 0) return false;
@@ -785,14 +802,17 @@ static bool route_cfg(int F, int m, int n_bins, int C, RouteCfg* out) {
     return true;
 }
 
-static int route_plain_atomics() {                          // tuning knob: B200FLOW_ROUTE_VARIANT bit1 = plain atomics (no merge)
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("B200FLOW_ROUTE_VARIANT"); v = e ? (atoi(e) >> 1) & 1 : 0; }
-    return v;        // default 0 = top-group merge (per KDD-full fit: 19.0 ms; plain atomics 26 ms)
+// histogram update of the fused kernel: 2 = rotated features (default), 1 = top-group merge, 0 = generic runtime loop.
+// Tuning knob B200FLOW_ROUTE_VARIANT, read per call: "merge" / "generic" (KDD-full, route per fit: rotated 14.8 ms, merge 17.3 ms).
+static int route_hist_variant() {
+    const char* e = getenv("B200FLOW_ROUTE_VARIANT");
+    if (e && !strcmp(e, "merge")) return 1;
+    if (e && !strcmp(e, "generic")) return 0;
+    return 2;
 }
 
 template <int NW, int KS>
-static cudaError_t route_launch(int M, bool merge, unsigned grid_cap, size_t smem, int per_sm_hint, int waves, int64_t n_chunks_max,
+static cudaError_t route_launch(int M, int merge, unsigned grid_cap, size_t smem, int per_sm_hint, int waves, int64_t n_chunks_max,
                                 const RouteArgs& a, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
 #define B2F_ROUTE_GO(KERNEL)                                                                                                   \
@@ -810,7 +830,8 @@ static cudaError_t route_launch(int M, bool merge, unsigned grid_cap, size_t sme
     }
 #define B2F_ROUTE_CASE(MM)                                                                                                     \
     case MM:                                                                                                                   \
-        if (merge) B2F_ROUTE_GO((route_hist_level_kernel<MM, NW, KS, 1>))                                                      \
+        if (merge == 1) B2F_ROUTE_GO((route_hist_level_kernel<MM, NW, KS, 1>))                                                 \
+        else if (merge == 2) B2F_ROUTE_GO((route_hist_level_kernel<MM, NW, KS, 2>))                                            \
         else B2F_ROUTE_GO((route_hist_level_kernel<0, NW, KS, 0>))                                                             \
         break;
     switch (M) {
@@ -988,7 +1009,8 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     a.subset_next = subset_next; a.m_total = m; a.n_bins = n_bins; a.C = C; a.hist_next = hist_next;
     static int waves = -1;                                    // CTAs per resident slot: > 1 lets the block scheduler even out the tail
     if (waves < 0) { const char* e = getenv("B200FLOW_ROUTE_WAVES"); waves = e ? atoi(e) : 2; if (waves < 1) waves = 1; }   // measured per fit: 17.7 (1), 17.4 (2-6), 17.6 ms (8)
-    const bool merge = !route_plain_atomics() && C <= 128;
+    int merge = route_hist_variant();
+    if (merge == 1 && C > 128) merge = 2;                      // the merge key packs the label into 8 bits
     for (int j0 = 0, pass = 0; j0 < m; j0 += cfg.m_pass, ++pass) {
         a.j0 = j0; a.m = m - j0 < cfg.m_pass ? m - j0 : cfg.m_pass; a.route = (route && pass == 0) ? 1 : 0;
         const int M = a.m <= 12 ? a.m : 0;

@@ -21,6 +21,8 @@ def test_route_hist_config_covers_the_reference_scripts_shapes():
         assert cfg is not None, shape
         chunk, m_pass = cfg
         assert m_pass == shape[1] and chunk in (256, 512, 1024)
+    # the measured optima: 8x2 for the narrow nodes, 16x1 / 32x1 for the wide ones
+    assert [_lib.route_hist_config(*s)[0] for s in [(41, 7, 70, 5), (78, 9, 78, 6), (41, 7, 70, 23), (78, 9, 78, 15)]] == [512, 512, 512, 1024]
     # DecisionTree: every feature in every node -> feature passes, the first of which routes
     chunk, m_pass = _lib.route_hist_config(41, 41, 70, 23)
     assert 1 <= m_pass < 41 and 2 * m_pass * 70 * 23 * 4 <= 227 * 1024
@@ -94,6 +96,20 @@ def test_every_launch_shape_builds_the_same_forest(shape, monkeypatch):
     nw, ks = (int(v) for v in shape.split("x"))
     assert m.train_stats["route_chunk"] == nw * ks * 32
     got = m.export()
+    assert forests_equal(got, want) == [] and np.array_equal(got["gain"], want["gain"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["merge", "generic"])
+@pytest.mark.parametrize("classes", [5, 23])
+def test_histogram_update_variants_build_the_same_forest(variant, classes, monkeypatch):
+    # B200FLOW_ROUTE_VARIANT: the default rotated-feature update vs the top-group merge vs the generic runtime loop
+    rec, plan, arity, C = _kdd_records(60000, classes, 29)
+    x, y, _ = plan.run(rec, torch.float64)
+    p = fr.ForestParams(num_trees=6, max_bins=70, max_depth=9, seed=3)
+    want = fr.fit_forest(x, y, C, arity, p).export()
+    monkeypatch.setenv("B200FLOW_ROUTE_VARIANT", variant)
+    got = fr.fit_forest(x, y, C, arity, p).export()
     assert forests_equal(got, want) == [] and np.array_equal(got["gain"], want["gain"])
 
 
