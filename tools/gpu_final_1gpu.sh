@@ -18,12 +18,8 @@ timeout 200 python tools/timeline.py --workload kdd_full > $O/timeline_kdd_full.
 timeout 200 python tools/timeline.py --workload kdd_script > $O/timeline_kdd_script.txt 2>&1
 # launch list of the bench command (serialised, cold-cache: compare shares)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/launches_kdd_full.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $O/launches_kdd_full.log 2>&1
-NCU="ncu --set full --clock-control none --import-source on"
-timeout 400 $NCU -k regex:route_hist_level -s 9 -c 1 -o $O/ncu_route_kdd_full python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $O/ncu_route_kdd_full.log 2>&1
-timeout 400 $NCU -k regex:"encode_bins|score_level|predict_kernel|bag_weights" -s 0 -c 12 -o $O/ncu_misc_kdd_full python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $O/ncu_misc_kdd_full.log 2>&1
-timeout 400 $NCU -k regex:route_hist_level -s 3 -c 1 -o $O/ncu_route_cicids_full python bench.py --workload cicids_full --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $O/ncu_route_cicids_full.log 2>&1
-timeout 400 $NCU -k regex:route_hist_level -s 3 -c 1 -o $O/ncu_route_kdd_script python bench.py --workload kdd_script --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $O/ncu_route_kdd_script.log 2>&1
-timeout 400 $NCU -k regex:"encode_kernel<float>" -c 2 -o $O/ncu_encode python tools/bench_encode.py --iters 1 > $O/ncu_encode.log 2>&1
+# full ncu captures (route_hist_level per workload, misc kernels, encode, csv) are taken separately: see profiles/r02_*_ncu.txt headers
+timeout 300 python tools/bench_csv.py 1000000 > $O/csv_bench.json 2> $O/csv_bench.err
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/final/bench_*.json')):
