@@ -132,9 +132,11 @@ def _raise_bad(bad, names, what):
         raise CsvFormatError("%s: %d string field(s) collide in the 64-bit dictionary hash" % (what, int(b[7])))
 
 
-def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_trail=False, device=None, stats=None):
+def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_trail=False, device=None, stats=None, shard=None):
     """-> (records uint8[n_rows, row_bytes] on the device, RecordSchema, {string column: [values in order of first appearance]})
-    stats (optional dict): receives the wall time of each phase in seconds (adds a device synchronize per phase)."""
+    stats (optional dict): receives the wall time of each phase in seconds (adds a device synchronize per phase).
+    shard = (rank, world): one process per GPU — the line index, the column types and the dictionaries come from ALL rows
+    (every rank gets the same schema and codes), but only this rank's contiguous block of rows is converted and returned."""
     import time
     require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -245,6 +247,11 @@ def read_csv(paths, header=False, infer_schema=False, strip_lead=False, strip_tr
         dicts.setdefault(names[c], [])
 
     lap("dictionaries_s")
+    if shard is not None:
+        from .dist import shard_bounds
+        lo, hi = shard_bounds(n_rows, int(shard[0]), int(shard[1]))
+        row_starts = row_starts[lo:hi].contiguous()
+        n_rows = hi - lo
     # ---- fields -> records
     rec = torch.zeros((max(n_rows, 1), schema.row_bytes), dtype=torch.uint8, device=dev)
     if n_rows:

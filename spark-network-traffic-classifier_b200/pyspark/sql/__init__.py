@@ -525,14 +525,20 @@ class DataFrameReader:
         trail = _truthy(ignoreTrailingWhiteSpace if ignoreTrailingWhiteSpace is not None else o.get("ignoreTrailingWhiteSpace", False))
         dev = torch.device("cuda", torch.cuda.current_device())
         engine = str(o.get("b200flow.csvEngine", "device")).lower()
+        import torch.distributed as tdist
+        from b200flow.dist import group, shard_bounds
+        shard = (tdist.get_rank(), tdist.get_world_size()) if group() is not None else None   # one process per GPU: a row block each
         if engine == "device":                                   # csrc/csv.cu: index, inference, dictionaries and parsing on the GPU
             from b200flow import csvio
             try:
-                rec, rschema, dicts = csvio.read_csv(paths, header, infer, lead, trail, dev)
+                rec, rschema, dicts = csvio.read_csv(paths, header, infer, lead, trail, dev, shard=shard)
             except csvio.CsvFormatError as e:
                 raise AnalysisException(str(e))
         elif engine == "host":                                   # explicit opt-in (quoted fields): pandas on the host, then one H2D copy
             rec, rschema, dicts = _read_csv(paths, header, infer, lead, trail, dev)
+            if shard is not None:
+                lo, hi = shard_bounds(rec.shape[0], *shard)
+                rec = rec[lo:hi].contiguous()
         else:
             raise ValueError("b200flow.csvEngine must be 'device' or 'host'")
         return DataFrame._from_records(rec, rschema, dicts, self._session)

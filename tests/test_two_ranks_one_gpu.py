@@ -61,6 +61,25 @@ def _worker(rank, world, port, out_dir):
             raw, prob, pred, lab = model.predict_records(shard, plan, want_label=True)
             cm = bdist.all_reduce_sum_(fr.confusion_matrix(pred, lab.to(torch.float64), C), grp)
             out[name]["cm"] = cm.cpu().numpy()
+        # spark.read.csv under one process per GPU: same schema and dictionary codes on every rank, a row block each
+        from b200flow import csvio
+        csv_path = os.path.join(out_dir, "flows.csv")
+        if rank == 0:
+            rng = np.random.default_rng(3)
+            with open(csv_path + ".tmp", "w") as f:
+                f.write("a,b,proto,c\n")
+                for i in range(5001):
+                    f.write("%d,%s,%s,%s\n" % (rng.integers(-9, 9), repr(float(rng.standard_normal())), ["tcp", "udp", "icmp", "gre"][int(rng.integers(0, 4)) if i > 2500 else 0],
+                                                "" if i % 97 == 0 else str(i)))
+            os.replace(csv_path + ".tmp", csv_path)
+        dist.barrier()
+        part, sch, dcts = csvio.read_csv([csv_path], header=True, infer_schema=True, shard=(rank, world))
+        np.save(os.path.join(out_dir, "csv_part%d.npy" % rank), part.cpu().numpy())
+        open(os.path.join(out_dir, "csv_meta%d.txt" % rank), "w").write(repr((sch.names, sch.types, dcts)))
+        if rank == 0:
+            whole, sch_w, dcts_w = csvio.read_csv([csv_path], header=True, infer_schema=True)
+            np.save(os.path.join(out_dir, "csv_whole.npy"), whole.cpu().numpy())
+            open(os.path.join(out_dir, "csv_meta_whole.txt"), "w").write(repr((sch_w.names, sch_w.types, dcts_w)))
         if rank == 0:
             for name, ex in out.items():
                 np.savez(os.path.join(out_dir, name + ".npz"), **ex)
@@ -106,3 +125,10 @@ def test_two_ranks_one_gpu_forest_equals_single_process(tmp_path):
         for k in single.files:
             assert np.array_equal(got[k], single[k]), "%s shards: %s" % (name, k)
     assert len(single["nid"]) > 300
+    # the CSV reader's row blocks: concatenated they are the whole file, with one schema and one dictionary (rank 1's block
+    # alone holds "udp" / "icmp" / "gre": the codes still come from the global order of first appearance)
+    parts = [np.load(tmp_path / ("csv_part%d.npy" % r)) for r in (0, 1)]
+    whole = np.load(tmp_path / "csv_whole.npy")
+    assert parts[0].shape[0] == 2500 and parts[1].shape[0] == 2501 and np.array_equal(np.concatenate(parts), whole)
+    metas = {open(tmp_path / n).read() for n in ("csv_meta0.txt", "csv_meta1.txt", "csv_meta_whole.txt")}
+    assert len(metas) == 1 and "'code'" in metas.pop()
