@@ -26,6 +26,15 @@ import math
 
 import torch
 
+from . import dist as bdist
+
+
+def _allsum(t, group):
+    """rows are sharded over ranks (one process per GPU): every statistic below is a sum over rows, reduced over the ranks, so
+    that each rank takes the same optimiser steps on the same numbers.  fp64 sums in rank order: equal on every rank; they differ
+    from the single-process value only by the association of the partial sums."""
+    return bdist.all_reduce_sum_(t, group) if group is not None else t
+
 
 class NaiveBayesFit:
     __slots__ = ("pi", "theta", "present")
@@ -34,15 +43,17 @@ class NaiveBayesFit:
         self.pi, self.theta, self.present = pi, theta, present
 
 
-def nb_fit(x, y, num_classes, smoothing=1.0):
-    """x [n, D] (any float dtype, >= 0), y [n] class indices -> NaiveBayesFit with pi [C], theta [C, D] (fp64)."""
+def nb_fit(x, y, num_classes, smoothing=1.0, group=None):
+    """x [n, D] (any float dtype, >= 0), y [n] class indices -> NaiveBayesFit with pi [C], theta [C, D] (fp64).
+    group: torch.distributed group over which the rows are sharded (None: single process)."""
     x = x.to(torch.float64)
-    if x.numel() and bool((x < 0).any().item()):
+    neg = _allsum((x < 0).any().to(torch.int64).reshape(1), group)
+    if int(neg.item()):
         raise ValueError("requirement failed: Naive Bayes requires nonnegative feature values but found a negative value.")
     C, D = int(num_classes), x.shape[1]
     yl = y.to(torch.int64)
-    n_c = torch.bincount(yl, minlength=C).to(torch.float64)
-    s = torch.zeros((C, D), dtype=torch.float64, device=x.device).index_add_(0, yl, x)
+    n_c = _allsum(torch.bincount(yl, minlength=C).to(torch.float64), group)
+    s = _allsum(torch.zeros((C, D), dtype=torch.float64, device=x.device).index_add_(0, yl, x), group)
     present = n_c > 0
     L = int(present.sum().item())
     lam = float(smoothing)
@@ -70,17 +81,21 @@ def _margins(xs, B, b, binomial):
     return torch.cat([torch.zeros_like(z), z], 1) if binomial else z
 
 
-def lr_loss_grad(xs, y1h, B, b, l2, binomial, fit_intercept=True):
-    """smooth part: mean multinomial log-loss + sum_j l2_j/2 |B_j|^2 (l2: scalar or one weight per feature) and its gradient."""
-    n = xs.shape[0]
+def lr_loss_grad(xs, y1h, B, b, l2, binomial, fit_intercept=True, n_total=None, group=None):
+    """smooth part: mean multinomial log-loss + sum_j l2_j/2 |B_j|^2 (l2: scalar or one weight per feature) and its gradient.
+    With a group: xs / y1h are this rank's rows, n_total the global row count; loss and gradient sums are all-reduced."""
+    n = xs.shape[0] if n_total is None else n_total
     z = _margins(xs, B, b, binomial)
     lse = torch.logsumexp(z, 1)
-    loss = (lse - (z * y1h).sum(1)).sum() / n + 0.5 * (l2 * B * B).sum()
-    R = (torch.softmax(z, 1) - y1h) / n                               # [n, C]
+    R = torch.softmax(z, 1) - y1h                                     # [n, C]
     if binomial:
         R = R[:, 1:]
-    gB = R.t() @ xs + l2 * B
-    gb = R.sum(0) if fit_intercept else torch.zeros_like(b)
+    packed = torch.cat([(lse - (z * y1h).sum(1)).sum().reshape(1), (R.t() @ xs).reshape(-1), R.sum(0)])
+    packed = _allsum(packed, group) / n
+    K, D = B.shape
+    loss = packed[0] + 0.5 * (l2 * B * B).sum()
+    gB = packed[1:1 + K * D].view(K, D) + l2 * B
+    gb = packed[1 + K * D:] if fit_intercept else torch.zeros_like(b)
     return loss, gB, gb
 
 
@@ -92,14 +107,22 @@ def _pseudo_gradient(x, g, c):
 
 
 def lr_fit(x, y, num_classes, max_iter=100, reg_param=0.0, elastic_net=0.0, tol=1e-6, fit_intercept=True, standardization=True,
-           family="auto", history=10):
+           family="auto", history=10, group=None):
     x = x.to(torch.float64)
-    n, D = x.shape
+    n_local, D = x.shape
     C = int(num_classes)
     binomial = family == "binomial" or (family == "auto" and C <= 2)
     if binomial and C > 2:
         raise ValueError("Binomial family only supports 1 or 2 outcome classes but found %d." % C)
-    std = x.std(0, unbiased=True) if n > 1 else torch.zeros(D, dtype=torch.float64, device=x.device)
+    if group is None:
+        n = n_local
+        std = x.std(0, unbiased=True) if n > 1 else torch.zeros(D, dtype=torch.float64, device=x.device)
+    else:                                                               # two passes over the shards: global mean, then squared deviations
+        head = _allsum(torch.cat([torch.tensor([float(n_local)], dtype=torch.float64, device=x.device), x.sum(0)]), group)
+        n = int(round(head[0].item()))
+        mean = head[1:] / max(n, 1)
+        ss = _allsum(((x - mean) ** 2).sum(0), group)
+        std = torch.sqrt(ss / (n - 1)) if n > 1 else torch.zeros(D, dtype=torch.float64, device=x.device)
     inv = torch.where(std > 0, 1.0 / std, torch.zeros_like(std))
     xs = x * inv                                                        # std 0 -> column of zeros -> coefficient stays 0
     yl = y.to(torch.int64)
@@ -110,7 +133,7 @@ def lr_fit(x, y, num_classes, max_iter=100, reg_param=0.0, elastic_net=0.0, tol=
     # standardization=False: MLlib still optimises in the scaled space but penalises the ORIGINAL-scale coefficients B / std
     l1w_row, l2w_row = (l1 * ones, l2 * ones) if standardization else (l1 * inv, l2 * inv * inv)
     K = 1 if binomial else C
-    counts = torch.bincount(yl, minlength=Cm).to(torch.float64)
+    counts = _allsum(torch.bincount(yl, minlength=Cm).to(torch.float64), group)
     B = torch.zeros((K, D), dtype=torch.float64, device=x.device)
     if not fit_intercept:
         b = torch.zeros(K, dtype=torch.float64, device=x.device)
@@ -126,7 +149,7 @@ def lr_fit(x, y, num_classes, max_iter=100, reg_param=0.0, elastic_net=0.0, tol=
 
     def smooth(v):
         Bv, bv = unpack(v)
-        f, gB, gb = lr_loss_grad(xs, y1h, Bv, bv, l2w_row, binomial, fit_intercept)
+        f, gB, gb = lr_loss_grad(xs, y1h, Bv, bv, l2w_row, binomial, fit_intercept, n, group)
         return f, torch.cat([gB.reshape(-1), gb])
 
     def full(v, f):

@@ -309,7 +309,7 @@ class LogisticRegression(Estimator):
         try:
             fit = _linear.lr_fit(x, y, C, max_iter=int(g("maxIter")), reg_param=float(g("regParam")), elastic_net=float(g("elasticNetParam")),
                                  tol=float(g("tol")), fit_intercept=bool(g("fitIntercept")), standardization=bool(g("standardization")),
-                                 family=g("family"))
+                                 family=g("family"), group=bdist.group())
         except ValueError as e:
             raise IllegalArgumentException(str(e))
         m = LogisticRegressionModel(fit, C)
@@ -356,7 +356,7 @@ class NaiveBayes(Estimator):
             raise IllegalArgumentException("only modelType='multinomial' is implemented")
         x, y, C, _ = _features_and_labels(df, self)
         try:
-            fit = _linear.nb_fit(x, y, C, float(self.getOrDefault("smoothing")))
+            fit = _linear.nb_fit(x, y, C, float(self.getOrDefault("smoothing")), group=bdist.group())
         except ValueError as e:
             raise IllegalArgumentException(str(e))
         m = NaiveBayesModel(fit, C)

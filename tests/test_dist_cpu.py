@@ -89,3 +89,40 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
     assert bdist.group() is None and bdist.global_offset(5, torch.device("cpu")) == (0, 5)
+
+
+def _linear_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from b200flow import linear
+        rng = np.random.default_rng(4)                       # same global data in every rank
+        n, D, C = 3001, 9, 4
+        y = rng.integers(0, C, n)
+        x = rng.poisson(rng.uniform(0.5, 5.0, size=(C, D))[y]).astype(np.float64)
+        x[:, 2] = 3.0
+        lo, hi = (0, 700) if rank == 0 else (700, n)         # uneven shards
+        xs, ys = torch.from_numpy(x[lo:hi]), torch.from_numpy(y[lo:hi])
+        nb = linear.nb_fit(xs, ys, C, 1.0, group=bdist.group())
+        lr = linear.lr_fit(xs, ys, C, max_iter=60, reg_param=0.1, elastic_net=0.5, tol=1e-12, family="multinomial", group=bdist.group())
+        np.savez(os.path.join(out_dir, "lin%d.npz" % rank), pi=nb.pi.numpy(), theta=nb.theta.numpy(), coef=lr.coef.numpy(), b=lr.intercept.numpy(),
+                 hist=np.array(lr.objective_history))
+        if rank == 0:
+            nb1 = linear.nb_fit(torch.from_numpy(x), torch.from_numpy(y), C, 1.0)
+            lr1 = linear.lr_fit(torch.from_numpy(x), torch.from_numpy(y), C, max_iter=60, reg_param=0.1, elastic_net=0.5, tol=1e-12, family="multinomial")
+            np.savez(os.path.join(out_dir, "lin_single.npz"), pi=nb1.pi.numpy(), theta=nb1.theta.numpy(), coef=lr1.coef.numpy(), b=lr1.intercept.numpy(),
+                     hist=np.array(lr1.objective_history))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_naive_bayes_and_logistic_regression_on_row_shards_gloo(tmp_path):
+    """SURVEY 8f-4 under one process per GPU: the sufficient statistics (NB) and the loss / gradient sums (LR) are all-reduced,
+    so every rank ends with the same model, equal to the single-process one up to the association of the fp64 partial sums."""
+    mp.start_processes(_linear_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    a, b, one = (np.load(tmp_path / f) for f in ("lin0.npz", "lin1.npz", "lin_single.npz"))
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k                                         # the ranks agree bit for bit
+    assert np.allclose(a["pi"], one["pi"], atol=1e-12) and np.allclose(a["theta"], one["theta"], atol=1e-12)
+    assert abs(a["hist"][-1] - one["hist"][-1]) < 1e-9
+    assert np.abs(a["coef"] - one["coef"]).max() < 1e-5 and np.abs(a["b"] - one["b"]).max() < 1e-5
