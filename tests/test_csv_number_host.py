@@ -162,3 +162,30 @@ def test_python_restatement_agrees_with_the_product_grammar(lib, tmp_path):
     assert types == ["i32", "f64", "code", "f64"]
     assert np.array_equal(cols["_c0"], pdf[0].to_numpy()) and np.array_equal(cols["_c1"], pdf[1].to_numpy())
     assert [dicts["_c2"][c] for c in cols["_c2"]] == list(pdf[2]) and np.array_equal(cols["_c3"], pdf[3].to_numpy(np.float64))
+
+
+def test_literals_next_to_rounding_boundaries(lib):
+    """The hardest inputs for a decimal -> double converter are literals a hair above or below the midpoint of two adjacent
+    doubles.  Built exactly with decimal arithmetic: midpoint, then cut or bumped at the 17th..19th significant digit."""
+    import decimal
+    import math
+    decimal.getcontext().prec = 60
+    rng = np.random.default_rng(21)
+    fields = []
+    for _ in range(30000):
+        d = float(rng.uniform(1, 10)) * 10.0 ** int(rng.integers(-8, 12))
+        mid = (decimal.Decimal(d) + decimal.Decimal(math.nextafter(d, math.inf))) / 2     # exact
+        digits = int(rng.integers(17, 20))
+        q = decimal.Decimal(1).scaleb(mid.adjusted() - digits + 1)
+        lo = mid.quantize(q, rounding=decimal.ROUND_FLOOR)
+        for v in (lo, lo + q):
+            s = format(v, "f") if rng.random() < 0.5 else format(v, "e")
+            fields.append(s)
+        if digits == 19 and rng.random() < 0.2:
+            fields.append(format(mid, "f"))                                              # the exact tie: > 19 digits, exact or refused
+    cls, st, val, _, _ = run(lib, fields)
+    want = np.array([float(f) for f in fields])
+    ok = st == OK
+    assert np.array_equal(bits(val[ok]), bits(want[ok])) and set(np.unique(st[~ok])) <= {UNSUPPORTED}
+    short = np.array([sum(ch.isdigit() for ch in f.split("e")[0].lstrip("0.")) <= 19 for f in fields])
+    assert ok[short].all()                                                              # <= 19 digits in range: always answered
