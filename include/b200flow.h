@@ -286,7 +286,8 @@ int b200flow_partition_level(const uint8_t* tp, int32_t tp_stride,
  * ceil(m / m_pass) feature passes over the entries, only the first of which routes — DecisionTree nodes, whose
  * histograms cover every feature), or returns 0 when even one feature's pair of child histograms does not fit
  * (then use partition_level followed by hist_level).
- * flags bit 0: route — write the kept entries to ent_out and count them in cursors; without it only the child
+ * flags bit 0: route — write the kept entries to ent_out and count them in cursors (8-byte aligned: a slot's pair is
+ * advanced by one 64-bit atomic); without it only the child
  * histograms are built (ent_out / cursors may be NULL): the level-0 pass, whose segments do not change, and the
  * pass that builds the deepest scored level, whose entries are never read again. */
 int b200flow_route_hist_config(int32_t F, int32_t m, int32_t n_bins, int32_t C, int32_t* chunk_rows, int32_t* m_pass);

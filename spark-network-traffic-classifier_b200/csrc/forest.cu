@@ -740,7 +740,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 4 : (NW == 16 ? 2 : 1)) rou
             __syncwarp();
             // reserve output positions (one atomic pair per warp step); the result is consumed one step later
             if (a.route && (nL | nR)) {
-                if (lane == 0) { p_bl = nL ? atomicAdd(&a.cursors[2 * s], nL) : 0; p_br = nR ? atomicAdd(&a.cursors[2 * s + 1], nR) : 0; }
+                if (lane == 0) {   // both cursors of the slot in ONE 64-bit atomic (left count in the low word): the top levels' few hundred cursors are hot
+                    const unsigned long long old = atomicAdd((unsigned long long*)(a.cursors + 2 * s), (unsigned long long)(uint32_t)nL | ((unsigned long long)(uint32_t)nR << 32));
+                    p_bl = (int)(uint32_t)old; p_br = (int)(uint32_t)(old >> 32);
+                }
 #pragma unroll
                 for (int k = 0; k < KS; ++k) p_e[k] = e[k];
                 p_dec = dec; p_sb = a.seg_begin[s]; p_se = a.seg_end[s];
@@ -992,7 +995,7 @@ extern "C" int b200flow_route_hist_level(const uint8_t* tp, int32_t tp_stride, i
     B2F_REQUIRE(tp && ent && seg_begin && seg_end && chunk_off && n_chunks_dev && split && child_slot && chunk_scratch &&
                     subset_next && hist_next, "route_hist_level: null pointer");
     const bool route = (flags & 1) != 0;
-    B2F_REQUIRE(!route || (ent_out && cursors), "route_hist_level: routing needs ent_out and cursors");
+    B2F_REQUIRE(!route || (ent_out && cursors && ((uintptr_t)cursors & 7) == 0), "route_hist_level: routing needs ent_out and 8-byte aligned cursors");
     B2F_REQUIRE((tp_stride & 15) == 0 && tp_stride >= (F + 1 + 15) / 16 * 16 && ((uintptr_t)tp & 15) == 0, "route_hist_level: bad TreePoint stride/alignment");
     B2F_REQUIRE(((uintptr_t)chunk_scratch & 15) == 0, "route_hist_level: chunk_scratch must be 16-byte aligned");
     RouteCfg cfg;
